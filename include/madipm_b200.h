@@ -1,0 +1,244 @@
+/*
+ * madipm_b200.h -- C ABI of libmadipm_b200.so, the B200 (sm_100a) backend for the
+ * per-iteration KKT hot path of MadIPM / MadQP.jl.
+ *
+ * This is what a Julia `ccall` (or any FFI) binds.  Plain pointers and sizes only.
+ * Index arrays that describe the problem are 1-based exactly as the Julia caller
+ * holds them (Int32 COO triplets, /root/reference/src/KKT/normalkkt.jl:51-77;
+ * Vector{Int} index sets, /root/reference/src/structure.jl:95-102); everything the
+ * library hands back through the symbolic getters is 0-based.
+ *
+ * Ownership: the caller owns every host array; the library copies during the call
+ * and never keeps a host pointer.  All device memory belongs to the handle.
+ * Threading: one handle = one CUDA stream = one caller thread; not re-entrant.
+ * Calls are stream-ordered; only calls that return scalars synchronise.
+ * Errors: no exceptions cross the boundary; every function returns a status code.
+ *
+ * There is no CPU fallback: numeric entry points return MADIPM_CUDA_ERROR when no
+ * sm_100-class device is present.  The symbolic entry points (set_pattern_*,
+ * analyze, the getters) are host code and work without a GPU.
+ */
+#ifndef MADIPM_B200_H
+#define MADIPM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct madipm_handle madipm_handle;
+
+/* ---- status codes (SURVEY.md 8b "Errors") ------------------------------------------ */
+enum {
+    MADIPM_OK = 0,
+    MADIPM_FACTOR_BREAKDOWN = 1, /* zero / non-finite pivot: feeds is_factorized(), /root/reference/src/utils.jl:54-62 */
+    MADIPM_NONFINITE = 2,        /* NaN in a solve residual: SolveException, /root/reference/src/linear_solver.jl:41-43 */
+    MADIPM_CUDA_ERROR = 3,       /* LinearSolverException on the Julia side, /root/reference/src/solver.jl:381-383 */
+    MADIPM_BAD_ARGUMENT = 4,
+    MADIPM_INTERNAL = 5
+};
+
+/* ---- configuration ------------------------------------------------------------------- */
+enum { MADIPM_KKT_K2 = 0, MADIPM_KKT_NORMAL = 1 };
+enum { MADIPM_ORDER_AMD = 0, MADIPM_ORDER_NATURAL = 1, MADIPM_ORDER_ND = 2 /* nested dissection, AMD leaves (default) */ };
+
+typedef struct {
+    int32_t kkt_kind;       /* MADIPM_KKT_K2: MadNLP.SparseKKTSystem (default, /root/reference/src/utils.jl:108);
+                               MADIPM_KKT_NORMAL: MadIPM.NormalKKTSystem (/root/reference/src/KKT/normalkkt.jl) */
+    int32_t ordering;
+    int32_t max_width;      /* supernode width cap */
+    int32_t relax_small;    /* relaxed amalgamation, see csrc/symbolic.hpp */
+    double relax_zeros[3];
+    int64_t subtree_work;   /* flop budget of one bottom subtree */
+    int32_t device;         /* CUDA device ordinal */
+    int32_t batch;          /* instances sharing one pattern (config C5); 1 for a single solve */
+    int32_t nd_leaf;        /* nested dissection leaf size, 0 = automatic */
+    int32_t reserved;
+} madipm_config;
+
+void madipm_default_config(madipm_config* cfg);
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+int32_t madipm_create(const madipm_config* cfg, madipm_handle** out);
+int32_t madipm_destroy(madipm_handle* h);
+const char* madipm_last_error(const madipm_handle* h);
+const char* madipm_version(void);
+
+/* ---- symbolic phase, once per pattern (replaces create_kkt_system + the linear-solver
+ *      constructor, /root/reference/src/KKT/normalkkt.jl:29-126) ------- */
+int32_t madipm_set_pattern_k2(madipm_handle* h, int32_t nvar, int32_t ncon,
+                              int64_t nnzh, const int32_t* hess_I, const int32_t* hess_J,
+                              int64_t nnzj, const int32_t* jac_I, const int32_t* jac_J,
+                              int32_t n_slack, const int64_t* ind_ineq);
+int32_t madipm_set_pattern_normal(madipm_handle* h, int32_t nvar, int32_t ncon,
+                                  int64_t nnzj, const int32_t* jac_I, const int32_t* jac_J,
+                                  int32_t n_slack, const int64_t* ind_ineq);
+/* ind_lb / ind_ub index into [x ; s] (/root/reference/src/structure.jl:144-151) */
+int32_t madipm_set_bounds_index(madipm_handle* h, int32_t nlb, const int64_t* ind_lb,
+                                int32_t nub, const int64_t* ind_ub);
+int32_t madipm_analyze(madipm_handle* h);
+
+typedef struct {
+    int32_t kkt_kind, nvar, n_slack, n_tot, ncon, nlb, nub, batch;
+    int32_t kkt_order;       /* N: order of the matrix that is factorised */
+    int64_t nnzh, nnzj;
+    int64_t kkt_nnz;         /* nnz of the lower-triangular CSC handed to the factorisation */
+    int64_t aug_coo_len;     /* K2: length of the augmented COO value array */
+    int64_t nnz_L;           /* exact nnz(L) */
+    int64_t nnz_stored;      /* doubles of supernodal panel storage */
+    double factor_flops;     /* sum_j colcount_j^2 */
+    int32_t nsuper, max_height, max_width;
+    int32_t n_subtrees, n_levels;
+    int64_t n_products;      /* normal equations: length of the product lists */
+    int64_t kkt_vec_len;     /* n_tot + ncon + nlb + nub: length of an UnreducedKKTVector */
+} madipm_info;
+int32_t madipm_get_info(const madipm_handle* h, madipm_info* out);
+
+/* integer results of the symbolic phase, copied to `out` (capacity `cap` entries);
+ * *len receives the length.  All 0-based. */
+enum {
+    MADIPM_SYM_PERM = 0,          /* perm[new] = old, length N */
+    MADIPM_SYM_ETREE_PARENT = 1,  /* parent in the permuted numbering, -1 root */
+    MADIPM_SYM_COLCOUNT = 2,
+    MADIPM_SYM_SUPER_FIRST = 3,   /* nsuper + 1 */
+    MADIPM_SYM_SUPER_PARENT = 4,
+    MADIPM_SYM_SUPER_ROWPTR = 5,  /* nsuper + 1 */
+    MADIPM_SYM_SUPER_ROWS = 6,
+    MADIPM_SYM_SUPER_XOFF = 7,    /* nsuper + 1 */
+    MADIPM_SYM_ASM_MAP = 8,       /* kkt_nnz: CSC nz -> panel slot */
+    MADIPM_SYM_KKT_COLPTR = 9,    /* N + 1 */
+    MADIPM_SYM_KKT_ROWVAL = 10,   /* kkt_nnz */
+    MADIPM_SYM_AUG_CSC_MAP = 11,  /* K2: aug COO entry -> CSC nz */
+    MADIPM_SYM_A_ROWPTR = 12,     /* CSR of A incl. slack columns */
+    MADIPM_SYM_A_COLIND = 13,
+    MADIPM_SYM_A_CSR_MAP = 14,    /* CSR slot -> COO index (0-based A_csr_map, normalkkt.jl:83-88) */
+    MADIPM_SYM_SUPER_LEVEL = 15,
+    MADIPM_SYM_PROD_PTR = 16,     /* normal equations product lists */
+    MADIPM_SYM_PROD_A = 17,
+    MADIPM_SYM_PROD_B = 18,
+    MADIPM_SYM_PROD_K = 19
+};
+int32_t madipm_get_symbolic(const madipm_handle* h, int32_t which, int64_t* out, int64_t cap, int64_t* len);
+
+/* ---- values, once per solve (eval_jac_wrapper! / eval_lag_hess_wrapper! +
+ *      compress_jacobian! / compress_hessian!, /root/reference/src/solver.jl:166-170,
+ *      /root/reference/src/KKT/normalkkt.jl:149-160).  Arrays are batch-major. ----------- */
+int32_t madipm_set_values(madipm_handle* h, const double* hess_V, const double* jac_V);
+
+/* ---- device vectors owned by the handle (MPCSolver fields, /root/reference/src/structure.jl:1-75,
+ *      and the KKT diagonals, /root/reference/src/KKT/normalkkt.jl:10-18) ------------------ */
+enum {
+    MADIPM_VEC_X = 0, MADIPM_VEC_XL, MADIPM_VEC_XU, MADIPM_VEC_ZL, MADIPM_VEC_ZU,   /* n_tot */
+    MADIPM_VEC_F, MADIPM_VEC_JACL, MADIPM_VEC_COST,                                 /* n_tot */
+    MADIPM_VEC_Y, MADIPM_VEC_C, MADIPM_VEC_RHS,                                     /* ncon */
+    MADIPM_VEC_D, MADIPM_VEC_P, MADIPM_VEC_W1, MADIPM_VEC_W2,                       /* kkt_vec_len */
+    MADIPM_VEC_CORR_LB, MADIPM_VEC_CORR_UB,                                         /* nlb, nub */
+    MADIPM_VEC_REG, MADIPM_VEC_PR_DIAG,                                             /* n_tot */
+    MADIPM_VEC_DU_DIAG,                                                             /* ncon */
+    MADIPM_VEC_L_DIAG, MADIPM_VEC_L_LOWER,                                          /* nlb */
+    MADIPM_VEC_U_DIAG, MADIPM_VEC_U_LOWER,                                          /* nub */
+    MADIPM_VEC_KKT_NZVAL,                                                           /* kkt_nnz (aug_com.nzval) */
+    MADIPM_VEC_COUNT
+};
+int32_t madipm_vec_len(const madipm_handle* h, int32_t vec, int64_t* len);     /* per instance */
+int32_t madipm_vec_set(madipm_handle* h, int32_t vec, const double* host);     /* batch * len doubles */
+int32_t madipm_vec_get(madipm_handle* h, int32_t vec, double* host);
+int32_t madipm_vec_fill(madipm_handle* h, int32_t vec, double value);
+int32_t madipm_vec_device_ptr(madipm_handle* h, int32_t vec, void** dev);      /* for zero-copy interop */
+int32_t madipm_synchronize(madipm_handle* h);
+void* madipm_stream(madipm_handle* h);                                         /* cudaStream_t */
+
+/* ---- AbstractKKTSystem / linear-solver operations --------------------------------------- */
+/* MadNLP.initialize!(kkt), /root/reference/src/KKT/normalkkt.jl:136-147 */
+int32_t madipm_kkt_initialize(madipm_handle* h);
+/* K1 set_aug_diagonal_reg!, /root/reference/src/kernels.jl:128-146 (one fused kernel) */
+int32_t madipm_set_aug_diagonal_reg(madipm_handle* h, double del_w, double del_c);
+/* solver.jl:16-18: reg = pr_diag = del_w, du_diag = del_c */
+int32_t madipm_set_initial_regularization(madipm_handle* h, double del_w, double del_c);
+/* K2a / K2b build_kkt!: K2 transfer! (/root/reference/scripts/cuda_wrapper.jl:17-28) or
+ * normal-equations assembly (/root/reference/src/utils.jl:266-298) into aug_com.nzval */
+int32_t madipm_build_kkt(madipm_handle* h);
+/* factorize!: supernodal LDL' (K2) / Cholesky-as-LDL' (normal).  *n_failed = instances whose
+ * factorisation broke down; status MADIPM_FACTOR_BREAKDOWN when > 0. Synchronises. */
+int32_t madipm_factorize(madipm_handle* h, int32_t* n_failed);
+/* is_factorized per instance (0/1), /root/reference/src/utils.jl:54-62 */
+int32_t madipm_is_factorized(madipm_handle* h, int32_t* flags);
+/* inertia of the last factorisation of instance `inst`: signs of D */
+int32_t madipm_inertia(madipm_handle* h, int32_t inst, int64_t* n_pos, int64_t* n_zero, int64_t* n_neg);
+/* solve!(linear_solver, rhs): in-place solve with the current factors on a device vector of
+ * length N per instance (pointer obtained from madipm_vec_device_ptr + offset) */
+int32_t madipm_linear_solve(madipm_handle* h, double* dev_rhs, int64_t stride);
+/* K4 / K4' MadNLP.solve!(kkt, w) on a KKT vector (reduce_rhs!, solve, finish_aug_solve!),
+ * /root/reference/src/KKT/normalkkt.jl:182-205 */
+int32_t madipm_kkt_solve(madipm_handle* h, int32_t vec_w);
+/* K5 mul!(w, kkt, v, alpha, beta), /root/reference/src/KKT/normalkkt.jl:207-219 */
+int32_t madipm_kkt_mul(madipm_handle* h, int32_t vec_w, int32_t vec_v, double alpha, double beta);
+/* K6 solve_system!(d, solver, p), /root/reference/src/linear_solver.jl:19-45.
+ * norms[3 * inst + {0,1,2}] = ||p - K d||inf, ||p||inf, ||d||inf.  Synchronises.
+ * Returns MADIPM_NONFINITE if any residual ratio is NaN. */
+int32_t madipm_solve_system(madipm_handle* h, int32_t vec_d, int32_t vec_p, double* norms);
+/* K7 jtprod!: out(n_tot) = A' * in(ncon); and the model products of K8 */
+enum { MADIPM_OP_A = 0, MADIPM_OP_AT = 1, MADIPM_OP_Q = 2 };
+int32_t madipm_spmv(madipm_handle* h, int32_t op, int32_t vec_out, int32_t vec_in);
+/* same on raw device pointers (per-instance strides in doubles) */
+int32_t madipm_spmv_ptr(madipm_handle* h, int32_t op, double* dev_out, int64_t stride_out,
+                        const double* dev_in, int64_t stride_in);
+
+/* ---- fused phases of mpc!.  Scalars come back per instance. ------------ */
+/* K8: f = Qx + cost, c = A x - s - rhs, obj = c0 + cost'x + x'Qx/2  (solver.jl:338-340).
+ * obj[inst]; does not synchronise unless obj != NULL. */
+int32_t madipm_eval_model(madipm_handle* h, double c0, double* obj);
+/* K7 + K15: jacl = A'y, then out[4*inst + ..] = { ||c||inf, ||f - zl + zu + jacl||inf,
+ * max complementarity (mu = 0), ||dx||inf }   (solver.jl:259-274) */
+int32_t madipm_phase_residuals(madipm_handle* h, double* out);
+/* K9 set_initial_primal_rhs! / set_initial_dual_rhs! (kernels.jl:1-19) */
+int32_t madipm_set_initial_primal_rhs(madipm_handle* h);
+int32_t madipm_set_initial_dual_rhs(madipm_handle* h);
+/* K9 set_predictive_rhs! (kernels.jl:21-41) */
+int32_t madipm_set_predictive_rhs(madipm_handle* h);
+/* K9 set_correction_rhs! (kernels.jl:43-61); mu per instance */
+int32_t madipm_set_correction_rhs(madipm_handle* h, const double* mu);
+/* K12 get_fraction_to_boundary_step (kernels.jl:242-305): out[8*inst + ..] =
+ * { alpha_xl, alpha_xu, alpha_zl, alpha_zu, idx_xl, idx_xu, idx_zl, idx_zu } (indices 1-based, 0 = none) */
+int32_t madipm_ratio_test(madipm_handle* h, const double* tau, double* out);
+/* K11 get_complementarity_measure / get_affine_complementarity_measure (kernels.jl:171-224);
+ * alpha_p / alpha_d per instance (NULL = 0: current complementarity) */
+int32_t madipm_complementarity(madipm_handle* h, const double* alpha_p, const double* alpha_d, double* out);
+/* K12 + K11 + K10 fused, the predictor bookkeeping of mpc! (solver.jl:295-297):
+ * ratio test with tau = 1, affine complementarity at those steps, corrections, current mu.
+ * out[4*inst + ..] = { alpha_aff_p, alpha_aff_d, mu_affine, mu_curr } */
+int32_t madipm_phase_affine(madipm_handle* h, double* out);
+/* K10 get_correction! (kernels.jl:63-75) and Gondzio's set_extra_correction! (kernels.jl:78-126) */
+int32_t madipm_get_correction(madipm_handle* h);
+int32_t madipm_set_extra_correction(madipm_handle* h, const double* alpha_p, const double* alpha_d,
+                                    double beta_min, double beta_max, const double* mu);
+/* K14 iterate update + adjust_boundary! (solver.jl:332-335, 342); `active` (NULL = all) masks
+ * finished instances of a batch */
+int32_t madipm_update_iterate(madipm_handle* h, const double* alpha_p, const double* alpha_d,
+                              const double* mu, const int32_t* active);
+/* MehrotraAdaptiveStep gathers (kernels.jl:351-368) without scalar device reads:
+ * out[inst*2 + ..] = { alpha_p, alpha_d } for gamma_f */
+int32_t madipm_mehrotra_step(madipm_handle* h, double gamma_f, double* out);
+/* starting point, solver.jl:35-118 (steps 3 onwards, after the two least-squares solves) */
+int32_t madipm_init_multipliers_and_shift(madipm_handle* h, double bound_fac);
+/* vector helpers the control loop uses directly */
+int32_t madipm_vec_copy(madipm_handle* h, int32_t dst, int32_t src);
+/* dst[0:len) += alpha * src[off_src : off_src+len) at offset off_dst (axpy on sub-ranges) */
+int32_t madipm_vec_axpy(madipm_handle* h, int32_t dst, int64_t off_dst, int32_t src, int64_t off_src,
+                        int64_t len, double alpha);
+int32_t madipm_vec_norm_inf(madipm_handle* h, int32_t vec, double* out);
+
+/* ---- measurement hooks -------------------------------------------------------------------- */
+/* number of kernel launches issued by this handle since creation */
+int64_t madipm_launch_count(const madipm_handle* h);
+/* accumulated device milliseconds per kernel class since the last reset (CUDA events on the
+ * handle's stream; enabled by madipm_profile(h, 1)) */
+enum { MADIPM_T_ASSEMBLY = 0, MADIPM_T_FACTOR, MADIPM_T_SOLVE, MADIPM_T_SPMV, MADIPM_T_VECTOR, MADIPM_T_COUNT };
+int32_t madipm_profile(madipm_handle* h, int32_t enable);
+int32_t madipm_profile_read(madipm_handle* h, double* ms, int64_t* calls, int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MADIPM_B200_H */
