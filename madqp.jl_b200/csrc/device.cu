@@ -1,0 +1,955 @@
+// Device half of the C ABI: device state, uploads and every numeric entry point.
+// One handle = one CUDA stream; all work is stream-ordered; entry points that return
+// scalars synchronise, the others do not.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "handle.hpp"
+#include "kernels_factor.cuh"
+#include "kernels_vec.cuh"
+
+namespace madipm {
+
+struct DeviceState {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int B = 1;
+    int n = 0, m = 0, nlb = 0, nub = 0, N = 0, kind = 0;
+    int64_t L = 0;
+    int64_t nnzA = 0, nnzQ = 0, nnzh = 0, nnzj = 0, nnzJfull = 0, kkt_nnz = 0, lx_stride = 0;
+    int nsuper = 0, n_subtrees = 0, n_levels = 0, h_cap = 0;
+    size_t factor_smem = 0;
+    std::vector<int> level_ptr;
+
+    std::vector<void*> allocs;
+
+    int *ind_lb = nullptr, *ind_ub = nullptr, *lb_of = nullptr, *ub_of = nullptr;
+    int *A_rp = nullptr, *A_ci = nullptr, *AT_rp = nullptr, *AT_ci = nullptr, *Q_rp = nullptr, *Q_ci = nullptr;
+    int *A_order = nullptr, *AT_src = nullptr, *Q_src = nullptr;
+    double *A_val = nullptr, *AT_val = nullptr, *Q_val = nullptr, *hessV = nullptr, *jacV = nullptr;
+    int *aug_map = nullptr, *diag_slot = nullptr;
+    double* const_diag = nullptr;
+    int64_t* prod_ptr = nullptr;
+    int *prod_a = nullptr, *prod_b = nullptr, *prod_k = nullptr;
+
+    int *sn_first = nullptr, *sn_rows = nullptr, *sn_of = nullptr;
+    int64_t *sn_rowptr = nullptr, *sn_xoff = nullptr, *asm_map = nullptr, *diag_pos = nullptr;
+    double *Lx = nullptr, *xw = nullptr;
+    int *perm = nullptr, *iperm = nullptr, *sub_first = nullptr, *sub_last = nullptr, *level_sn = nullptr;
+    int* fail = nullptr;
+    std::vector<int> h_fail;
+
+    double* vec[MADIPM_VEC_COUNT] = {};
+    int64_t veclen[MADIPM_VEC_COUNT] = {};
+    double *buffer_n = nullptr, *buffer_m = nullptr;
+
+    double* red_scratch = nullptr;
+    unsigned int* red_counter = nullptr;
+    double *d_out = nullptr, *d_out2 = nullptr, *d_steps = nullptr, *d_mu = nullptr, *d_tau = nullptr, *d_ones = nullptr;
+    int* d_active = nullptr;
+    unsigned long long* d_inertia = nullptr;
+    double* h_out = nullptr;   // pinned
+
+    bool values_set = false;
+    bool profiling = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double t_ms[MADIPM_T_COUNT] = {};
+    int64_t t_calls[MADIPM_T_COUNT] = {};
+};
+
+namespace {
+
+#define CUDA_OK(h, call)                                                                   \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            (h)->error = std::string(#call) + ": " + cudaGetErrorString(e_);               \
+            return MADIPM_CUDA_ERROR;                                                      \
+        }                                                                                  \
+    } while (0)
+
+#define LAUNCH(h, kernel, grid, block, smem, ...)                                          \
+    do {                                                                                   \
+        kernel<<<grid, block, smem, (h)->dev->stream>>>(__VA_ARGS__);                      \
+        ++(h)->launches;                                                                   \
+    } while (0)
+
+template <class T>
+int32_t dev_alloc(madipm_handle* h, T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    void* q = nullptr;
+    CUDA_OK(h, cudaMalloc(&q, count * sizeof(T)));
+    h->dev->allocs.push_back(q);
+    *p = static_cast<T*>(q);
+    return MADIPM_OK;
+}
+
+template <class T, class S>
+int32_t upload_as(madipm_handle* h, T** p, const std::vector<S>& v) {
+    std::vector<T> tmp(v.size());
+    for (size_t i = 0; i < v.size(); ++i) tmp[i] = static_cast<T>(v[i]);
+    int32_t rc = dev_alloc(h, p, tmp.size());
+    if (rc) return rc;
+    if (!tmp.empty()) CUDA_OK(h, cudaMemcpy(*p, tmp.data(), tmp.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return MADIPM_OK;
+}
+
+inline int vec_blocks(int64_t n) {
+    int64_t b = (n + kVecThreads - 1) / kVecThreads;
+    return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(b, kMaxRedBlocks)));
+}
+
+VecView make_view(const DeviceState& d) {
+    VecView V;
+    V.n = d.n; V.m = d.m; V.nlb = d.nlb; V.nub = d.nub;
+    V.ind_lb = d.ind_lb; V.ind_ub = d.ind_ub; V.lb_of = d.lb_of; V.ub_of = d.ub_of;
+    V.x = d.vec[MADIPM_VEC_X]; V.xl = d.vec[MADIPM_VEC_XL]; V.xu = d.vec[MADIPM_VEC_XU];
+    V.zl = d.vec[MADIPM_VEC_ZL]; V.zu = d.vec[MADIPM_VEC_ZU]; V.f = d.vec[MADIPM_VEC_F];
+    V.jacl = d.vec[MADIPM_VEC_JACL]; V.cost = d.vec[MADIPM_VEC_COST];
+    V.y = d.vec[MADIPM_VEC_Y]; V.c = d.vec[MADIPM_VEC_C]; V.rhs = d.vec[MADIPM_VEC_RHS];
+    V.reg = d.vec[MADIPM_VEC_REG]; V.pr_diag = d.vec[MADIPM_VEC_PR_DIAG]; V.du_diag = d.vec[MADIPM_VEC_DU_DIAG];
+    V.l_diag = d.vec[MADIPM_VEC_L_DIAG]; V.l_lower = d.vec[MADIPM_VEC_L_LOWER];
+    V.u_diag = d.vec[MADIPM_VEC_U_DIAG]; V.u_lower = d.vec[MADIPM_VEC_U_LOWER];
+    V.corr_lb = d.vec[MADIPM_VEC_CORR_LB]; V.corr_ub = d.vec[MADIPM_VEC_CORR_UB];
+    V.sn = d.n; V.sm = d.m; V.slb = d.nlb; V.sub = d.nub; V.sL = d.L;
+    return V;
+}
+
+FactorView make_factor_view(const DeviceState& d) {
+    FactorView F;
+    F.sn_first = d.sn_first; F.sn_rowptr = d.sn_rowptr; F.sn_rows = d.sn_rows; F.sn_xoff = d.sn_xoff;
+    F.sn_of = d.sn_of; F.Lx = d.Lx; F.lx_stride = d.lx_stride; F.fail = d.fail; F.h_cap = d.h_cap;
+    return F;
+}
+
+struct Timer {
+    madipm_handle* h;
+    int cls;
+    Timer(madipm_handle* hh, int c) : h(hh), cls(c) {
+        if (h->dev->profiling) cudaEventRecord(h->dev->ev0, h->dev->stream);
+    }
+    ~Timer() {
+        DeviceState* d = h->dev;
+        if (d->profiling) {
+            cudaEventRecord(d->ev1, d->stream);
+            cudaEventSynchronize(d->ev1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, d->ev0, d->ev1);
+            d->t_ms[cls] += ms;
+            d->t_calls[cls] += 1;
+        }
+    }
+};
+
+int32_t fetch(madipm_handle* h, const double* dsrc, double* hdst, size_t count) {
+    DeviceState* d = h->dev;
+    CUDA_OK(h, cudaMemcpyAsync(d->h_out, dsrc, count * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+    CUDA_OK(h, cudaStreamSynchronize(d->stream));
+    CUDA_OK(h, cudaGetLastError());
+    std::memcpy(hdst, d->h_out, count * sizeof(double));
+    return MADIPM_OK;
+}
+
+int32_t spmv_launch(madipm_handle* h, int rows, int64_t nnz, const int* rp, const int* ci, const double* val,
+                    int64_t val_stride, const double* x, int64_t xs, double* y, int64_t ys, double alpha, double beta) {
+    DeviceState* d = h->dev;
+    if (rows <= 0) return MADIPM_OK;
+    const double avg = static_cast<double>(nnz) / rows;
+    dim3 grid(1, d->B);
+    auto blocks = [&](int lanes) {
+        int64_t rpb = kVecThreads / lanes;
+        return static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((rows + rpb - 1) / rpb, 148 * 16)));
+    };
+    if (avg <= 2.5) { grid.x = blocks(2); LAUNCH(h, k_spmv<2>, grid, kVecThreads, 0, rows, rp, ci, val, val_stride, x, xs, y, ys, alpha, beta); }
+    else if (avg <= 6.0) { grid.x = blocks(4); LAUNCH(h, k_spmv<4>, grid, kVecThreads, 0, rows, rp, ci, val, val_stride, x, xs, y, ys, alpha, beta); }
+    else if (avg <= 12.0) { grid.x = blocks(8); LAUNCH(h, k_spmv<8>, grid, kVecThreads, 0, rows, rp, ci, val, val_stride, x, xs, y, ys, alpha, beta); }
+    else if (avg <= 24.0) { grid.x = blocks(16); LAUNCH(h, k_spmv<16>, grid, kVecThreads, 0, rows, rp, ci, val, val_stride, x, xs, y, ys, alpha, beta); }
+    else { grid.x = blocks(32); LAUNCH(h, k_spmv<32>, grid, kVecThreads, 0, rows, rp, ci, val, val_stride, x, xs, y, ys, alpha, beta); }
+    return MADIPM_OK;
+}
+
+__global__ void k_scatter_add(int64_t n, const int* __restrict__ map, const double* __restrict__ src, int64_t sstride,
+                              double* __restrict__ dst, int64_t dstride) {
+    src += blockIdx.y * sstride;
+    dst += blockIdx.y * dstride;
+    for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < n;
+         k += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        atomicAdd(&dst[map[k]], src[k]);
+}
+
+// K2a: only the diagonal slots of aug_com.nzval change between iterations
+// (transfer! semantics, /root/reference/scripts/cuda_wrapper.jl:17-28, restricted to the entries that moved)
+__global__ void k_build_kkt_k2(int n, int m, const int* __restrict__ diag_slot, const double* __restrict__ const_diag,
+                               const double* __restrict__ pr_diag, const double* __restrict__ du_diag,
+                               double* __restrict__ nzval, int64_t nz_stride) {
+    const int inst = blockIdx.y;
+    const_diag += static_cast<int64_t>(inst) * (n + m);
+    pr_diag += static_cast<int64_t>(inst) * n;
+    du_diag += static_cast<int64_t>(inst) * m;
+    nzval += inst * nz_stride;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n + m; i += gridDim.x * blockDim.x) {
+        const double v = (i < n) ? pr_diag[i] : du_diag[i - n];
+        nzval[diag_slot[i]] = v + const_diag[i];
+    }
+}
+
+__global__ void k_extract_diag(int N, const int* __restrict__ diag_slot, const double* __restrict__ nzval,
+                               int64_t nz_stride, double* __restrict__ const_diag) {
+    nzval += blockIdx.y * nz_stride;
+    const_diag += static_cast<int64_t>(blockIdx.y) * N;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x)
+        const_diag[i] = nzval[diag_slot[i]];
+}
+
+__global__ void k_perm_gather(int N, const int* __restrict__ perm, const double* __restrict__ src, int64_t sstride,
+                              double* __restrict__ dst, int64_t dstride) {
+    src += blockIdx.y * sstride;
+    dst += blockIdx.y * dstride;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += gridDim.x * blockDim.x) dst[k] = src[perm[k]];
+}
+
+__global__ void k_perm_scatter(int N, const int* __restrict__ perm, const double* __restrict__ src, int64_t sstride,
+                               double* __restrict__ dst, int64_t dstride) {
+    src += blockIdx.y * sstride;
+    dst += blockIdx.y * dstride;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += gridDim.x * blockDim.x) dst[perm[k]] = src[k];
+}
+
+int32_t check(madipm_handle* h, bool need_values = false) {
+    if (!h) return MADIPM_BAD_ARGUMENT;
+    if (!h->analyzed) { h->error = "numeric call before analyze"; return MADIPM_BAD_ARGUMENT; }
+    if (!h->dev) {
+        int32_t rc = device_create(h);
+        if (rc) { device_destroy(h); return rc; }
+    }
+    if (need_values && !h->dev->values_set) { h->error = "numeric call before set_values"; return MADIPM_BAD_ARGUMENT; }
+    cudaSetDevice(h->dev->device);
+    return MADIPM_OK;
+}
+
+int32_t tri_solve(madipm_handle* h) {
+    DeviceState* d = h->dev;
+    FactorView F = make_factor_view(*d);
+    const int T = 128;
+    if (d->n_subtrees > 0)
+        LAUNCH(h, k_forward_subtrees, dim3(d->n_subtrees, d->B), T, 0, F, d->xw, (int64_t)d->N, d->sub_first, d->sub_last);
+    for (int l = 0; l < d->n_levels; ++l) {
+        int cnt = d->level_ptr[l + 1] - d->level_ptr[l];
+        LAUNCH(h, k_forward_level, dim3(cnt, d->B), T, 0, F, d->xw, (int64_t)d->N, d->level_sn + d->level_ptr[l]);
+    }
+    for (int l = d->n_levels - 1; l >= 0; --l) {
+        int cnt = d->level_ptr[l + 1] - d->level_ptr[l];
+        LAUNCH(h, k_backward_level, dim3(cnt, d->B), T, 0, F, d->xw, (int64_t)d->N, d->level_sn + d->level_ptr[l]);
+    }
+    if (d->n_subtrees > 0)
+        LAUNCH(h, k_backward_subtrees, dim3(d->n_subtrees, d->B), T, 0, F, d->xw, (int64_t)d->N, d->sub_first, d->sub_last);
+    return MADIPM_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+int32_t device_create(madipm_handle* h) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        h->error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)";
+        return MADIPM_CUDA_ERROR;
+    }
+    if (h->cfg.device < 0 || h->cfg.device >= count) { h->error = "bad device ordinal"; return MADIPM_BAD_ARGUMENT; }
+    CUDA_OK(h, cudaSetDevice(h->cfg.device));
+    cudaDeviceProp prop;
+    CUDA_OK(h, cudaGetDeviceProperties(&prop, h->cfg.device));
+    if (prop.major < 10) { h->error = "device is not sm_100-class; this library targets B200 only"; return MADIPM_CUDA_ERROR; }
+
+    DeviceState* d = new DeviceState();
+    h->dev = d;
+    d->device = h->cfg.device;
+    CUDA_OK(h, cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    CUDA_OK(h, cudaEventCreate(&d->ev0));
+    CUDA_OK(h, cudaEventCreate(&d->ev1));
+    const KktPattern& p = h->pat;
+    const Symbolic& s = h->sym;
+    if (p.A_rowptr.back() > INT32_MAX || p.kkt_colptr.back() > INT32_MAX || (int64_t)s.sn_rows.size() > INT32_MAX ||
+        (int64_t)p.prod_a.size() > INT32_MAX) {
+        h->error = "pattern too large for 32-bit device indices";
+        return MADIPM_BAD_ARGUMENT;
+    }
+    d->B = h->cfg.batch;
+    d->n = p.n_tot; d->m = p.m; d->nlb = h->nlb; d->nub = h->nub; d->N = p.N; d->kind = p.kind;
+    d->L = static_cast<int64_t>(p.n_tot) + p.m + h->nlb + h->nub;
+    d->nnzA = p.A_rowptr.back(); d->nnzQ = p.Q_rowptr.empty() ? 0 : p.Q_rowptr.back();
+    d->nnzh = p.nnzh; d->nnzj = p.nnzj; d->nnzJfull = p.nnzj + p.n_slack;
+    d->kkt_nnz = p.kkt_colptr.back();
+    d->lx_stride = s.nnz_stored;
+    d->nsuper = s.nsuper; d->n_subtrees = s.n_subtrees; d->n_levels = s.n_levels;
+    d->level_ptr.assign(s.level_ptr.begin(), s.level_ptr.end());
+    const int B = d->B;
+    int32_t rc;
+#define UP(T, dst, src) if ((rc = upload_as<T>(h, &d->dst, src))) return rc
+    // index sets and inverse maps
+    std::vector<int> lb_of(d->n, -1), ub_of(d->n, -1);
+    for (int k = 0; k < h->nlb; ++k) lb_of[h->ind_lb[k]] = k;
+    for (int k = 0; k < h->nub; ++k) ub_of[h->ind_ub[k]] = k;
+    UP(int, ind_lb, h->ind_lb); UP(int, ind_ub, h->ind_ub); UP(int, lb_of, lb_of); UP(int, ub_of, ub_of);
+    // operators
+    UP(int, A_rp, p.A_rowptr); UP(int, A_ci, p.A_colind); UP(int, A_order, p.A_csr_order);
+    UP(int, AT_rp, p.AT_rowptr); UP(int, AT_ci, p.AT_colind); UP(int, AT_src, p.AT_src);
+    std::vector<int64_t> qrp = p.Q_rowptr;
+    if (qrp.empty()) qrp.assign(static_cast<size_t>(d->n) + 1, 0);
+    UP(int, Q_rp, qrp); UP(int, Q_ci, p.Q_colind); UP(int, Q_src, p.Q_src);
+    if ((rc = dev_alloc(h, &d->A_val, B * d->nnzA))) return rc;
+    if ((rc = dev_alloc(h, &d->AT_val, B * d->nnzA))) return rc;
+    if ((rc = dev_alloc(h, &d->Q_val, B * d->nnzQ))) return rc;
+    if ((rc = dev_alloc(h, &d->hessV, B * d->nnzh))) return rc;
+    if ((rc = dev_alloc(h, &d->jacV, B * d->nnzJfull))) return rc;
+    // KKT matrix
+    if (p.kind == 0) {
+        UP(int, aug_map, p.aug_csc_map); UP(int, diag_slot, p.diag_slot);
+        if ((rc = dev_alloc(h, &d->const_diag, static_cast<size_t>(B) * d->N))) return rc;
+    } else {
+        UP(int64_t, prod_ptr, p.prod_ptr); UP(int, prod_a, p.prod_a); UP(int, prod_b, p.prod_b); UP(int, prod_k, p.prod_k);
+    }
+    // factor structure
+    UP(int, sn_first, s.sn_first); UP(int64_t, sn_rowptr, s.sn_rowptr); UP(int, sn_rows, s.sn_rows);
+    UP(int64_t, sn_xoff, s.sn_xoff); UP(int, sn_of, s.sn_of); UP(int64_t, asm_map, s.asm_map);
+    UP(int, perm, s.perm); UP(int, iperm, s.iperm);
+    UP(int, sub_first, s.subtree_first); UP(int, sub_last, s.subtree_last); UP(int, level_sn, s.level_sn);
+    std::vector<int64_t> diag_pos(d->N);
+    for (int sn = 0; sn < s.nsuper; ++sn) {
+        int64_t hs = s.sn_rowptr[sn + 1] - s.sn_rowptr[sn];
+        for (int j = s.sn_first[sn]; j < s.sn_first[sn + 1]; ++j)
+            diag_pos[j] = s.sn_xoff[sn] + static_cast<int64_t>(j - s.sn_first[sn]) * (hs + 1);
+    }
+    UP(int64_t, diag_pos, diag_pos);
+#undef UP
+    if ((rc = dev_alloc(h, &d->Lx, static_cast<size_t>(B) * d->lx_stride))) return rc;
+    if ((rc = dev_alloc(h, &d->xw, static_cast<size_t>(B) * d->N))) return rc;
+    if ((rc = dev_alloc(h, &d->fail, B))) return rc;
+    d->h_fail.assign(B, 0);
+    d->h_cap = std::max(64, s.max_h);
+    d->factor_smem = static_cast<size_t>(d->h_cap) * 12 + 256 * 8;
+    if (d->factor_smem > 200 * 1024) {
+        h->error = "supernode height " + std::to_string(s.max_h) + " exceeds the single-block factor path";
+        return MADIPM_INTERNAL;
+    }
+    CUDA_OK(h, cudaFuncSetAttribute(k_factor_subtrees, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->factor_smem));
+    CUDA_OK(h, cudaFuncSetAttribute(k_factor_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->factor_smem));
+
+    // vectors
+    const int64_t n = d->n, m = d->m;
+    int64_t* vl = d->veclen;
+    for (int v : {MADIPM_VEC_X, MADIPM_VEC_XL, MADIPM_VEC_XU, MADIPM_VEC_ZL, MADIPM_VEC_ZU, MADIPM_VEC_F, MADIPM_VEC_JACL,
+                  MADIPM_VEC_COST, MADIPM_VEC_REG, MADIPM_VEC_PR_DIAG}) vl[v] = n;
+    for (int v : {MADIPM_VEC_Y, MADIPM_VEC_C, MADIPM_VEC_RHS, MADIPM_VEC_DU_DIAG}) vl[v] = m;
+    for (int v : {MADIPM_VEC_D, MADIPM_VEC_P, MADIPM_VEC_W1, MADIPM_VEC_W2}) vl[v] = d->L;
+    vl[MADIPM_VEC_CORR_LB] = vl[MADIPM_VEC_L_DIAG] = vl[MADIPM_VEC_L_LOWER] = d->nlb;
+    vl[MADIPM_VEC_CORR_UB] = vl[MADIPM_VEC_U_DIAG] = vl[MADIPM_VEC_U_LOWER] = d->nub;
+    vl[MADIPM_VEC_KKT_NZVAL] = d->kkt_nnz;
+    for (int v = 0; v < MADIPM_VEC_COUNT; ++v) {
+        if ((rc = dev_alloc(h, &d->vec[v], static_cast<size_t>(B) * vl[v]))) return rc;
+        CUDA_OK(h, cudaMemsetAsync(d->vec[v], 0, static_cast<size_t>(B) * std::max<int64_t>(vl[v], 1) * sizeof(double), d->stream));
+    }
+    if ((rc = dev_alloc(h, &d->buffer_n, static_cast<size_t>(B) * n))) return rc;
+    if ((rc = dev_alloc(h, &d->buffer_m, static_cast<size_t>(B) * m))) return rc;
+    // reductions
+    if ((rc = dev_alloc(h, &d->red_scratch, static_cast<size_t>(B) * kMaxRedBlocks * 8))) return rc;
+    if ((rc = dev_alloc(h, &d->red_counter, B))) return rc;
+    CUDA_OK(h, cudaMemsetAsync(d->red_counter, 0, B * sizeof(unsigned int), d->stream));
+    if ((rc = dev_alloc(h, &d->d_out, static_cast<size_t>(B) * 16))) return rc;
+    if ((rc = dev_alloc(h, &d->d_out2, static_cast<size_t>(B) * 16))) return rc;
+    if ((rc = dev_alloc(h, &d->d_steps, static_cast<size_t>(B) * 2))) return rc;
+    if ((rc = dev_alloc(h, &d->d_mu, B))) return rc;
+    if ((rc = dev_alloc(h, &d->d_tau, B))) return rc;
+    if ((rc = dev_alloc(h, &d->d_ones, B))) return rc;
+    if ((rc = dev_alloc(h, &d->d_active, B))) return rc;
+    if ((rc = dev_alloc(h, &d->d_inertia, static_cast<size_t>(B) * 3))) return rc;
+    LAUNCH(h, k_fill, dim3(1, 1), 256, 0, (int64_t)B, d->d_ones, (int64_t)0, 1.0);
+    CUDA_OK(h, cudaMallocHost(reinterpret_cast<void**>(&d->h_out), static_cast<size_t>(B) * 32 * sizeof(double)));
+    CUDA_OK(h, cudaStreamSynchronize(d->stream));
+    return MADIPM_OK;
+}
+
+void device_destroy(madipm_handle* h) {
+    DeviceState* d = h->dev;
+    if (!d) return;
+    cudaSetDevice(d->device);
+    if (d->stream) cudaStreamSynchronize(d->stream);
+    for (void* p : d->allocs) cudaFree(p);
+    if (d->h_out) cudaFreeHost(d->h_out);
+    if (d->ev0) cudaEventDestroy(d->ev0);
+    if (d->ev1) cudaEventDestroy(d->ev1);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    delete d;
+    h->dev = nullptr;
+}
+
+}  // namespace madipm
+
+using namespace madipm;
+
+extern "C" {
+
+// ---- values -----------------------------------------------------------------------------------
+int32_t madipm_set_values(madipm_handle* h, const double* hess_V, const double* jac_V) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    const int B = d->B;
+    if ((d->nnzh > 0 && !hess_V) || (d->nnzj > 0 && !jac_V)) return MADIPM_BAD_ARGUMENT;
+    Timer t(h, MADIPM_T_ASSEMBLY);
+    if (d->nnzh) CUDA_OK(h, cudaMemcpyAsync(d->hessV, hess_V, sizeof(double) * B * d->nnzh, cudaMemcpyHostToDevice, d->stream));
+    if (d->nnzJfull > d->nnzj)
+        LAUNCH(h, k_fill, dim3(vec_blocks(d->nnzJfull), B), kVecThreads, 0, d->nnzJfull, d->jacV, d->nnzJfull, -1.0);   // slack columns: -1 (normalkkt.jl:151)
+    if (d->nnzj)
+        CUDA_OK(h, cudaMemcpy2DAsync(d->jacV, sizeof(double) * d->nnzJfull, jac_V, sizeof(double) * d->nnzj,
+                                     sizeof(double) * d->nnzj, B, cudaMemcpyHostToDevice, d->stream));
+    // compress_jacobian! (normalkkt.jl:149-158): AT.nzval[i] = A.V[A_csr_map[i]]
+    if (d->nnzA) {
+        LAUNCH(h, k_gather, dim3(vec_blocks(d->nnzA), B), kVecThreads, 0, d->nnzA, d->A_order, d->jacV, d->nnzJfull, d->A_val, d->nnzA);
+        LAUNCH(h, k_gather, dim3(vec_blocks(d->nnzA), B), kVecThreads, 0, d->nnzA, d->AT_src, d->A_val, d->nnzA, d->AT_val, d->nnzA);
+    }
+    if (d->nnzQ)
+        LAUNCH(h, k_gather, dim3(vec_blocks(d->nnzQ), B), kVecThreads, 0, d->nnzQ, d->Q_src, d->hessV, d->nnzh, d->Q_val, d->nnzQ);
+    if (d->kind == 0) {
+        // constant part of aug_com.nzval: Hessian and Jacobian blocks (duplicates summed); diagonals later
+        double* nz = d->vec[MADIPM_VEC_KKT_NZVAL];
+        CUDA_OK(h, cudaMemsetAsync(nz, 0, sizeof(double) * B * d->kkt_nnz, d->stream));
+        if (d->nnzh)
+            LAUNCH(h, k_scatter_add, dim3(vec_blocks(d->nnzh), B), kVecThreads, 0, d->nnzh, d->aug_map + d->n, d->hessV, d->nnzh, nz, d->kkt_nnz);
+        if (d->nnzJfull)
+            LAUNCH(h, k_scatter_add, dim3(vec_blocks(d->nnzJfull), B), kVecThreads, 0, d->nnzJfull, d->aug_map + d->n + d->nnzh, d->jacV, d->nnzJfull, nz, d->kkt_nnz);
+        LAUNCH(h, k_extract_diag, dim3(vec_blocks(d->N), B), kVecThreads, 0, d->N, d->diag_slot, nz, d->kkt_nnz, d->const_diag);
+    }
+    d->values_set = true;
+    return MADIPM_OK;
+}
+
+// ---- vectors ----------------------------------------------------------------------------------
+int32_t madipm_vec_len(const madipm_handle* h, int32_t vec, int64_t* len) {
+    if (!h || !len || vec < 0 || vec >= MADIPM_VEC_COUNT) return MADIPM_BAD_ARGUMENT;
+    const KktPattern& p = h->pat;
+    int64_t n = p.n_tot, m = p.m, L = n + m + h->nlb + h->nub;
+    switch (vec) {
+        case MADIPM_VEC_Y: case MADIPM_VEC_C: case MADIPM_VEC_RHS: case MADIPM_VEC_DU_DIAG: *len = m; break;
+        case MADIPM_VEC_D: case MADIPM_VEC_P: case MADIPM_VEC_W1: case MADIPM_VEC_W2: *len = L; break;
+        case MADIPM_VEC_CORR_LB: case MADIPM_VEC_L_DIAG: case MADIPM_VEC_L_LOWER: *len = h->nlb; break;
+        case MADIPM_VEC_CORR_UB: case MADIPM_VEC_U_DIAG: case MADIPM_VEC_U_LOWER: *len = h->nub; break;
+        case MADIPM_VEC_KKT_NZVAL: *len = p.kkt_colptr.empty() ? 0 : p.kkt_colptr.back(); break;
+        default: *len = n;
+    }
+    return MADIPM_OK;
+}
+
+int32_t madipm_vec_set(madipm_handle* h, int32_t vec, const double* host) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    if (vec < 0 || vec >= MADIPM_VEC_COUNT || !host) return MADIPM_BAD_ARGUMENT;
+    DeviceState* d = h->dev;
+    CUDA_OK(h, cudaMemcpyAsync(d->vec[vec], host, sizeof(double) * d->B * d->veclen[vec], cudaMemcpyHostToDevice, d->stream));
+    return MADIPM_OK;
+}
+
+int32_t madipm_vec_get(madipm_handle* h, int32_t vec, double* host) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    if (vec < 0 || vec >= MADIPM_VEC_COUNT || !host) return MADIPM_BAD_ARGUMENT;
+    DeviceState* d = h->dev;
+    CUDA_OK(h, cudaMemcpyAsync(host, d->vec[vec], sizeof(double) * d->B * d->veclen[vec], cudaMemcpyDeviceToHost, d->stream));
+    CUDA_OK(h, cudaStreamSynchronize(d->stream));
+    return MADIPM_OK;
+}
+
+int32_t madipm_vec_fill(madipm_handle* h, int32_t vec, double value) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    if (vec < 0 || vec >= MADIPM_VEC_COUNT) return MADIPM_BAD_ARGUMENT;
+    DeviceState* d = h->dev;
+    LAUNCH(h, k_fill, dim3(vec_blocks(d->veclen[vec]), d->B), kVecThreads, 0, d->veclen[vec], d->vec[vec], d->veclen[vec], value);
+    return MADIPM_OK;
+}
+
+int32_t madipm_vec_device_ptr(madipm_handle* h, int32_t vec, void** dev) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    if (vec < 0 || vec >= MADIPM_VEC_COUNT || !dev) return MADIPM_BAD_ARGUMENT;
+    *dev = h->dev->vec[vec];
+    return MADIPM_OK;
+}
+
+int32_t madipm_synchronize(madipm_handle* h) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    CUDA_OK(h, cudaStreamSynchronize(h->dev->stream));
+    return MADIPM_OK;
+}
+
+void* madipm_stream(madipm_handle* h) { return (h && h->dev) ? h->dev->stream : nullptr; }
+
+int32_t madipm_vec_copy(madipm_handle* h, int32_t dst, int32_t src) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (dst < 0 || src < 0 || dst >= MADIPM_VEC_COUNT || src >= MADIPM_VEC_COUNT || d->veclen[dst] != d->veclen[src]) return MADIPM_BAD_ARGUMENT;
+    CUDA_OK(h, cudaMemcpyAsync(d->vec[dst], d->vec[src], sizeof(double) * d->B * d->veclen[dst], cudaMemcpyDeviceToDevice, d->stream));
+    return MADIPM_OK;
+}
+
+int32_t madipm_vec_axpy(madipm_handle* h, int32_t dst, int64_t off_dst, int32_t src, int64_t off_src, int64_t len, double alpha) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (dst < 0 || src < 0 || dst >= MADIPM_VEC_COUNT || src >= MADIPM_VEC_COUNT || len < 0 || off_dst < 0 || off_src < 0 ||
+        off_dst + len > d->veclen[dst] || off_src + len > d->veclen[src]) return MADIPM_BAD_ARGUMENT;
+    Timer t(h, MADIPM_T_VECTOR);
+    LAUNCH(h, k_axpy, dim3(vec_blocks(len), d->B), kVecThreads, 0, len, d->vec[dst] + off_dst, d->veclen[dst], d->vec[src] + off_src, d->veclen[src], alpha);
+    return MADIPM_OK;
+}
+
+int32_t madipm_vec_norm_inf(madipm_handle* h, int32_t vec, double* out) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (vec < 0 || vec >= MADIPM_VEC_COUNT || !out) return MADIPM_BAD_ARGUMENT;
+    Timer t(h, MADIPM_T_VECTOR);
+    LAUNCH(h, k_norm_inf, dim3(vec_blocks(d->veclen[vec]), d->B), kVecThreads, 0, d->veclen[vec], d->vec[vec], d->veclen[vec], d->red_scratch, d->red_counter, d->d_out);
+    return fetch(h, d->d_out, out, d->B);
+}
+
+// ---- KKT system ---------------------------------------------------------------------------------
+int32_t madipm_kkt_initialize(madipm_handle* h) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    const struct { int v; double x; } init[] = {
+        {MADIPM_VEC_REG, 1.0}, {MADIPM_VEC_PR_DIAG, 1.0}, {MADIPM_VEC_DU_DIAG, 0.0}, {MADIPM_VEC_L_LOWER, 0.0},
+        {MADIPM_VEC_U_LOWER, 0.0}, {MADIPM_VEC_L_DIAG, 1.0}, {MADIPM_VEC_U_DIAG, 1.0}};
+    for (auto& it : init)
+        if ((rc = madipm_vec_fill(h, it.v, it.x))) return rc;
+    return MADIPM_OK;
+}
+
+int32_t madipm_set_aug_diagonal_reg(madipm_handle* h, double del_w, double del_c) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    Timer t(h, MADIPM_T_ASSEMBLY);
+    LAUNCH(h, k_set_aug_diagonal_reg, dim3(vec_blocks(std::max(d->n, d->m)), d->B), kVecThreads, 0, make_view(*d), del_w, del_c);
+    return MADIPM_OK;
+}
+
+int32_t madipm_set_initial_regularization(madipm_handle* h, double del_w, double del_c) {
+    int32_t rc;
+    if ((rc = madipm_vec_fill(h, MADIPM_VEC_REG, del_w))) return rc;
+    if ((rc = madipm_vec_fill(h, MADIPM_VEC_PR_DIAG, del_w))) return rc;
+    return madipm_vec_fill(h, MADIPM_VEC_DU_DIAG, del_c);
+}
+
+int32_t madipm_build_kkt(madipm_handle* h) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    Timer t(h, MADIPM_T_ASSEMBLY);
+    double* nz = d->vec[MADIPM_VEC_KKT_NZVAL];
+    if (d->kind == 0) {
+        LAUNCH(h, k_build_kkt_k2, dim3(vec_blocks(d->N), d->B), kVecThreads, 0, d->n, d->m, d->diag_slot, d->const_diag,
+               d->vec[MADIPM_VEC_PR_DIAG], d->vec[MADIPM_VEC_DU_DIAG], nz, d->kkt_nnz);
+    } else {
+        LAUNCH(h, k_assemble_normal, dim3(vec_blocks(d->kkt_nnz), d->B), kVecThreads, 0, d->kkt_nnz, d->prod_ptr, d->prod_a,
+               d->prod_b, d->prod_k, d->A_val, d->nnzA, d->vec[MADIPM_VEC_PR_DIAG], (int64_t)d->n, nz, d->kkt_nnz);
+    }
+    return MADIPM_OK;
+}
+
+int32_t madipm_factorize(madipm_handle* h, int32_t* n_failed) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    const int B = d->B;
+    {
+        Timer t(h, MADIPM_T_FACTOR);
+        CUDA_OK(h, cudaMemsetAsync(d->Lx, 0, sizeof(double) * B * d->lx_stride, d->stream));
+        CUDA_OK(h, cudaMemsetAsync(d->fail, 0, sizeof(int) * B, d->stream));
+        LAUNCH(h, k_assemble_panels, dim3(vec_blocks(d->kkt_nnz) * 4, B), kVecThreads, 0, d->kkt_nnz, d->asm_map,
+               d->vec[MADIPM_VEC_KKT_NZVAL], d->kkt_nnz, d->Lx, d->lx_stride);
+        FactorView F = make_factor_view(*d);
+        if (d->n_subtrees > 0)
+            LAUNCH(h, k_factor_subtrees, dim3(d->n_subtrees, B), 128, d->factor_smem, F, d->sub_first, d->sub_last);
+        for (int l = 0; l < d->n_levels; ++l) {
+            int cnt = d->level_ptr[l + 1] - d->level_ptr[l];
+            LAUNCH(h, k_factor_level, dim3(cnt, B), 256, d->factor_smem, F, d->level_sn + d->level_ptr[l]);
+        }
+        CUDA_OK(h, cudaMemcpyAsync(d->h_fail.data(), d->fail, sizeof(int) * B, cudaMemcpyDeviceToHost, d->stream));
+        CUDA_OK(h, cudaStreamSynchronize(d->stream));
+    }
+    CUDA_OK(h, cudaGetLastError());
+    int bad = 0;
+    for (int i = 0; i < B; ++i) bad += d->h_fail[i] != 0;
+    if (n_failed) *n_failed = bad;
+    return bad ? MADIPM_FACTOR_BREAKDOWN : MADIPM_OK;
+}
+
+int32_t madipm_is_factorized(madipm_handle* h, int32_t* flags) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    if (!flags) return MADIPM_BAD_ARGUMENT;
+    for (int i = 0; i < h->dev->B; ++i) flags[i] = h->dev->h_fail[i] == 0;
+    return MADIPM_OK;
+}
+
+int32_t madipm_inertia(madipm_handle* h, int32_t inst, int64_t* n_pos, int64_t* n_zero, int64_t* n_neg) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (inst < 0 || inst >= d->B) return MADIPM_BAD_ARGUMENT;
+    CUDA_OK(h, cudaMemsetAsync(d->d_inertia, 0, sizeof(unsigned long long) * 3 * d->B, d->stream));
+    LAUNCH(h, k_inertia, dim3(vec_blocks(d->N), d->B), kVecThreads, 0, d->N, d->diag_pos, d->Lx, d->lx_stride, d->d_inertia);
+    std::vector<unsigned long long> out(3 * d->B);
+    CUDA_OK(h, cudaMemcpyAsync(out.data(), d->d_inertia, sizeof(unsigned long long) * 3 * d->B, cudaMemcpyDeviceToHost, d->stream));
+    CUDA_OK(h, cudaStreamSynchronize(d->stream));
+    if (n_pos) *n_pos = out[inst * 3];
+    if (n_zero) *n_zero = out[inst * 3 + 1];
+    if (n_neg) *n_neg = out[inst * 3 + 2];
+    return MADIPM_OK;
+}
+
+int32_t madipm_linear_solve(madipm_handle* h, double* dev_rhs, int64_t stride) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (!dev_rhs) return MADIPM_BAD_ARGUMENT;
+    Timer t(h, MADIPM_T_SOLVE);
+    LAUNCH(h, k_perm_gather, dim3(vec_blocks(d->N), d->B), kVecThreads, 0, d->N, d->perm, dev_rhs, stride, d->xw, (int64_t)d->N);
+    if ((rc = tri_solve(h))) return rc;
+    LAUNCH(h, k_perm_scatter, dim3(vec_blocks(d->N), d->B), kVecThreads, 0, d->N, d->perm, d->xw, (int64_t)d->N, dev_rhs, stride);
+    return MADIPM_OK;
+}
+
+int32_t madipm_kkt_solve(madipm_handle* h, int32_t vec_w) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (vec_w < MADIPM_VEC_D || vec_w > MADIPM_VEC_W2) return MADIPM_BAD_ARGUMENT;
+    Timer t(h, MADIPM_T_SOLVE);
+    VecView V = make_view(*d);
+    double* w = d->vec[vec_w];
+    const dim3 gN(vec_blocks(d->N), d->B), gn(vec_blocks(d->n), d->B), gm(vec_blocks(d->m), d->B);
+    if (d->kind == 0) {
+        LAUNCH(h, k_k2_presolve, gN, kVecThreads, 0, V, w, d->perm, d->N, d->xw, (int64_t)d->N);
+        if ((rc = tri_solve(h))) return rc;
+        LAUNCH(h, k_k2_postsolve, gN, kVecThreads, 0, V, w, d->iperm, d->N, d->xw, (int64_t)d->N);
+    } else {
+        LAUNCH(h, k_normal_pre, gn, kVecThreads, 0, V, w, d->buffer_n, (int64_t)d->n);
+        LAUNCH(h, k_normal_rhs, gm, kVecThreads, 0, V, d->A_rp, d->A_ci, d->A_val, d->nnzA, w, d->buffer_n, (int64_t)d->n, d->perm, d->xw, (int64_t)d->N);
+        if ((rc = tri_solve(h))) return rc;
+        LAUNCH(h, k_normal_unperm, gm, kVecThreads, 0, V, w, d->iperm, d->xw, (int64_t)d->N);
+        LAUNCH(h, k_normal_post, gn, kVecThreads, 0, V, d->AT_rp, d->AT_ci, d->AT_val, d->nnzA, w);
+    }
+    return MADIPM_OK;
+}
+
+int32_t madipm_kkt_mul(madipm_handle* h, int32_t vec_w, int32_t vec_v, double alpha, double beta) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (vec_w < MADIPM_VEC_D || vec_w > MADIPM_VEC_W2 || vec_v < MADIPM_VEC_D || vec_v > MADIPM_VEC_W2 || vec_w == vec_v) return MADIPM_BAD_ARGUMENT;
+    Timer t(h, MADIPM_T_SPMV);
+    double* w = d->vec[vec_w];
+    const double* v = d->vec[vec_v];
+    // wx = alpha * (H vx + A' vy) + beta * wx ;  wy = alpha * A vx + beta * wy
+    if (d->kind == 0 && d->nnzQ > 0) {
+        spmv_launch(h, d->n, d->nnzQ, d->Q_rp, d->Q_ci, d->Q_val, d->nnzQ, v, d->L, w, d->L, alpha, beta);
+        spmv_launch(h, d->n, d->nnzA, d->AT_rp, d->AT_ci, d->AT_val, d->nnzA, v + d->n, d->L, w, d->L, alpha, 1.0);
+    } else {
+        spmv_launch(h, d->n, d->nnzA, d->AT_rp, d->AT_ci, d->AT_val, d->nnzA, v + d->n, d->L, w, d->L, alpha, beta);
+    }
+    spmv_launch(h, d->m, d->nnzA, d->A_rp, d->A_ci, d->A_val, d->nnzA, v, d->L, w + d->n, d->L, alpha, beta);
+    LAUNCH(h, k_kktmul_tail, dim3(vec_blocks(std::max(d->n, d->m)), d->B), kVecThreads, 0, make_view(*d), w, v, alpha, beta);
+    return MADIPM_OK;
+}
+
+int32_t madipm_solve_system(madipm_handle* h, int32_t vec_d, int32_t vec_p, double* norms) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (!norms || vec_d == MADIPM_VEC_W1 || vec_p == MADIPM_VEC_W1) return MADIPM_BAD_ARGUMENT;
+    if ((rc = madipm_vec_copy(h, vec_d, vec_p))) return rc;                 // linear_solver.jl:25
+    if ((rc = madipm_kkt_solve(h, vec_d))) return rc;                       // :26
+    if ((rc = madipm_vec_copy(h, MADIPM_VEC_W1, vec_p))) return rc;         // :30
+    if ((rc = madipm_kkt_mul(h, MADIPM_VEC_W1, vec_d, -1.0, 1.0))) return rc;   // :31
+    {
+        Timer t(h, MADIPM_T_VECTOR);
+        LAUNCH(h, k_norms3, dim3(vec_blocks(d->L), d->B), kVecThreads, 0, d->L, d->vec[MADIPM_VEC_W1], d->vec[vec_p],
+               d->vec[vec_d], d->L, d->red_scratch, d->red_counter, d->d_out);
+    }
+    if ((rc = fetch(h, d->d_out, norms, 3 * d->B))) return rc;
+    for (int i = 0; i < d->B; ++i) {
+        double ratio = norms[3 * i] / std::max(1.0, norms[3 * i + 1]);
+        if (std::isnan(ratio)) return MADIPM_NONFINITE;                     // :41-43
+    }
+    return MADIPM_OK;
+}
+
+int32_t madipm_spmv_ptr(madipm_handle* h, int32_t op, double* dev_out, int64_t so, const double* dev_in, int64_t si) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    Timer t(h, MADIPM_T_SPMV);
+    switch (op) {
+        case MADIPM_OP_A: return spmv_launch(h, d->m, d->nnzA, d->A_rp, d->A_ci, d->A_val, d->nnzA, dev_in, si, dev_out, so, 1.0, 0.0);
+        case MADIPM_OP_AT: return spmv_launch(h, d->n, d->nnzA, d->AT_rp, d->AT_ci, d->AT_val, d->nnzA, dev_in, si, dev_out, so, 1.0, 0.0);
+        case MADIPM_OP_Q: return spmv_launch(h, d->n, d->nnzQ, d->Q_rp, d->Q_ci, d->Q_val, d->nnzQ, dev_in, si, dev_out, so, 1.0, 0.0);
+        default: return MADIPM_BAD_ARGUMENT;
+    }
+}
+
+int32_t madipm_spmv(madipm_handle* h, int32_t op, int32_t vec_out, int32_t vec_in) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (vec_out < 0 || vec_in < 0 || vec_out >= MADIPM_VEC_COUNT || vec_in >= MADIPM_VEC_COUNT || vec_out == vec_in) return MADIPM_BAD_ARGUMENT;
+    const int64_t want_in = (op == MADIPM_OP_AT) ? d->m : d->n, want_out = (op == MADIPM_OP_A) ? d->m : d->n;
+    if (d->veclen[vec_in] < want_in || d->veclen[vec_out] < want_out) return MADIPM_BAD_ARGUMENT;
+    return madipm_spmv_ptr(h, op, d->vec[vec_out], d->veclen[vec_out], d->vec[vec_in], d->veclen[vec_in]);
+}
+
+// ---- fused phases -------------------------------------------------------------------------------
+int32_t madipm_eval_model(madipm_handle* h, double c0, double* obj) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    {
+        Timer t(h, MADIPM_T_SPMV);
+        LAUNCH(h, k_eval_model, dim3(vec_blocks(std::max(d->n, d->m)), d->B), kVecThreads, 0, make_view(*d), d->Q_rp, d->Q_ci,
+               d->Q_val, d->nnzQ, d->A_rp, d->A_ci, d->A_val, d->nnzA, d->red_scratch, d->red_counter, d->d_out);
+    }
+    if (obj) {
+        std::vector<double> tmp(2 * d->B);
+        if ((rc = fetch(h, d->d_out, tmp.data(), 2 * d->B))) return rc;
+        for (int i = 0; i < d->B; ++i) obj[i] = c0 + tmp[2 * i] + 0.5 * tmp[2 * i + 1];
+    }
+    return MADIPM_OK;
+}
+
+int32_t madipm_phase_residuals(madipm_handle* h, double* out) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (!out) return MADIPM_BAD_ARGUMENT;
+    {
+        Timer t(h, MADIPM_T_SPMV);
+        LAUNCH(h, k_residuals, dim3(vec_blocks(std::max(d->n, d->m)), d->B), kVecThreads, 0, make_view(*d), d->AT_rp, d->AT_ci,
+               d->AT_val, d->nnzA, d->vec[MADIPM_VEC_D], d->red_scratch, d->red_counter, d->d_out);
+    }
+    return fetch(h, d->d_out, out, 4 * d->B);
+}
+
+static int32_t set_rhs(madipm_handle* h, int mode, const double* mu) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    Timer t(h, MADIPM_T_VECTOR);
+    if (mode == 3) {
+        if (!mu) return MADIPM_BAD_ARGUMENT;
+        CUDA_OK(h, cudaMemcpyAsync(d->d_mu, mu, sizeof(double) * d->B, cudaMemcpyHostToDevice, d->stream));
+    }
+    const int top = std::max(std::max(d->n, d->m), std::max(d->nlb, d->nub));
+    LAUNCH(h, k_set_rhs, dim3(vec_blocks(top), d->B), kVecThreads, 0, make_view(*d), d->vec[MADIPM_VEC_P], mode, d->d_mu);
+    return MADIPM_OK;
+}
+int32_t madipm_set_initial_primal_rhs(madipm_handle* h) { return set_rhs(h, 0, nullptr); }
+int32_t madipm_set_initial_dual_rhs(madipm_handle* h) { return set_rhs(h, 1, nullptr); }
+int32_t madipm_set_predictive_rhs(madipm_handle* h) { return set_rhs(h, 2, nullptr); }
+int32_t madipm_set_correction_rhs(madipm_handle* h, const double* mu) { return set_rhs(h, 3, mu); }
+
+static void launch_ratio(madipm_handle* h, const double* tau_dev, double* out_dev) {
+    DeviceState* d = h->dev;
+    LAUNCH(h, k_ratio_test, dim3(vec_blocks(std::max(d->nlb, d->nub)), d->B), kVecThreads, 0, make_view(*d), d->vec[MADIPM_VEC_D],
+           tau_dev, d->red_scratch, d->red_counter, out_dev);
+}
+
+int32_t madipm_ratio_test(madipm_handle* h, const double* tau, double* out) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (!tau || !out) return MADIPM_BAD_ARGUMENT;
+    {
+        Timer t(h, MADIPM_T_VECTOR);
+        CUDA_OK(h, cudaMemcpyAsync(d->d_tau, tau, sizeof(double) * d->B, cudaMemcpyHostToDevice, d->stream));
+        launch_ratio(h, d->d_tau, d->d_out);
+    }
+    return fetch(h, d->d_out, out, 8 * d->B);
+}
+
+int32_t madipm_complementarity(madipm_handle* h, const double* alpha_p, const double* alpha_d, double* out) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (!out) return MADIPM_BAD_ARGUMENT;
+    std::vector<double> st(2 * d->B, 0.0);
+    for (int i = 0; i < d->B; ++i) { st[2 * i] = alpha_p ? alpha_p[i] : 0.0; st[2 * i + 1] = alpha_d ? alpha_d[i] : 0.0; }
+    {
+        Timer t(h, MADIPM_T_VECTOR);
+        CUDA_OK(h, cudaMemcpyAsync(d->d_steps, st.data(), sizeof(double) * 2 * d->B, cudaMemcpyHostToDevice, d->stream));
+        LAUNCH(h, k_complementarity, dim3(vec_blocks(std::max(d->nlb, d->nub)), d->B), kVecThreads, 0, make_view(*d),
+               d->vec[MADIPM_VEC_D], d->d_steps, 0, d->red_scratch, d->red_counter, d->d_out);
+    }
+    std::vector<double> tmp(4 * d->B);
+    if ((rc = fetch(h, d->d_out, tmp.data(), 4 * d->B))) return rc;
+    const int nb = d->nlb + d->nub;
+    for (int i = 0; i < d->B; ++i) {
+        out[2 * i] = nb ? (tmp[4 * i] + tmp[4 * i + 1]) / nb : 0.0;
+        out[2 * i + 1] = nb ? (tmp[4 * i + 2] + tmp[4 * i + 3]) / nb : 0.0;
+    }
+    return MADIPM_OK;
+}
+
+int32_t madipm_phase_affine(madipm_handle* h, double* out) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (!out) return MADIPM_BAD_ARGUMENT;
+    {
+        Timer t(h, MADIPM_T_VECTOR);
+        launch_ratio(h, d->d_ones, d->d_out2);                                                   // tau = 1 (solver.jl:295)
+        LAUNCH(h, k_steps_from_ratio, (d->B + 127) / 128, 128, 0, d->B, d->d_out2, d->d_steps);
+        LAUNCH(h, k_complementarity, dim3(vec_blocks(std::max(d->nlb, d->nub)), d->B), kVecThreads, 0, make_view(*d),
+               d->vec[MADIPM_VEC_D], d->d_steps, 1, d->red_scratch, d->red_counter, d->d_out);   // solver.jl:296-297
+    }
+    std::vector<double> st(2 * d->B), tmp(4 * d->B);
+    CUDA_OK(h, cudaMemcpyAsync(d->h_out + 16 * d->B, d->d_steps, sizeof(double) * 2 * d->B, cudaMemcpyDeviceToHost, d->stream));
+    if ((rc = fetch(h, d->d_out, tmp.data(), 4 * d->B))) return rc;
+    std::memcpy(st.data(), d->h_out + 16 * d->B, sizeof(double) * 2 * d->B);
+    const int nb = d->nlb + d->nub;
+    for (int i = 0; i < d->B; ++i) {
+        out[4 * i] = st[2 * i];
+        out[4 * i + 1] = st[2 * i + 1];
+        out[4 * i + 2] = nb ? (tmp[4 * i] + tmp[4 * i + 1]) / nb : 0.0;
+        out[4 * i + 3] = nb ? (tmp[4 * i + 2] + tmp[4 * i + 3]) / nb : 0.0;
+    }
+    return MADIPM_OK;
+}
+
+int32_t madipm_get_correction(madipm_handle* h) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    Timer t(h, MADIPM_T_VECTOR);
+    LAUNCH(h, k_complementarity, dim3(vec_blocks(std::max(d->nlb, d->nub)), d->B), kVecThreads, 0, make_view(*d),
+           d->vec[MADIPM_VEC_D], (const double*)nullptr, 1, d->red_scratch, d->red_counter, d->d_out);
+    return MADIPM_OK;
+}
+
+int32_t madipm_set_extra_correction(madipm_handle* h, const double* alpha_p, const double* alpha_d, double bmin, double bmax, const double* mu) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (!alpha_p || !alpha_d || !mu) return MADIPM_BAD_ARGUMENT;
+    std::vector<double> st(2 * d->B);
+    for (int i = 0; i < d->B; ++i) { st[2 * i] = alpha_p[i]; st[2 * i + 1] = alpha_d[i]; }
+    Timer t(h, MADIPM_T_VECTOR);
+    CUDA_OK(h, cudaMemcpyAsync(d->d_steps, st.data(), sizeof(double) * 2 * d->B, cudaMemcpyHostToDevice, d->stream));
+    CUDA_OK(h, cudaMemcpyAsync(d->d_mu, mu, sizeof(double) * d->B, cudaMemcpyHostToDevice, d->stream));
+    LAUNCH(h, k_extra_correction, dim3(vec_blocks(std::max(d->nlb, d->nub)), d->B), kVecThreads, 0, make_view(*d),
+           d->vec[MADIPM_VEC_D], d->d_steps, bmin, bmax, d->d_mu);
+    return MADIPM_OK;
+}
+
+int32_t madipm_update_iterate(madipm_handle* h, const double* alpha_p, const double* alpha_d, const double* mu, const int32_t* active) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (!alpha_p || !alpha_d || !mu) return MADIPM_BAD_ARGUMENT;
+    std::vector<double> st(2 * d->B);
+    for (int i = 0; i < d->B; ++i) { st[2 * i] = alpha_p[i]; st[2 * i + 1] = alpha_d[i]; }
+    Timer t(h, MADIPM_T_VECTOR);
+    CUDA_OK(h, cudaMemcpyAsync(d->d_steps, st.data(), sizeof(double) * 2 * d->B, cudaMemcpyHostToDevice, d->stream));
+    CUDA_OK(h, cudaMemcpyAsync(d->d_mu, mu, sizeof(double) * d->B, cudaMemcpyHostToDevice, d->stream));
+    if (active) CUDA_OK(h, cudaMemcpyAsync(d->d_active, active, sizeof(int) * d->B, cudaMemcpyHostToDevice, d->stream));
+    LAUNCH(h, k_update_iterate, dim3(vec_blocks(std::max(d->n, d->m)), d->B), kVecThreads, 0, make_view(*d), d->vec[MADIPM_VEC_D],
+           d->d_steps, d->d_mu, active ? d->d_active : (const int*)nullptr);
+    return MADIPM_OK;
+}
+
+int32_t madipm_mehrotra_step(madipm_handle* h, double gamma_f, double* out) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (!out) return MADIPM_BAD_ARGUMENT;
+    {
+        Timer t(h, MADIPM_T_VECTOR);
+        launch_ratio(h, d->d_ones, d->d_out2);
+        LAUNCH(h, k_steps_from_ratio, (d->B + 127) / 128, 128, 0, d->B, d->d_out2, d->d_steps);
+        LAUNCH(h, k_complementarity, dim3(vec_blocks(std::max(d->nlb, d->nub)), d->B), kVecThreads, 0, make_view(*d),
+               d->vec[MADIPM_VEC_D], d->d_steps, 0, d->red_scratch, d->red_counter, d->d_out);
+        LAUNCH(h, k_mehrotra_step, (d->B + 127) / 128, 128, 0, make_view(*d), d->B, d->vec[MADIPM_VEC_D], d->d_out2, d->d_out,
+               gamma_f, d->d_steps);
+    }
+    return fetch(h, d->d_steps, out, 2 * d->B);
+}
+
+int32_t madipm_init_multipliers_and_shift(madipm_handle* h, double bound_fac) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    const int B = d->B;
+    VecView V = make_view(*d);
+    const dim3 g(vec_blocks(d->n), B);
+    // step 3 (solver.jl:35-39): res = A'y + f
+    if ((rc = madipm_spmv(h, MADIPM_OP_AT, MADIPM_VEC_JACL, MADIPM_VEC_Y))) return rc;
+    std::vector<double> r(8 * B), del(2 * B);
+    LAUNCH(h, k_start_a, g, kVecThreads, 0, V, d->red_scratch, d->red_counter, d->d_out);
+    if ((rc = fetch(h, d->d_out, r.data(), 4 * B))) return rc;
+    for (int i = 0; i < B; ++i) {
+        del[2 * i] = std::max(0.0, std::max(-1.5 * r[4 * i], -1.5 * r[4 * i + 1]));          // delta_x, l.68-72
+        del[2 * i + 1] = std::max(0.0, std::max(-1.5 * r[4 * i + 2], -1.5 * r[4 * i + 3]));  // delta_s, l.74-78
+    }
+    CUDA_OK(h, cudaMemcpyAsync(d->d_steps, del.data(), sizeof(double) * 2 * B, cudaMemcpyHostToDevice, d->stream));
+    LAUNCH(h, k_start_b, g, kVecThreads, 0, V, d->d_steps, d->red_scratch, d->red_counter, d->d_out);
+    if ((rc = fetch(h, d->d_out, r.data(), 6 * B))) return rc;
+    for (int i = 0; i < B; ++i) {
+        const double* q = &r[6 * i];
+        double mu = 0.0;
+        if (d->nlb) mu += q[0];
+        if (d->nub) mu += q[1];
+        del[2 * i] = mu / (2 * (q[2] + q[3]));        // delta_x2, l.93
+        del[2 * i + 1] = mu / (2 * (q[4] + q[5]));    // delta_s2, l.94
+    }
+    CUDA_OK(h, cudaMemcpyAsync(d->d_steps, del.data(), sizeof(double) * 2 * B, cudaMemcpyHostToDevice, d->stream));
+    LAUNCH(h, k_start_c, g, kVecThreads, 0, V, d->d_steps, bound_fac, d->red_scratch, d->red_counter, d->d_out);
+    if ((rc = fetch(h, d->d_out, r.data(), 4 * B))) return rc;
+    for (int i = 0; i < B; ++i)
+        for (int k = 0; k < 4; ++k)
+            if (!(r[4 * i + k] > 0.0)) {   // the four @assert of solver.jl:120-123
+                h->error = "starting point left the interior (assert of solver.jl:120-123)";
+                return MADIPM_INTERNAL;
+            }
+    return MADIPM_OK;
+}
+
+// ---- measurement hooks ----------------------------------------------------------------------------
+int32_t madipm_profile(madipm_handle* h, int32_t enable) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    h->dev->profiling = enable != 0;
+    return MADIPM_OK;
+}
+
+int32_t madipm_profile_read(madipm_handle* h, double* ms, int64_t* calls, int32_t reset) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    for (int i = 0; i < MADIPM_T_COUNT; ++i) {
+        if (ms) ms[i] = h->dev->t_ms[i];
+        if (calls) calls[i] = h->dev->t_calls[i];
+        if (reset) { h->dev->t_ms[i] = 0; h->dev->t_calls[i] = 0; }
+    }
+    return MADIPM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,486 @@
+"""Host-side mirror of MadIPM's solver interface on top of the B200 backend.
+
+In the target deployment the Mehrotra predictor-corrector control
+(/root/reference/src/solver.jl) stays in Julia and reaches the GPU through the
+``ccall`` shim of INTEGRATION.md.  Julia is not available in this environment,
+so this module is the stand-in caller: ``MPCSolver`` has the reference's option
+names, status names and call structure (``initialize!``, ``mpc!``, ``solve!``),
+and every numeric step is one call through the C ABI (``_lib.Handle``).  No
+numerical work is done here beyond scalars; nothing falls back to the CPU.
+
+One ``MPCSolver`` drives ``batch`` instances that share a sparsity pattern
+(batch = 1 for a single solve; the C5 configuration uses batch > 1).
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from ._lib import Handle, MadIPMError
+
+# MadNLP.Status names used by the reference (solver.jl:279-283, 359-390)
+SOLVE_SUCCEEDED = "SOLVE_SUCCEEDED"
+MAXIMUM_ITERATIONS_EXCEEDED = "MAXIMUM_ITERATIONS_EXCEEDED"
+ERROR_IN_STEP_COMPUTATION = "ERROR_IN_STEP_COMPUTATION"
+INTERNAL_ERROR = "INTERNAL_ERROR"
+INITIAL = "INITIAL"
+
+
+class SolveException(Exception):
+    """MadNLP.SolveException, /root/reference/src/linear_solver.jl:41-43."""
+
+
+# ---- option types of /root/reference/src/utils.jl:17-48 ------------------------------------------
+@dataclass
+class ConservativeStep:
+    tau: float = 0.995
+
+
+@dataclass
+class AdaptiveStep:
+    tau_min: float = 0.99
+
+
+@dataclass
+class MehrotraAdaptiveStep:
+    gamma_f: float = 0.99
+
+
+@dataclass
+class NoRegularization:
+    pass
+
+
+@dataclass
+class FixedRegularization:
+    delta_p: float = 1e-8
+    delta_d: float = 0.0
+
+
+@dataclass
+class AdaptiveRegularization:
+    delta_p: float = 1e-8
+    delta_d: float = -1e-9
+    delta_min: float = 1e-9
+
+
+@dataclass
+class IPMOptions:
+    """/root/reference/src/utils.jl:69-103 (fields that reach the hot path)."""
+    tol: float = 1e-8
+    kkt_system: str = "K2"               # "K2" = MadNLP.SparseKKTSystem (default), "NORMAL" = MadIPM.NormalKKTSystem
+    max_iter: int = 3000
+    scaling: bool = True
+    bound_push: float = 1e-2
+    bound_fac: float = 1e-2
+    bound_relax_factor: float = 1e-8
+    regularization: object = field(default_factory=lambda: FixedRegularization(1e-8, 0.0))
+    step_rule: object = field(default_factory=lambda: AdaptiveStep(0.99))
+    max_ncorr: int = 0
+    mu_init: float = 1e-1
+    mu_min: float = 1e-11
+    tol_linear_solve: float = 1e-8
+    check_residual: bool = False
+    # backend options (the linear-solver options of the reference's `opt_linear_solver`)
+    ordering: int = _lib.ORDER_ND
+    max_width: int = 64
+    subtree_work: int = 2_000_000
+    nd_leaf: int = 0
+    device: int = 0
+
+
+@dataclass
+class IndexConstraints:
+    ind_eq: np.ndarray
+    ind_ineq: np.ndarray
+    ind_lb: np.ndarray
+    ind_ub: np.ndarray
+
+
+def get_index_constraints(lvar, uvar, lcon, ucon):
+    """MadNLP.get_index_constraints (call site /root/reference/src/structure.jl:95-102); 0-based."""
+    if np.any(lvar == uvar):
+        raise NotImplementedError("fixed variables are removed by MadNLP's MakeParameter before the hot path")
+    ind_eq = np.nonzero(lcon == ucon)[0]
+    ind_ineq = np.nonzero(lcon != ucon)[0]
+    xl = np.concatenate([lvar, lcon[ind_ineq]])
+    xu = np.concatenate([uvar, ucon[ind_ineq]])
+    return IndexConstraints(ind_eq, ind_ineq, np.nonzero(xl > -np.inf)[0], np.nonzero(xu < np.inf)[0])
+
+
+def _push_inside(x, l, u, bound_push, bound_fac):
+    """MadNLP.initialize_variables! (Ipopt's projection of x0 into the interior of [l, u])."""
+    out = x.copy()
+    fl, fu = np.isfinite(l), np.isfinite(u)
+    with np.errstate(invalid="ignore"):
+        pl = np.minimum(bound_push * np.maximum(1.0, np.abs(l)), bound_fac * (u - l))
+        pu = np.minimum(bound_push * np.maximum(1.0, np.abs(u)), bound_fac * (u - l))
+        both = fl & fu
+        out[both] = np.minimum(u - pu, np.maximum(l + pl, x))[both]
+        lo = fl & ~fu
+        out[lo] = np.maximum(l + bound_push * np.maximum(1.0, np.abs(l)), x)[lo]
+        up = ~fl & fu
+        out[up] = np.minimum(u - bound_push * np.maximum(1.0, np.abs(u)), x)[up]
+    return out
+
+
+@dataclass
+class ExecutionStats:
+    status: list
+    iter: np.ndarray
+    objective: np.ndarray
+    solution: np.ndarray
+    multipliers: np.ndarray
+    inf_pr: np.ndarray
+    inf_du: np.ndarray
+    inf_compl: np.ndarray
+    total_time: float
+    init_time: float
+
+
+class B200KKTSystem:
+    """The AbstractKKTSystem + linear-solver pair as one object
+    (method list of /root/reference/src/KKT/normalkkt.jl:128-220)."""
+
+    def __init__(self, handle: Handle, kind: str):
+        self.h = handle
+        self.kind = kind
+
+    def initialize(self):                      # MadNLP.initialize!(kkt)
+        self.h.kkt_initialize()
+
+    def build_kkt(self):                       # MadNLP.build_kkt!
+        self.h.build_kkt()
+
+    def factorize(self):                       # MadNLP.factorize!(kkt.linear_solver)
+        return self.h.factorize()
+
+    def is_factorized(self):                   # MadIPM.is_factorized
+        return self.h.is_factorized()
+
+    def solve(self, w="D"):                    # MadNLP.solve!(kkt, w)
+        self.h.kkt_solve(w)
+
+    def mul(self, w, v, alpha=1.0, beta=0.0):  # LinearAlgebra.mul!(w, kkt, v, alpha, beta)
+        self.h.kkt_mul(w, v, alpha, beta)
+
+    def jtprod(self, out, inp):                # MadNLP.jtprod!
+        self.h.spmv(_lib.OP_AT, out, inp)
+
+    def is_inertia_correct(self, n_pos, n_zero, n_neg, n, m):
+        if self.kind == "NORMAL":
+            return n_zero == 0 and n_pos == m          # normalkkt.jl:132-134
+        return n_zero == 0 and n_pos == n and n_neg == m
+
+
+class MPCSolver:
+    """MadIPM.MPCSolver(qp; kwargs...) (/root/reference/src/structure.jl:77-176)."""
+
+    def __init__(self, qp, **kwargs):
+        self.qps = list(qp) if isinstance(qp, (list, tuple)) else [qp]
+        q0 = self.qps[0]
+        self.B = len(self.qps)
+        self.opt = IPMOptions(**kwargs)
+        opt = self.opt
+        t0 = time.perf_counter()
+        ic = get_index_constraints(q0.lvar, q0.uvar, q0.lcon, q0.ucon)
+        for q in self.qps[1:]:
+            jc = get_index_constraints(q.lvar, q.uvar, q.lcon, q.ucon)
+            if not (np.array_equal(ic.ind_ineq, jc.ind_ineq) and np.array_equal(ic.ind_lb, jc.ind_lb)
+                    and np.array_equal(ic.ind_ub, jc.ind_ub) and np.array_equal(q.A_rows, q0.A_rows)
+                    and np.array_equal(q.A_cols, q0.A_cols) and np.array_equal(q.H_rows, q0.H_rows)):
+                raise ValueError("batched instances must share one sparsity pattern and bound structure")
+        self.ic = ic
+        self.nx, self.m = q0.nvar, q0.ncon
+        self.ns = ic.ind_ineq.size
+        self.n = self.nx + self.ns
+        self.nlb, self.nub = ic.ind_lb.size, ic.ind_ub.size
+        if opt.kkt_system == "NORMAL" and q0.nnzh > 0:
+            raise ValueError("The KKT system NormalKKTSystem supports only linear programs.")   # normalkkt.jl:43-46
+        kind = _lib.KKT_K2 if opt.kkt_system == "K2" else _lib.KKT_NORMAL
+        self.h = Handle(kkt_kind=kind, batch=self.B, device=opt.device, ordering=opt.ordering,
+                        max_width=opt.max_width, subtree_work=opt.subtree_work, nd_leaf=opt.nd_leaf)
+        if kind == _lib.KKT_K2:
+            self.h.set_pattern_k2(self.nx, self.m, q0.H_rows + 1, q0.H_cols + 1, q0.A_rows + 1, q0.A_cols + 1,
+                                  ic.ind_ineq + 1)
+        else:
+            self.h.set_pattern_normal(self.nx, self.m, q0.A_rows + 1, q0.A_cols + 1, ic.ind_ineq + 1)
+        self.h.set_bounds_index(ic.ind_lb + 1, ic.ind_ub + 1)
+        self.info = self.h.analyze()
+        self.kkt = B200KKTSystem(self.h, opt.kkt_system)
+        self.analysis_time = time.perf_counter() - t0
+        B = self.B
+        self.obj_val = np.zeros(B)
+        self.obj_scale = np.ones(B)
+        self.con_scale = np.ones((B, self.m))
+        self.mu = np.zeros(B)
+        self.alpha_p = np.zeros(B)
+        self.alpha_d = np.zeros(B)
+        self.inf_pr = np.zeros(B)
+        self.inf_du = np.zeros(B)
+        self.inf_compl = np.zeros(B)
+        self.norm_b = np.zeros(B)
+        self.norm_c = np.zeros(B)
+        self.del_w = 0.0
+        self.del_c = 0.0
+        self.k = 0
+        self.iters = np.zeros(B, dtype=np.int64)
+        self.status = [INITIAL] * B
+        self.active = np.ones(B, dtype=np.int32)
+        self.trace = []
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    # ---- solver.jl:127-182 -----------------------------------------------------------------------
+    def initialize(self):
+        opt, ic, h = self.opt, self.ic, self.h
+        B, nx, ns, n, m = self.B, self.nx, self.ns, self.n, self.m
+        X = np.zeros((B, n)); XL = np.zeros((B, n)); XU = np.zeros((B, n))
+        Y = np.zeros((B, m)); RHS = np.zeros((B, m)); COST = np.zeros((B, n))
+        HV = np.zeros((B, self.qps[0].nnzh)); JV = np.zeros((B, self.qps[0].nnzj))
+        tol = opt.bound_relax_factor
+        for b, qp in enumerate(self.qps):
+            # MadNLP.initialize!(cb, x, xl, xu, y, rhs, ind_ineq; tol, bound_push, bound_fac)  (solver.jl:131-142)
+            lvar = qp.lvar - np.maximum(1.0, np.abs(qp.lvar)) * tol
+            uvar = qp.uvar + np.maximum(1.0, np.abs(qp.uvar)) * tol
+            x0 = _push_inside(np.asarray(qp.x0, dtype=float), lvar, uvar, opt.bound_push, opt.bound_fac)
+            cons0 = np.zeros(m)
+            np.add.at(cons0, qp.A_rows, qp.A_vals * x0[qp.A_cols])
+            ls = qp.lcon[ic.ind_ineq] - np.maximum(1.0, np.abs(qp.lcon[ic.ind_ineq])) * tol
+            us = qp.ucon[ic.ind_ineq] + np.maximum(1.0, np.abs(qp.ucon[ic.ind_ineq])) * tol
+            s0 = _push_inside(cons0[ic.ind_ineq], ls, us, opt.bound_push, opt.bound_fac)
+            X[b] = np.concatenate([x0, s0]); XL[b] = np.concatenate([lvar, ls]); XU[b] = np.concatenate([uvar, us])
+            Y[b] = qp.y0
+            RHS[b] = np.where(qp.lcon == qp.ucon, qp.lcon, 0.0)
+            # MadNLP.set_scaling!(..., 100.0)  (solver.jl:148-159)
+            if opt.scaling:
+                rowmax = np.ones(m)
+                np.maximum.at(rowmax, qp.A_rows, np.abs(qp.A_vals))
+                self.con_scale[b] = np.minimum(1.0, 100.0 / rowmax)
+                g0 = qp.c.astype(float).copy()
+                np.add.at(g0, qp.H_rows, qp.H_vals * x0[qp.H_cols])
+                off = qp.H_rows != qp.H_cols
+                np.add.at(g0, qp.H_cols[off], qp.H_vals[off] * x0[qp.H_rows[off]])
+                gmax = float(np.max(np.abs(g0))) if nx else 0.0
+                self.obj_scale[b] = min(1.0, 100.0 / gmax) if gmax > 0 else 1.0
+                cs = self.con_scale[b]
+                Y[b] = Y[b] / cs
+                RHS[b] = RHS[b] * cs
+                X[b, nx:] *= cs[ic.ind_ineq]; XL[b, nx:] *= cs[ic.ind_ineq]; XU[b, nx:] *= cs[ic.ind_ineq]
+            COST[b, :nx] = qp.c * self.obj_scale[b]
+            HV[b] = qp.H_vals * self.obj_scale[b]          # eval_lag_hess_wrapper! (solver.jl:170)
+            JV[b] = qp.A_vals * self.con_scale[b][qp.A_rows]   # eval_jac_wrapper! (solver.jl:167)
+        self._c0 = np.array([qp.c0 for qp in self.qps]) * self.obj_scale
+        for name, arr in (("X", X), ("XL", XL), ("XU", XU), ("Y", Y), ("RHS", RHS), ("COST", COST)):
+            h.vec_set(name, arr)
+            self.h2d_bytes += arr.nbytes
+        for name in ("ZL", "ZU", "JACL"):
+            h.vec_fill(name, 0.0)
+        h.set_values(HV, JV)                                 # compress_jacobian! / compress_hessian!
+        self.h2d_bytes += HV.nbytes + JV.nbytes
+        self.kkt.initialize()                                # solver.jl:162
+        self._init_regularization()                          # solver.jl:163
+        self.obj_val = self._eval_callbacks()                # solver.jl:166-169
+        self.norm_b = np.max(np.abs(RHS), axis=1) if m else np.zeros(B)     # solver.jl:173
+        self.norm_c = h.vec_norm_inf("F")                    # solver.jl:174
+        self.init_starting_point()                           # solver.jl:177
+        self.mu[:] = opt.mu_init                             # solver.jl:179
+
+    def _eval_callbacks(self):
+        # eval_f / eval_cons / eval_grad_f wrappers in one fused device pass (solver.jl:338-340)
+        if self.B == 1:
+            return self.h.eval_model(float(self._c0[0]))
+        return self.h.eval_model(0.0) + self._c0
+
+    def _init_regularization(self):
+        """kernels.jl:380-408."""
+        r = self.opt.regularization
+        self.del_w = 1.0
+        self.del_c = 0.0 if isinstance(r, NoRegularization) else r.delta_d
+        self._reg = None if isinstance(r, NoRegularization) else type(r)(**r.__dict__)
+
+    def _update_regularization(self):
+        """kernels.jl:386-417."""
+        r = self._reg
+        if r is None:
+            self.del_w, self.del_c = 0.0, 0.0
+        elif isinstance(r, FixedRegularization):
+            self.del_w, self.del_c = r.delta_p, r.delta_d
+        else:
+            r.delta_p = max(r.delta_p / 10.0, r.delta_min)
+            r.delta_d = min(r.delta_d / 10.0, -r.delta_min)
+            self.del_w, self.del_c = r.delta_p, r.delta_d
+
+    # ---- linear_solver.jl ------------------------------------------------------------------------
+    def factorize_wrapper(self):
+        """MadNLP.factorize_wrapper!: build_kkt! + factorize!."""
+        self.kkt.build_kkt()
+        return self.kkt.factorize()
+
+    def factorize_regularized_system(self):
+        """/root/reference/src/linear_solver.jl:6-17."""
+        for _ in range(3):
+            self.h.set_aug_diagonal_reg(self.del_w, self.del_c)
+            self.factorize_wrapper()
+            if np.all(self.kkt.is_factorized()[self.active.astype(bool)]):
+                break
+            self.del_w *= 100.0
+            self.del_c *= 100.0
+
+    def solve_system(self):
+        """/root/reference/src/linear_solver.jl:19-45 on (d, p)."""
+        rc, norms = self.h.solve_system("D", "P")
+        ratio = norms[:, 0] / np.maximum(1.0, norms[:, 1])
+        act = self.active.astype(bool)
+        self.last_residual_ratio = ratio
+        if np.any(np.isnan(ratio[act])) or (self.opt.check_residual and np.any(ratio[act] > self.opt.tol_linear_solve)):
+            raise SolveException()
+
+    # ---- solver.jl:6-125 ---------------------------------------------------------------------------
+    def init_starting_point(self):
+        h = self.h
+        h.set_initial_regularization(self.del_w, self.del_c)        # l.16-18
+        self.factorize_wrapper()                                    # l.21
+        h.set_initial_primal_rhs()                                  # l.25
+        self.solve_system()                                         # l.26
+        h.vec_axpy("X", 0, "D", 0, self.n, 1.0)                     # l.28
+        h.set_initial_dual_rhs()                                    # l.31
+        self.solve_system()                                         # l.32
+        h.vec_fill("Y", 0.0)
+        h.vec_axpy("Y", 0, "D", self.n, self.m, 1.0)                # l.33  y .= dual(d)
+        try:
+            h.init_multipliers_and_shift(self.opt.bound_fac)        # l.35-123
+        except MadIPMError as e:
+            if e.code == _lib.INTERNAL:
+                raise AssertionError(str(e))
+            raise
+
+    # ---- kernels.jl:226-236, 307-374 -----------------------------------------------------------------
+    def update_barrier(self, mu_affine, mu_curr):
+        has_inequalities = (self.nlb + self.nub) > 0       # SURVEY note B.1
+        if has_inequalities:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                sigma = np.clip((mu_affine / mu_curr) ** 3, 1e-6, 10.0)
+        else:
+            sigma = np.ones(self.B)
+        self.mu = np.maximum(self.opt.mu_min, sigma * mu_curr)
+
+    def get_fraction_to_boundary_step(self, tau):
+        r = self.h.ratio_test(tau)
+        return np.minimum(r[:, 0], r[:, 1]), np.minimum(r[:, 2], r[:, 3])
+
+    def update_step(self):
+        rule = self.opt.step_rule
+        if isinstance(rule, ConservativeStep):
+            self.alpha_p, self.alpha_d = self.get_fraction_to_boundary_step(rule.tau)
+        elif isinstance(rule, AdaptiveStep):
+            tau = np.maximum(1 - self.mu, rule.tau_min)
+            self.alpha_p, self.alpha_d = self.get_fraction_to_boundary_step(tau)
+        elif isinstance(rule, MehrotraAdaptiveStep):
+            s = self.h.mehrotra_step(rule.gamma_f)
+            self.alpha_p, self.alpha_d = s[:, 0].copy(), s[:, 1].copy()
+        else:
+            raise TypeError(rule)
+
+    def gondzio_correction_direction(self, mu_curr, max_ncorr):
+        """/root/reference/src/solver.jl:200-251 (batch: every instance follows instance-wise accept/reject
+        only when batch == 1; for batch > 1 the correction is kept if all active instances accept it)."""
+        delta, bmin, bmax, tau = 0.1, 0.1, 10.0, 0.995
+        h = self.h
+        alpha_p, alpha_d = self.get_fraction_to_boundary_step(tau)
+        act = self.active.astype(bool)
+        for _ in range(max_ncorr):
+            ta_p = np.minimum(alpha_p + delta, 1.0)
+            ta_d = np.minimum(alpha_d + delta, 1.0)
+            ga = h.complementarity(ta_p, ta_d)[:, 0]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                mu = (ga / mu_curr) ** 2 * ga
+            h.set_extra_correction(ta_p, ta_d, bmin, bmax, mu)
+            h.set_correction_rhs(mu)
+            h.vec_copy("W2", "D")
+            self.solve_system()
+            hp, hd = self.get_fraction_to_boundary_step(tau)
+            if np.any((hp < 1.005 * alpha_p)[act]) or np.any((hd < 1.005 * alpha_d)[act]):
+                h.vec_copy("D", "W2")
+                break
+            alpha_p, alpha_d = hp, hd
+        return alpha_p, alpha_d
+
+    # ---- solver.jl:254-345 -----------------------------------------------------------------------------
+    def mpc(self):
+        opt, h = self.opt, self.h
+        while True:
+            res = h.phase_residuals()                                   # l.259-274
+            self.inf_pr = res[:, 0] / np.maximum(1.0, self.norm_b)
+            self.inf_du = res[:, 1] / np.maximum(1.0, self.norm_c)
+            self.inf_compl = res[:, 2] / np.maximum(1.0, self.norm_c)
+            self.trace.append(dict(k=self.k, obj=(self.obj_val / self.obj_scale).copy(), inf_pr=self.inf_pr.copy(),
+                                   inf_du=self.inf_du.copy(), inf_compl=self.inf_compl.copy(), mu=self.mu.copy(),
+                                   alpha_p=np.array(self.alpha_p, copy=True), alpha_d=np.array(self.alpha_d, copy=True),
+                                   norm_dx=res[:, 3].copy()))
+            err = np.maximum(self.inf_pr, np.maximum(self.inf_du, self.inf_compl))
+            for b in range(self.B):                                     # l.279-283
+                if self.active[b]:
+                    if err[b] <= opt.tol:
+                        self.status[b] = SOLVE_SUCCEEDED; self.active[b] = 0; self.iters[b] = self.k
+                    elif self.k >= opt.max_iter:
+                        self.status[b] = MAXIMUM_ITERATIONS_EXCEEDED; self.active[b] = 0; self.iters[b] = self.k
+            if not self.active.any():
+                return
+            self._update_regularization()                               # l.288
+            self.factorize_regularized_system()                         # l.289
+            h.set_predictive_rhs()                                      # l.294 affine_direction!
+            self.solve_system()
+            aff = h.phase_affine()                                      # l.295-297
+            mu_affine, mu_curr = aff[:, 2], aff[:, 3]
+            self.update_barrier(mu_affine, mu_curr)                     # l.302
+            h.set_correction_rhs(self.mu)                               # l.307-311
+            self.solve_system()
+            if opt.max_ncorr > 0:                                       # l.316-324
+                self.gondzio_correction_direction(mu_curr, opt.max_ncorr)
+            self.update_step()                                          # l.329
+            h.update_iterate(self.alpha_p, self.alpha_d, self.mu,       # l.332-335 and 342
+                             None if self.B == 1 else self.active)
+            obj = self._eval_callbacks()                                # l.338-340
+            act = self.active.astype(bool)
+            self.obj_val = np.where(act, obj, self.obj_val)
+            self.k += 1
+
+    # ---- solver.jl:347-403 -------------------------------------------------------------------------------
+    def solve(self):
+        t0 = time.perf_counter()
+        self.init_time = 0.0
+        try:
+            self.initialize()
+            self.init_time = time.perf_counter() - t0
+            self.mpc()
+        except SolveException:
+            self._fail(ERROR_IN_STEP_COMPUTATION)
+        except AssertionError:
+            self._fail(INTERNAL_ERROR)
+        except MadIPMError as e:
+            if e.code == _lib.CUDA_ERROR:
+                raise
+            self._fail(ERROR_IN_STEP_COMPUTATION if e.code in (_lib.NONFINITE, _lib.FACTOR_BREAKDOWN) else INTERNAL_ERROR)
+        x = self.h.vec_get("X").reshape(self.B, -1)
+        y = self.h.vec_get("Y").reshape(self.B, -1)
+        self.d2h_bytes += x.nbytes + y.nbytes
+        self.total_time = time.perf_counter() - t0
+        return ExecutionStats(
+            status=list(self.status), iter=self.iters.copy(), objective=self.obj_val / self.obj_scale,
+            solution=x[:, :self.nx].copy(), multipliers=y * self.con_scale / self.obj_scale[:, None],
+            inf_pr=self.inf_pr.copy(), inf_du=self.inf_du.copy(), inf_compl=self.inf_compl.copy(),
+            total_time=self.total_time, init_time=self.init_time)
+
+    def _fail(self, status):
+        for b in range(self.B):
+            if self.active[b]:
+                self.status[b] = status
+                self.iters[b] = self.k
+        self.active[:] = 0
+
+    def close(self):
+        self.h.close()
