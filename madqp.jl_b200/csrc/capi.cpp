@@ -112,7 +112,13 @@ int32_t madipm_analyze(madipm_handle* h) {
     o.relax_small = h->cfg.relax_small;
     for (int i = 0; i < 3; ++i) o.relax_zeros[i] = h->cfg.relax_zeros[i];
     o.subtree_work = h->cfg.subtree_work;
-    MADIPM_TRY(h, analyze(h->pat.N, h->pat.kkt_colptr.data(), h->pat.kkt_rowval.data(), o, h->sym));
+    std::vector<uint8_t> delayed;
+    if (h->pat.kind == 0) {   // K2: constraint rows wait for a neighbouring variable (see symbolic.hpp)
+        delayed.assign(h->pat.N, 0);
+        for (int32_t i = h->pat.n_tot; i < h->pat.N; ++i) delayed[i] = 1;
+    }
+    MADIPM_TRY(h, analyze(h->pat.N, h->pat.kkt_colptr.data(), h->pat.kkt_rowval.data(), o, h->sym,
+                          delayed.empty() ? nullptr : delayed.data()));
     h->analyzed = true;
     return MADIPM_OK;
 }

@@ -345,8 +345,10 @@ k_ratio_test(VecView V, const double* __restrict__ d, const double* __restrict__
     const double* dzu = dzl + V.nlb;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     ArgMin a[4];
+    // threads start from the neutral element (+inf, 0); the reference's init (1.0, 0) is applied
+    // once, as the leftmost element, by the finalising block.
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { a[q].v = 1.0; a[q].i = 0; }
+    for (int q = 0; q < 4; ++q) { a[q].v = inf; a[q].i = 0; }
     // each thread owns a CONTIGUOUS chunk so that "earlier/later" is preserved by the tree
     const int top = max(V.nlb, V.nub);
     const int total_threads = gridDim.x * blockDim.x;
@@ -415,9 +417,7 @@ k_ratio_test(VecView V, const double* __restrict__ d, const double* __restrict__
             ArgMin r; r.v = 1.0; r.i = 0;   // the init element is the leftmost
             for (unsigned int b = 0; b < gridDim.x; ++b) {
                 ArgMin e; e.v = __ldcg(base + b * 8 + q); e.i = static_cast<int>(__ldcg(base + b * 8 + 4 + q));
-                // blocks that saw nothing report (1.0, 0): combining keeps semantics (ties -> later, idx 0 harmless
-                // only if no real element tied at 1.0 earlier; guard it)
-                if (e.i != 0 || e.v < r.v) r = argmin_combine(r, e);
+                if (e.i != 0) r = argmin_combine(r, e);   // blocks that saw no element report (+inf, 0)
             }
             out[static_cast<size_t>(inst) * 8 + q] = r.v;
             out[static_cast<size_t>(inst) * 8 + 4 + q] = static_cast<double>(r.i);

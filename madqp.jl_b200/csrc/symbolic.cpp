@@ -2,6 +2,7 @@
 #include "symbolic.hpp"
 
 #include <algorithm>
+#include <climits>
 #include <cstring>
 #include <numeric>
 #include <stdexcept>
@@ -360,7 +361,8 @@ void column_counts(int32_t n, const PermutedPattern& pp, const std::vector<int32
 
 }  // namespace
 
-void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const SymbolicOptions& opt, Symbolic& S) {
+void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const SymbolicOptions& opt, Symbolic& S,
+             const uint8_t* delayed) {
     S = Symbolic();
     S.n = n;
     S.nnz_lower = colptr[n];
@@ -378,7 +380,78 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
         if (perm0[k] < 0 || perm0[k] >= n || ip0[perm0[k]] != -1) throw std::runtime_error("analyze: invalid permutation");
         ip0[perm0[k]] = k;
     }
-
+    // ---- 1b. delay flagged nodes (K2 constraint rows) until just after a partner neighbour.
+    // Partners are DISTINCT (a bipartite matching): at every stage the eliminated constraints then
+    // have a structurally nonsingular block against the eliminated variables, so no pivot is
+    // structurally zero even with delta_c = 0, and no pivot is the bare -1e-8 regularisation.
+    if (delayed) {
+        std::vector<int64_t> dptr(static_cast<size_t>(n) + 1, 0);
+        for (int32_t j = 0; j < n; ++j)
+            for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
+                int32_t i = rowval[p];
+                if (i == j) continue;
+                if (delayed[i] && !delayed[j]) ++dptr[i + 1];
+                if (delayed[j] && !delayed[i]) ++dptr[j + 1];
+            }
+        for (int32_t v = 0; v < n; ++v) dptr[v + 1] += dptr[v];
+        std::vector<int32_t> dadj(dptr[n]);
+        {
+            std::vector<int64_t> at(dptr.begin(), dptr.end() - 1);
+            for (int32_t j = 0; j < n; ++j)
+                for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
+                    int32_t i = rowval[p];
+                    if (i == j) continue;
+                    if (delayed[i] && !delayed[j]) dadj[at[i]++] = j;
+                    if (delayed[j] && !delayed[i]) dadj[at[j]++] = i;
+                }
+        }
+        std::vector<int32_t> dnodes;
+        for (int32_t k = 0; k < n; ++k) if (delayed[perm0[k]]) dnodes.push_back(perm0[k]);   // in elimination order
+        std::vector<int32_t> owner(n, -1), partner(n, -1), seen(n, -1), via(n, -1), queue;
+        for (int32_t v : dnodes) {
+            int32_t best = -1;
+            for (int64_t p = dptr[v]; p < dptr[v + 1]; ++p) {
+                int32_t x = dadj[p];
+                if (owner[x] < 0 && (best < 0 || ip0[x] < ip0[best])) best = x;
+            }
+            if (best >= 0) { owner[best] = v; partner[v] = best; continue; }
+            // augmenting path (breadth first over alternating paths)
+            queue.clear();
+            queue.push_back(v);
+            int32_t found = -1;
+            for (size_t qh = 0; qh < queue.size() && found < 0; ++qh) {
+                int32_t u = queue[qh];
+                for (int64_t p = dptr[u]; p < dptr[u + 1]; ++p) {
+                    int32_t x = dadj[p];
+                    if (seen[x] == v) continue;
+                    seen[x] = v;
+                    via[x] = u;
+                    if (owner[x] < 0) { found = x; break; }
+                    queue.push_back(owner[x]);
+                }
+            }
+            while (found >= 0) {
+                int32_t u = via[found];
+                int32_t prev = partner[u];
+                owner[found] = u;
+                partner[u] = found;
+                found = (u == v) ? -1 : prev;
+            }
+        }
+        std::vector<int64_t> key(n);
+        for (int32_t v = 0; v < n; ++v) {
+            int64_t k = 2 * static_cast<int64_t>(ip0[v]);
+            if (delayed[v] && partner[v] >= 0 && ip0[v] < ip0[partner[v]]) k = 2 * static_cast<int64_t>(ip0[partner[v]]) + 1;
+            key[v] = k;
+        }
+        std::vector<int32_t> order(n);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+            return key[a] < key[b] || (key[a] == key[b] && ip0[a] < ip0[b]);
+        });
+        perm0 = order;
+        for (int32_t k = 0; k < n; ++k) ip0[perm0[k]] = k;
+    }
     // ---- 2. etree + counts in the AMD numbering, then one postorder that puts the
     //         heaviest child last (so it can chain into its parent's supernode)
     {

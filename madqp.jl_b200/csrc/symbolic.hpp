@@ -77,7 +77,13 @@ struct Symbolic {
 };
 
 // lower CSC (0-based): colptr[n+1], rowval sorted ascending in each column, rows >= col.
-void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const SymbolicOptions& opt, Symbolic& out);
+// `delayed` (optional, n flags): nodes that must not be eliminated before at least one of their
+// neighbours.  For the K2 system these are the constraint rows: eliminated first, their pivot
+// would be the bare dual regularisation delta_c (-1e-8, or 0 with the reference's default), which
+// makes LDL' without pivoting inaccurate or impossible; eliminated right after a neighbouring
+// variable x_j the pivot is -delta_c - a_ij^2 / pivot(x_j).
+void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const SymbolicOptions& opt, Symbolic& out,
+             const uint8_t* delayed = nullptr);
 
 // ---- K2 / normal-equations KKT structures -------------------------------------------------
 struct KktPattern {

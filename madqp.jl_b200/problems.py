@@ -85,11 +85,13 @@ def _window_rows(rng, m, n, per_row, half_width, stride):
 
 
 def _finish(name, rng, n, m, A_rows, A_cols, A_vals, H_rows, H_cols, H_vals,
-            upper_fraction, meta):
-    """Pick the KKT point and derive b, c, bounds (SURVEY 8d common rules)."""
+            upper_fraction, meta, bound_rng=None):
+    """Pick the KKT point and derive b, c, bounds (SURVEY 8d common rules).
+    ``bound_rng`` fixes WHICH variables are boxed independently of the values (batch members
+    must share the bound structure as well as the sparsity pattern)."""
     lvar = np.zeros(n)
     uvar = np.full(n, INF)
-    has_ub = rng.random(n) < upper_fraction
+    has_ub = (bound_rng if bound_rng is not None else rng).random(n) < upper_fraction
     uvar[has_ub] = 10.0
 
     x_star = rng.uniform(0.5, 1.5, n)
@@ -272,7 +274,8 @@ def small_qp(instance=0, pattern_seed=0, n=200, m=100, nnz=2000):
     A_vals = _values(rng, A_rows.size)
     H = _banded_q(rng, n, 1)
     return _finish(f"small_qp_{instance}", rng, n, m, A_rows, A_cols, A_vals, *H,
-                   upper_fraction=0.5, meta=dict(config="C5", instance=instance))
+                   upper_fraction=0.5, meta=dict(config="C5", instance=instance),
+                   bound_rng=np.random.default_rng(7_000_003 + pattern_seed))
 
 
 def simple_lp():

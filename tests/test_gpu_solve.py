@@ -1,0 +1,126 @@
+"""GPU parity tests of the whole solve through the C ABI against the CPU oracle (north star: same
+termination status, iterations within +-1, objective to 1e-8 relative), mirroring the reference's own
+tests (/root/reference/test/runtests.jl)."""
+import numpy as np
+import pytest
+
+from madqp_jl_b200 import _lib
+from madqp_jl_b200 import problems as P
+from madqp_jl_b200.mpc import (AdaptiveRegularization, AdaptiveStep, ConservativeStep, FixedRegularization,
+                               MehrotraAdaptiveStep, MPCSolver, NoRegularization)
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_opts(kw):
+    out = {}
+    r = kw.get("regularization")
+    if isinstance(r, NoRegularization):
+        out["regularization"] = ("none",)
+    elif isinstance(r, FixedRegularization):
+        out["regularization"] = ("fixed", r.delta_p, r.delta_d)
+    elif isinstance(r, AdaptiveRegularization):
+        out["regularization"] = ("adaptive", r.delta_p, r.delta_d, r.delta_min)
+    sr = kw.get("step_rule")
+    if isinstance(sr, ConservativeStep):
+        out["step_rule"] = ("conservative", sr.tau)
+    elif isinstance(sr, AdaptiveStep):
+        out["step_rule"] = ("adaptive", sr.tau_min)
+    elif isinstance(sr, MehrotraAdaptiveStep):
+        out["step_rule"] = ("mehrotra", sr.gamma_f)
+    for k in ("kkt_system", "max_ncorr", "tol", "max_iter", "scaling", "mu_min"):
+        if k in kw:
+            out[k] = kw[k]
+    return out
+
+
+def compare(qp, obj_rtol=1e-8, sol_atol=1e-5, **kw):
+    s = MPCSolver(qp, **kw)
+    st = s.solve()
+    ref = O.MPCOracle(qp, perm=s.h.symbolic("PERM"), **oracle_opts(kw)).solve()
+    assert st.status[0] == ref.status, (st.status, ref.status)
+    assert abs(int(st.iter[0]) - ref.k) <= 1, (st.iter, ref.k)
+    assert abs(st.objective[0] - ref.objective) <= obj_rtol * max(1.0, abs(ref.objective))
+    np.testing.assert_allclose(st.solution[0], ref.solution, atol=sol_atol * max(1.0, np.max(np.abs(ref.solution))))
+    # the first iterations follow the same trajectory
+    for a, b in list(zip(s.trace, ref.trace))[:3]:
+        np.testing.assert_allclose(a["inf_pr"][0], b["inf_pr"], rtol=1e-6, atol=1e-12)
+        np.testing.assert_allclose(a["inf_du"][0], b["inf_du"], rtol=1e-6, atol=1e-12)
+        np.testing.assert_allclose(a["mu"][0], b["mu"], rtol=1e-6)
+    assert s.h.launch_count() > 0
+    s.close()
+    return st, ref
+
+
+def test_simple_lp_known_answer(golden):
+    """/root/reference/test/runtests.jl:24-55, 139-180."""
+    st, _ = compare(P.simple_lp(), regularization=NoRegularization())
+    assert abs(st.objective[0] - golden["simple_lp"]["objective"]) <= 1e-8
+    st2, _ = compare(P.simple_lp(), kkt_system="NORMAL")
+    assert abs(st2.objective[0] - st.objective[0]) <= 1e-6           # runtests.jl:175
+    np.testing.assert_allclose(st2.solution, st.solution, atol=1e-6)
+    np.testing.assert_allclose(st2.multipliers, st.multipliers, atol=1e-6)
+
+
+@pytest.mark.parametrize("n,m", [(10, 0), (10, 5), (50, 10), (20, 15)])
+def test_dense_dummy_sizes(n, m):
+    """Sizes of /root/reference/test/runtests.jl:57-73 on seeded instances (DenseDummyQP itself is Julia-RNG)."""
+    qp = P.maros_meszaros_like(seed=n + m, n=n, m=m, nnz=max(m, n * m // 3)) if m else P.maros_meszaros_like(seed=n, n=n, m=1, nnz=3)
+    compare(qp)
+    compare(qp, max_ncorr=5)
+
+
+@pytest.mark.parametrize("rule", [AdaptiveStep(0.99), ConservativeStep(0.99), MehrotraAdaptiveStep(0.99)])
+def test_step_rules(rule):
+    """runtests.jl:80-92."""
+    st, _ = compare(P.inequality_qp(seed=2), step_rule=rule)
+    assert st.status[0] == "SOLVE_SUCCEEDED"
+
+
+@pytest.mark.parametrize("reg", [FixedRegularization(1e-8, -1e-9), AdaptiveRegularization(1e-8, -1e-9, 1e-9)])
+def test_regularisation_variants(reg):
+    """runtests.jl:117-135: regularised == unregularised to 1e-6."""
+    qp = P.inequality_qp(seed=1)
+    base, _ = compare(qp, regularization=NoRegularization())
+    st, _ = compare(qp, regularization=reg)
+    assert abs(st.objective[0] - base.objective[0]) <= 1e-6
+    np.testing.assert_allclose(st.solution, base.solution, atol=1e-6)
+
+
+@pytest.mark.parametrize("maker,kw,opts", [
+    (P.maros_meszaros_like, dict(), dict()),                                                        # C1
+    (P.maros_meszaros_like, dict(seed=1), dict(max_ncorr=3)),
+    (P.banded_qp, dict(n=20000, m=10000), dict()),                                                  # C3 shape
+    (P.sparse_lp, dict(n=4000, m=2000), dict(kkt_system="NORMAL")),                                 # C2 shape
+    (P.sparse_lp, dict(n=4000, m=2000), dict(kkt_system="K2")),
+    (P.transportation_lp, dict(n_src=60, n_dst=80, n_arcs=1500), dict(kkt_system="NORMAL")),        # C4 shape
+    (P.small_qp, dict(instance=3), dict()),                                                         # C5 member
+])
+def test_config_shapes_match_oracle(maker, kw, opts):
+    compare(maker(**kw), regularization=FixedRegularization(1e-8, -1e-8), **opts)
+
+
+@pytest.mark.parametrize("ordering", [_lib.ORDER_AMD, _lib.ORDER_ND, _lib.ORDER_NATURAL])
+def test_orderings_give_the_same_answer(ordering):
+    qp = P.banded_qp(n=3000, m=1500)
+    compare(qp, regularization=FixedRegularization(1e-8, -1e-8), ordering=ordering, nd_leaf=80, subtree_work=20000)
+
+
+def test_max_iter_status():
+    qp = P.maros_meszaros_like(seed=2, n=200, m=100, nnz=800)
+    st, ref = compare(qp, max_iter=3, regularization=FixedRegularization(1e-8, -1e-8))
+    assert st.status[0] == "MAXIMUM_ITERATIONS_EXCEEDED" and int(st.iter[0]) == 3
+
+
+def test_batch_matches_single_solves():
+    """C5: a batch sharing one pattern gives, per instance, what a single solve gives."""
+    qps = [P.small_qp(instance=i) for i in range(6)]
+    sb = MPCSolver(qps, regularization=FixedRegularization(1e-8, -1e-8))
+    stb = sb.solve()
+    for i, qp in enumerate(qps):
+        ref = O.MPCOracle(qp, perm=sb.h.symbolic("PERM"), regularization=("fixed", 1e-8, -1e-8)).solve()
+        assert stb.status[i] == ref.status
+        assert abs(int(stb.iter[i]) - ref.k) <= 1
+        assert abs(stb.objective[i] - ref.objective) <= 1e-8 * max(1.0, abs(ref.objective))
+    sb.close()

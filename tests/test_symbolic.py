@@ -1,0 +1,182 @@
+"""CPU tests of the library's symbolic phase (host code, no GPU): bit-exact against the golden
+fixtures and against the oracle's restatements of the same reference functions."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import ROOT, analyze_handle
+from madqp_jl_b200 import _lib
+from madqp_jl_b200 import problems as P
+from oracle import oracle as O
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "madipm_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(madipm_[a-z0-9_]+)\s*\(", hdr)))
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    assert set(declared) == set(_lib.EXPORTED_SYMBOLS), set(declared) ^ set(_lib.EXPORTED_SYMBOLS)
+
+
+def test_version_string():
+    lib = _lib.load()
+    assert b"sm_100a" in lib.madipm_version()
+
+
+def test_bad_arguments_are_reported_not_thrown():
+    h = _lib.Handle()
+    with pytest.raises(_lib.MadIPMError) as e:
+        h.analyze()                      # before set_pattern
+    assert e.value.code == _lib.BAD_ARGUMENT
+    with pytest.raises(_lib.MadIPMError):
+        h.set_pattern_k2(2, 1, [], [], [5], [1], [])      # row index out of range
+    h2 = _lib.Handle(kkt_kind=_lib.KKT_NORMAL)
+    with pytest.raises(_lib.MadIPMError):
+        h2.set_pattern_k2(2, 1, [], [], [1], [1], [])     # wrong kind for this handle
+
+
+def test_numeric_calls_fail_loudly_without_gpu():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    h, _ = analyze_handle(P.simple_lp())
+    with pytest.raises(_lib.MadIPMError) as e:
+        h.vec_fill("X", 0.0)
+    assert e.value.code == _lib.CUDA_ERROR and "no CPU fallback" in str(e.value)
+
+
+def test_csr_map_and_normal_pattern_golden(golden):
+    """S1/S2/S3 through the C ABI against the fixtures (0-based getters vs 1-based fixtures)."""
+    for c in golden["sparse_cases"]:
+        if "Cp" not in c or len(c["I"]) == 0:
+            continue
+        m, n = c["m"], c["n"]
+        h = _lib.Handle(kkt_kind=_lib.KKT_NORMAL, ordering=_lib.ORDER_NATURAL)
+        h.set_pattern_normal(n, m, c["I"], c["J"], [])
+        assert (h.symbolic("A_ROWPTR") + 1).tolist() == c["Bp"]
+        assert (h.symbolic("A_COLIND") + 1).tolist() == c["Bj"]
+        assert (h.symbolic("A_CSR_MAP") + 1).tolist() == c["order"]
+        assert (h.symbolic("KKT_COLPTR") + 1).tolist() == c["Cp"]
+        assert (h.symbolic("KKT_ROWVAL") + 1).tolist() == c["Cj"]
+        # product lists reproduce tril(A D A') exactly
+        Bx = np.array(c["Bx"]); D = np.array(c["D"])
+        pp, pa, pb, pk = (h.symbolic(k) for k in ("PROD_PTR", "PROD_A", "PROD_B", "PROD_K"))
+        Cx = [float(sum((Bx[pa[t]] * D[pk[t]]) * Bx[pb[t]] for t in range(pp[e], pp[e + 1]))) for e in range(len(c["Cj"]))]
+        assert Cx == c["Cx"]
+
+
+@pytest.mark.parametrize("maker,kw", [(P.sparse_lp, dict(n=400, m=200)), (P.transportation_lp, dict(n_src=30, n_dst=40, n_arcs=300))])
+def test_normal_pattern_matches_oracle_scan(maker, kw):
+    """S3 by column lists == the reference's O(m nnz) scan (oracle restatement), bit for bit."""
+    qp = maker(**kw)
+    h, _ = analyze_handle(qp, "NORMAL")
+    Ap, Aj, _ = O.coo_to_csr(qp.ncon, qp.nvar, (qp.A_rows + 1).astype(np.int32), (qp.A_cols + 1).astype(np.int32),
+                             np.ones(qp.nnzj))
+    Cp, Cj = O.build_normal_system(qp.ncon, qp.nvar, Ap, Aj)
+    assert np.array_equal(h.symbolic("KKT_COLPTR") + 1, Cp) and np.array_equal(h.symbolic("KKT_ROWVAL") + 1, Cj)
+    assert np.array_equal(h.symbolic("A_ROWPTR") + 1, Ap) and np.array_equal(h.symbolic("A_COLIND") + 1, Aj)
+
+
+@pytest.mark.parametrize("qp", [P.inequality_qp(seed=0), P.maros_meszaros_like(n=120, m=60, nnz=400)])
+def test_k2_pattern_matches_oracle(qp):
+    """S4: aug COO block order + coo_to_csc map == the oracle's restatement."""
+    h, ic = analyze_handle(qp, "K2")
+    o = O.MPCOracle(qp)
+    assert np.array_equal(h.symbolic("KKT_COLPTR") + 1, o.aug_colptr)
+    assert np.array_equal(h.symbolic("KKT_ROWVAL") + 1, o.aug_rowval)
+    assert np.array_equal(h.symbolic("AUG_CSC_MAP") + 1, o.aug_csc_map)
+    assert np.array_equal(h.symbolic("A_CSR_MAP") + 1, o.A_csr_map)
+    info = h.info()
+    assert info["n_slack"] == ic.ind_ineq.size and info["kkt_order"] == qp.nvar + ic.ind_ineq.size + qp.ncon
+
+
+@pytest.mark.parametrize("ordering", [_lib.ORDER_AMD, _lib.ORDER_ND, _lib.ORDER_NATURAL])
+@pytest.mark.parametrize("maker,kw,kkt", [
+    (P.banded_qp, dict(n=3000, m=1500), "K2"),
+    (P.maros_meszaros_like, dict(n=300, m=150, nnz=1500), "K2"),
+    (P.sparse_lp, dict(n=2000, m=1000), "NORMAL"),
+    (P.simple_lp, {}, "K2"),
+])
+def test_symbolic_factorisation_is_exact(ordering, maker, kw, kkt):
+    """Given the library's permutation, its etree and column counts equal the oracle's
+    LDL symbolic phase bit for bit; the supernodal structure covers exactly the pattern of L."""
+    qp = maker(**kw)
+    h, _ = analyze_handle(qp, kkt, ordering=ordering, nd_leaf=64)
+    info = h.info()
+    N = info["kkt_order"]
+    perm = h.symbolic("PERM")
+    assert np.array_equal(np.sort(perm), np.arange(N))
+    cp, ri = h.symbolic("KKT_COLPTR"), h.symbolic("KKT_ROWVAL")
+    s = O.LDLSolver(N, (cp + 1).astype(np.int32), (ri + 1).astype(np.int32), np.ones(ri.size), perm)
+    assert np.array_equal(h.symbolic("ETREE_PARENT"), s.parent)
+    assert np.array_equal(h.symbolic("COLCOUNT"), s.colcount)
+    assert info["nnz_L"] == s.nnz_L and info["factor_flops"] == s.flops
+    # supernodes: partition of the columns, rows sorted, own columns first, exact cover of L's pattern
+    first, rp, rows = h.symbolic("SUPER_FIRST"), h.symbolic("SUPER_ROWPTR"), h.symbolic("SUPER_ROWS")
+    assert first[0] == 0 and first[-1] == N and np.all(np.diff(first) > 0)
+    # pattern of L from the oracle's numeric factor of a diagonally dominant matrix with that pattern
+    iperm = np.empty(N, dtype=np.int64); iperm[perm] = np.arange(N)
+    col_of = np.repeat(np.arange(N), np.diff(cp))
+    vals = np.where(ri == col_of, 4.0 * N, 1e-3)
+    s2 = O.LDLSolver(N, (cp + 1).astype(np.int32), (ri + 1).astype(np.int32), vals, perm)
+    assert s2.factorize()
+    lcols = [set() for _ in range(N)]
+    for j in range(N):
+        lcols[j] = set(s2.Li[s2.Lp[j]:s2.Lp[j + 1]].tolist())
+    for sn in range(first.size - 1):
+        r = rows[rp[sn]:rp[sn + 1]]
+        w = first[sn + 1] - first[sn]
+        assert np.array_equal(r[:w], np.arange(first[sn], first[sn + 1])) and np.all(np.diff(r) > 0)
+        for k, j in enumerate(range(first[sn], first[sn + 1])):
+            assert lcols[j] <= set(r[k + 1:].tolist())      # relaxed supernodes may hold extra (zero) rows
+    # assembly map: injective, and lands on the (row, col) it claims
+    amap, xoff = h.symbolic("ASM_MAP"), h.symbolic("SUPER_XOFF")
+    assert np.unique(amap).size == amap.size
+    sn_of = np.repeat(np.arange(first.size - 1), np.diff(first))
+    for p in np.random.default_rng(0).integers(0, amap.size, min(200, amap.size)):
+        a, b = iperm[ri[p]], iperm[col_of[p]]
+        r, c = max(a, b), min(a, b)
+        sn = sn_of[c]
+        hgt = rp[sn + 1] - rp[sn]
+        off = amap[p] - xoff[sn]
+        assert off // hgt == c - first[sn] and rows[rp[sn] + off % hgt] == r
+
+
+def test_fill_is_comparable_to_scipy_minimum_degree():
+    """Ordering quality sanity check: AMD / ND fill within 1.6x of SuperLU's MMD(A'+A)."""
+    from scipy.sparse.linalg import splu
+    qp = P.banded_qp(n=4000, m=2000)
+    h, _ = analyze_handle(qp, "K2", ordering=_lib.ORDER_AMD)
+    cp, ri = h.symbolic("KKT_COLPTR"), h.symbolic("KKT_ROWVAL")
+    N = h.info()["kkt_order"]
+    col_of = np.repeat(np.arange(N), np.diff(cp))
+    K = sp.csc_matrix((np.where(ri == col_of, 1e3, 1.0), (ri, col_of)), shape=(N, N))
+    K = K + sp.tril(K, -1).T
+    lu = splu(K.tocsc(), permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.0, options=dict(SymmetricMode=True))
+    assert h.info()["nnz_L"] <= 1.6 * lu.L.nnz
+    h2, _ = analyze_handle(qp, "K2", ordering=_lib.ORDER_ND, nd_leaf=128)
+    assert h2.info()["nnz_L"] <= 3.0 * lu.L.nnz
+    assert h2.info()["n_levels"] < h.info()["n_levels"]          # the reason ND is the default
+
+
+def test_schedule_covers_every_supernode_once():
+    qp = P.banded_qp(n=6000, m=3000)
+    h, _ = analyze_handle(qp, "K2", subtree_work=50_000, nd_leaf=100)
+    level, parent = h.symbolic("SUPER_LEVEL"), h.symbolic("SUPER_PARENT")
+    info = h.info()
+    assert info["n_subtrees"] > 1 and info["n_levels"] >= 1
+    for s, p in enumerate(parent):
+        if p >= 0:
+            assert p > s                                      # postorder
+            if level[s] > 0:
+                assert level[p] > level[s]                    # a top node's parent is on a later level
+            else:
+                assert level[p] >= 0
