@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 KKT hot-path backend (contract: see DESIGN.md section 6).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C3|C2|C1|C5]
+
+One "step" is one full interior-point solve (initialize! + mpc!, to max(inf_pr, inf_du, inf_compl) <= 1e-8)
+of the named synthetic workload.  The metric is IPM iterations per second (BASELINE.json); ms_per_step is
+the time-to-1e-8 of one solve.
+
+  value  : device-resident -- the solve's inputs (iterate, bounds, rhs, cost, Jacobian/Hessian values, symbolic
+           structures) are already in HBM when the timed region starts; CUDA events on the solver's stream.
+  e2e    : the same solve through the public API (MPCSolver.solve) from HOST buffers: host->device copy of that
+           step's inputs and device->host read of the solution inside the timed region.
+  N > 1  : one process per GPU; a single solve does not shard (DESIGN.md "replicas only"), so every rank solves
+           its own replica of the workload (weak scaling); --workload C5 shards the batch of independent QPs
+           across the ranks instead and gathers the per-instance status with one NCCL all_gather.
+
+--impl reference times the restated CPU path of the reference (oracle/, scalar up-looking LDL', one thread)
+on a bounded sample of the same workload; it never touches the GPU.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from madqp_jl_b200 import problems  # noqa: E402
+
+METRIC, UNIT = "ipm_iters_per_sec", "iter/s"
+
+
+def make_workload(name, scale=1.0, seed=0):
+    s = scale
+    if name == "C3":
+        qp = problems.banded_qp(seed=seed, n=int(500_000 * s), m=int(250_000 * s))
+        return [qp], "K2", "C3: synthetic convex QP n=500k m=250k, 1M nnz A + pentadiagonal Q, K2 augmented LDL'"
+    if name == "C2":
+        qp = problems.sparse_lp(seed=seed, n=int(200_000 * s), m=int(100_000 * s))
+        return [qp], "NORMAL", "C2: synthetic sparse LP n=200k m=100k, 1M nnz, normal-equations Cholesky"
+    if name == "C1":
+        return [problems.maros_meszaros_like(seed=seed)], "K2", "C1: Maros-Meszaros-shaped QP n=1k m=500"
+    if name == "C4":
+        k = max(1, int(25_000 * s))
+        qp = problems.transportation_lp(seed=seed, n_src=k, n_dst=k, n_arcs=int(2_000_000 * s))
+        return [qp], "NORMAL", "C4: transportation LP"
+    if name == "C5":
+        nb = max(1, int(4096 * s))
+        return [problems.small_qp(instance=i) for i in range(nb)], "K2", f"C5: batch of {nb} independent QPs n=200 m=100"
+    raise SystemExit(f"unknown workload {name}")
+
+
+def solver_options():
+    """SURVEY 8d 'Solver options for timing' (the reference's benchmark settings, max_ncorr = 0)."""
+    from madqp_jl_b200.mpc import AdaptiveStep, FixedRegularization
+    return dict(tol=1e-8, max_iter=300, scaling=True, step_rule=AdaptiveStep(0.995),
+                regularization=FixedRegularization(1e-8, -1e-8), max_ncorr=0)
+
+
+ORACLE_OPTIONS = dict(tol=1e-8, max_iter=300, scaling=True, step_rule=("adaptive", 0.995),
+                      regularization=("fixed", 1e-8, -1e-8), max_ncorr=0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(sm))
+
+
+def cpu_perm(qp, kkt):
+    """Fill-reducing permutation for the CPU baseline: AMD (what the reference's LDLFactorizations uses) with
+    the same constraint-delay rule; computed by the library's HOST-side ordering code, no GPU involved."""
+    from madqp_jl_b200 import _lib
+    from madqp_jl_b200.mpc import get_index_constraints
+    ic = get_index_constraints(qp.lvar, qp.uvar, qp.lcon, qp.ucon)
+    h = _lib.Handle(kkt_kind=_lib.KKT_K2 if kkt == "K2" else _lib.KKT_NORMAL, ordering=_lib.ORDER_AMD)
+    if kkt == "K2":
+        h.set_pattern_k2(qp.nvar, qp.ncon, qp.H_rows + 1, qp.H_cols + 1, qp.A_rows + 1, qp.A_cols + 1, ic.ind_ineq + 1)
+    else:
+        h.set_pattern_normal(qp.nvar, qp.ncon, qp.A_rows + 1, qp.A_cols + 1, ic.ind_ineq + 1)
+    h.set_bounds_index(ic.ind_lb + 1, ic.ind_ub + 1)
+    info = h.analyze()
+    perm = h.symbolic("PERM")
+    h.close()
+    return perm, info
+
+
+def cpu_sample(qp, kkt, budget_s, max_sample_iters=None):
+    """Restated reference CPU path (oracle) on a bounded sample: initialize! plus as many mpc! iterations as fit
+    in ~budget_s seconds.  Returns (iterations per second over the sample, description)."""
+    from oracle import oracle as O
+    perm, info = cpu_perm(qp, kkt)
+    o = O.MPCOracle(qp, perm=perm, kkt_system=kkt, **ORACLE_OPTIONS)
+    t0 = time.perf_counter()
+    o.initialize()
+    t_init = time.perf_counter() - t0
+    # one iteration to calibrate, then the number that fits the budget
+    o.opt.max_iter = 1
+    t1 = time.perf_counter()
+    status = o.mpc()
+    t_one = time.perf_counter() - t1
+    n_more = int(max(0, min(300 - 1, (budget_s - t_init - t_one) / max(t_one, 1e-9))))
+    if max_sample_iters is not None:
+        n_more = min(n_more, max_sample_iters - 1)
+    if status != O.SOLVE_SUCCEEDED and n_more > 0:
+        o.opt.max_iter = 1 + n_more
+        status = o.mpc()
+    total = time.perf_counter() - t0
+    iters = o.k
+    done = status == O.SOLVE_SUCCEEDED
+    desc = (f"oracle (restated reference CPU path: scalar up-looking LDL', AMD ordering, 1 thread): initialize! + {iters} "
+            f"mpc! iterations of the same workload in {total:.1f} s" + (" (ran to convergence)" if done else " (bounded sample)")
+            + f"; nnz(L)={info['nnz_L']}, factor flops={info['factor_flops']:.3g}")
+    return iters / total, desc, dict(iters=iters, seconds=total, converged=done, t_factor=o.t_factor, n_factor=o.n_factor)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    qps, kkt, wname = make_workload(args.workload, args.scale)
+    qp = qps[0]
+    per_step = []
+    detail = None
+    for step in range(args.warmup + args.steps):
+        ips, desc, detail = cpu_sample(qp, kkt, budget_s=args.cpu_budget, max_sample_iters=args.cpu_iters)
+        if step >= args.warmup:
+            per_step.append((ips, detail["seconds"]))
+    value = float(np.mean([p[0] for p in per_step]))
+    line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=float(np.mean([p[1] for p in per_step]) * 1e3), higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload=wname, kkt=kkt, n=qp.nvar, m=qp.ncon, nnz_A=qp.nnzj, nnz_Q=qp.nnzh,
+                            note="each step is a bounded sample (initialize! + a fixed number of mpc! iterations)"),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=1, kind="port", sample=desc),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0, detail=detail)
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from madqp_jl_b200.mpc import MPCSolver
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this benchmark has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    qps, kkt, wname = make_workload(args.workload, args.scale)
+    sharded = args.workload == "C5" and world > 1
+    if sharded:   # independent instances: rank r takes a contiguous slice, no data-path collective
+        per = (len(qps) + world - 1) // world
+        qps = qps[rank * per:(rank + 1) * per]
+    solver = MPCSolver(qps if len(qps) > 1 else qps[0], kkt_system=kkt, device=local, **solver_options())
+    solver.keep_snapshot = True
+    h = solver.h
+    info = solver.info
+
+    # ---- warm-up (full end-to-end solves)
+    stats = None
+    for _ in range(max(args.warmup, 1)):
+        stats = solver.solve()
+    iters_per_solve = float(np.sum(stats.iter))
+    ok = all(s == "SOLVE_SUCCEEDED" for s in stats.status)
+    sstream = torch.cuda.ExternalStream(h.stream(), device=torch.device("cuda", local))
+
+    def timed(resident):
+        h.profile(2)
+        h.profile_read(reset=True)
+        launches0 = h.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.perf_counter()
+        e0.record(sstream)
+        it = 0.0
+        for _ in range(args.steps):
+            st = solver.solve(resident=resident)
+            it += float(np.sum(st.iter))
+        e1.record(sstream)
+        barrier()
+        wall = time.perf_counter() - t0
+        dev_ms = e0.elapsed_time(e1)
+        prof = h.profile_read(reset=True)
+        h.profile(0)
+        t = torch.tensor([dev_ms / 1e3, wall, it], dtype=torch.float64, device="cuda")
+        if world > 1:
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            tsum = t.clone()
+            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            sec, wall, it = float(tmax[0]), float(tmax[1]), float(tsum[2])
+        else:
+            sec, it = float(t[0]), float(t[2])
+        return dict(sec=sec, wall=wall, iters=it, launches=h.launch_count() - launches0, prof=prof, stats=st)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    res = timed(resident=True)
+    e2e = timed(resident=False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- gather per-instance status (the only collective on the path)
+    if world > 1:
+        status_code = torch.tensor([1.0 if s == "SOLVE_SUCCEEDED" else 0.0 for s in res["stats"].status], dtype=torch.float64, device="cuda")
+        gathered = [torch.zeros_like(status_code) for _ in range(world)]
+        dist.all_gather(gathered, status_code)
+        ok = ok and bool(torch.cat(gathered).min().item() == 1.0)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
+        # dominant kernel: k_factor_subtrees.  Algorithmic bytes per launch:
+        # every panel entry is read and written once (16 B), the KKT values enter once (8 B + 8 B map).
+        prof = res["prof"]
+        sub_ms, sub_calls = prof["factor_subtrees"]
+        fac_ms, fac_calls = prof["factor"]
+        B = len(qps)
+        alg_bytes = 16.0 * info["nnz_stored"] * B
+        sub_avg_s = (sub_ms / max(sub_calls, 1)) / 1e3
+        achieved = alg_bytes / sub_avg_s / 1e9 if sub_avg_s > 0 else 0.0
+        roofline = dict(bound="hbm", kernel="k_factor_subtrees", achieved=achieved, peak=hbm_peak, unit="GB/s",
+                        frac=achieved / hbm_peak, traffic=None, peak_source=peak_src,
+                        algorithmic_bytes_per_launch=alg_bytes, avg_launch_ms=sub_avg_s * 1e3, launches=sub_calls,
+                        share_of_step=sub_ms / 1e3 / res["sec"] if res["sec"] > 0 else None,
+                        factor_phase_ms_avg=fac_ms / max(fac_calls, 1),
+                        factor_tflops=info["factor_flops"] * B / ((fac_ms / max(fac_calls, 1)) / 1e3) / 1e12 if fac_ms > 0 else None)
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            roofline["traffic"] = traffic.get("k_factor_subtrees_dram_bytes_per_launch")
+        except (OSError, ValueError):
+            pass
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            v, desc, _ = cpu_sample(qps[0], kkt, budget_s=args.cpu_budget)
+            cpu = dict(value=v, unit=UNIT, cores=1, kind="port", sample=desc)
+        n_rep = world if not sharded else 1
+        line = dict(
+            metric=METRIC, value=res["iters"] / res["sec"], unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+            ms_per_step=res["sec"] / args.steps * 1e3, higher_is_better=True,
+            scaling="strong" if sharded else "weak", vs_baseline=None, dtype="f64", data="synthetic",
+            config=dict(workload=wname, kkt=kkt, n=qps[0].nvar, m=qps[0].ncon, nnz_A=qps[0].nnzj, nnz_Q=qps[0].nnzh,
+                        instances_per_gpu=len(qps), replicas=n_rep, kkt_order=info["kkt_order"], nnz_L=info["nnz_L"],
+                        factor_flops=info["factor_flops"], nsuper=info["nsuper"], n_subtrees=info["n_subtrees"],
+                        n_levels=info["n_levels"], ordering="nested dissection + AMD leaves, constraints delayed",
+                        options="tol=1e-8 max_iter=300 AdaptiveStep(0.995) FixedRegularization(1e-8,-1e-8) scaling max_ncorr=0",
+                        l2="inputs larger than L2: factor panels %.0f MB + operators, no flush" % (info["nnz_stored"] * 8 / 1e6),
+                        parallelism="replicas only (one solve per GPU)" if not sharded else f"batch sharded {world} ways"),
+            clocks=clocks,
+            e2e=dict(value=e2e["iters"] / e2e["wall"], unit=UNIT, h2d_bytes_per_step=int(solver.h2d_bytes),
+                     d2h_bytes_per_step=int(solver.d2h_bytes), ms_per_step=e2e["wall"] / args.steps * 1e3),
+            gpu_launches=int(res["launches"]),
+            roofline=roofline, cpu_baseline=cpu,
+            iterations_per_solve=iters_per_solve, time_to_tol_s=res["sec"] / args.steps, converged=ok,
+            analysis_s=solver.analysis_time, wall_s_resident=res["wall"],
+        )
+        print(json.dumps(line), flush=True)
+    solver.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (development only)")
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the oracle sample")
+    ap.add_argument("--cpu-iters", type=int, default=None)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

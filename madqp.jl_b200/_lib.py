@@ -30,7 +30,7 @@ SYM = dict(PERM=0, ETREE_PARENT=1, COLCOUNT=2, SUPER_FIRST=3, SUPER_PARENT=4, SU
            SUPER_XOFF=7, ASM_MAP=8, KKT_COLPTR=9, KKT_ROWVAL=10, AUG_CSC_MAP=11, A_ROWPTR=12, A_COLIND=13,
            A_CSR_MAP=14, SUPER_LEVEL=15, PROD_PTR=16, PROD_A=17, PROD_B=18, PROD_K=19)
 
-T_CLASSES = ["assembly", "factor", "solve", "spmv", "vector"]
+T_CLASSES = ["assembly", "factor", "solve", "spmv", "vector", "factor_subtrees"]
 
 
 class MadIPMError(RuntimeError):
@@ -109,6 +109,8 @@ _SIGNATURES = {
     "madipm_vec_copy": ([C.c_int32, C.c_int32], C.c_int32),
     "madipm_vec_axpy": ([C.c_int32, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_double], C.c_int32),
     "madipm_vec_norm_inf": ([C.c_int32, _PD], C.c_int32),
+    "madipm_snapshot_inputs": ([], C.c_int32),
+    "madipm_restore_inputs": ([], C.c_int32),
     "madipm_launch_count": ([], C.c_int64),
     "madipm_profile": ([C.c_int32], C.c_int32),
     "madipm_profile_read": ([_PD, _P64, C.c_int32], C.c_int32),
@@ -385,12 +387,19 @@ class Handle:
     def init_multipliers_and_shift(self, bound_fac):
         self._check(self.lib.madipm_init_multipliers_and_shift(self._h, bound_fac))
 
+    def snapshot_inputs(self):
+        self._check(self.lib.madipm_snapshot_inputs(self._h))
+
+    def restore_inputs(self):
+        self._check(self.lib.madipm_restore_inputs(self._h))
+
     # -- measurement
     def launch_count(self):
         return int(self.lib.madipm_launch_count(self._h))
 
-    def profile(self, enable=True):
-        self._check(self.lib.madipm_profile(self._h, int(enable)))
+    def profile(self, level=1):
+        """1: every class with a sync per call (diagnostics); 2: factorisation only, no extra sync; 0: off."""
+        self._check(self.lib.madipm_profile(self._h, int(level)))
 
     def profile_read(self, reset=True):
         ms = np.zeros(len(T_CLASSES))

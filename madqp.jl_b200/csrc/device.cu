@@ -48,6 +48,7 @@ struct DeviceState {
     double* vec[MADIPM_VEC_COUNT] = {};
     int64_t veclen[MADIPM_VEC_COUNT] = {};
     double *buffer_n = nullptr, *buffer_m = nullptr;
+    double* snap[4] = {nullptr, nullptr, nullptr, nullptr};   // device copies of X, XL, XU, Y
 
     double* red_scratch = nullptr;
     unsigned int* red_counter = nullptr;
@@ -57,8 +58,8 @@ struct DeviceState {
     double* h_out = nullptr;   // pinned
 
     bool values_set = false;
-    bool profiling = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int profiling = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     double t_ms[MADIPM_T_COUNT] = {};
     int64_t t_calls[MADIPM_T_COUNT] = {};
 };
@@ -133,11 +134,11 @@ struct Timer {
     madipm_handle* h;
     int cls;
     Timer(madipm_handle* hh, int c) : h(hh), cls(c) {
-        if (h->dev->profiling) cudaEventRecord(h->dev->ev0, h->dev->stream);
+        if (h->dev->profiling == 1) cudaEventRecord(h->dev->ev0, h->dev->stream);
     }
     ~Timer() {
         DeviceState* d = h->dev;
-        if (d->profiling) {
+        if (d->profiling == 1) {
             cudaEventRecord(d->ev1, d->stream);
             cudaEventSynchronize(d->ev1);
             float ms = 0;
@@ -275,6 +276,8 @@ int32_t device_create(madipm_handle* h) {
     CUDA_OK(h, cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
     CUDA_OK(h, cudaEventCreate(&d->ev0));
     CUDA_OK(h, cudaEventCreate(&d->ev1));
+    CUDA_OK(h, cudaEventCreate(&d->ev2));
+    CUDA_OK(h, cudaEventCreate(&d->ev3));
     const KktPattern& p = h->pat;
     const Symbolic& s = h->sym;
     if (p.A_rowptr.back() > INT32_MAX || p.kkt_colptr.back() > INT32_MAX || (int64_t)s.sn_rows.size() > INT32_MAX ||
@@ -386,6 +389,8 @@ void device_destroy(madipm_handle* h) {
     if (d->h_out) cudaFreeHost(d->h_out);
     if (d->ev0) cudaEventDestroy(d->ev0);
     if (d->ev1) cudaEventDestroy(d->ev1);
+    if (d->ev2) cudaEventDestroy(d->ev2);
+    if (d->ev3) cudaEventDestroy(d->ev3);
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d;
     h->dev = nullptr;
@@ -572,21 +577,33 @@ int32_t madipm_factorize(madipm_handle* h, int32_t* n_failed) {
     if (rc) return rc;
     DeviceState* d = h->dev;
     const int B = d->B;
+    const bool light = d->profiling == 2;
     {
         Timer t(h, MADIPM_T_FACTOR);
+        if (light) cudaEventRecord(d->ev0, d->stream);
         CUDA_OK(h, cudaMemsetAsync(d->Lx, 0, sizeof(double) * B * d->lx_stride, d->stream));
         CUDA_OK(h, cudaMemsetAsync(d->fail, 0, sizeof(int) * B, d->stream));
         LAUNCH(h, k_assemble_panels, dim3(vec_blocks(d->kkt_nnz) * 4, B), kVecThreads, 0, d->kkt_nnz, d->asm_map,
                d->vec[MADIPM_VEC_KKT_NZVAL], d->kkt_nnz, d->Lx, d->lx_stride);
         FactorView F = make_factor_view(*d);
+        if (light) cudaEventRecord(d->ev2, d->stream);
         if (d->n_subtrees > 0)
             LAUNCH(h, k_factor_subtrees, dim3(d->n_subtrees, B), 128, d->factor_smem, F, d->sub_first, d->sub_last);
+        if (light) cudaEventRecord(d->ev3, d->stream);
         for (int l = 0; l < d->n_levels; ++l) {
             int cnt = d->level_ptr[l + 1] - d->level_ptr[l];
             LAUNCH(h, k_factor_level, dim3(cnt, B), 256, d->factor_smem, F, d->level_sn + d->level_ptr[l]);
         }
+        if (light) cudaEventRecord(d->ev1, d->stream);
         CUDA_OK(h, cudaMemcpyAsync(d->h_fail.data(), d->fail, sizeof(int) * B, cudaMemcpyDeviceToHost, d->stream));
         CUDA_OK(h, cudaStreamSynchronize(d->stream));
+        if (light) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, d->ev0, d->ev1);
+            d->t_ms[MADIPM_T_FACTOR] += ms; d->t_calls[MADIPM_T_FACTOR] += 1;
+            cudaEventElapsedTime(&ms, d->ev2, d->ev3);
+            d->t_ms[MADIPM_T_FACTOR_SUBTREES] += ms; d->t_calls[MADIPM_T_FACTOR_SUBTREES] += 1;
+        }
     }
     CUDA_OK(h, cudaGetLastError());
     int bad = 0;
@@ -933,11 +950,37 @@ int32_t madipm_init_multipliers_and_shift(madipm_handle* h, double bound_fac) {
     return MADIPM_OK;
 }
 
+// ---- device-resident inputs -----------------------------------------------------------------------
+static const int kSnapVec[4] = {MADIPM_VEC_X, MADIPM_VEC_XL, MADIPM_VEC_XU, MADIPM_VEC_Y};
+
+int32_t madipm_snapshot_inputs(madipm_handle* h) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    for (int k = 0; k < 4; ++k) {
+        const size_t bytes = sizeof(double) * d->B * d->veclen[kSnapVec[k]];
+        if (!d->snap[k] && (rc = dev_alloc(h, &d->snap[k], static_cast<size_t>(d->B) * d->veclen[kSnapVec[k]]))) return rc;
+        CUDA_OK(h, cudaMemcpyAsync(d->snap[k], d->vec[kSnapVec[k]], bytes, cudaMemcpyDeviceToDevice, d->stream));
+    }
+    return MADIPM_OK;
+}
+
+int32_t madipm_restore_inputs(madipm_handle* h) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (!d->snap[0]) { h->error = "restore_inputs before snapshot_inputs"; return MADIPM_BAD_ARGUMENT; }
+    for (int k = 0; k < 4; ++k)
+        CUDA_OK(h, cudaMemcpyAsync(d->vec[kSnapVec[k]], d->snap[k], sizeof(double) * d->B * d->veclen[kSnapVec[k]],
+                                   cudaMemcpyDeviceToDevice, d->stream));
+    return MADIPM_OK;
+}
+
 // ---- measurement hooks ----------------------------------------------------------------------------
 int32_t madipm_profile(madipm_handle* h, int32_t enable) {
     int32_t rc = check(h);
     if (rc) return rc;
-    h->dev->profiling = enable != 0;
+    h->dev->profiling = enable;
     return MADIPM_OK;
 }
 
