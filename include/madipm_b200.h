@@ -92,6 +92,8 @@ typedef struct {
     int32_t n_subtrees, n_levels;
     int64_t n_products;      /* normal equations: length of the product lists */
     int64_t kkt_vec_len;     /* n_tot + ncon + nlb + nub: length of an UnreducedKKTVector */
+    int32_t n_subtrees_small;   /* subtrees whose panels all fit the high-occupancy launch */
+    int32_t subtree_max_panel;  /* largest panel (doubles) inside a subtree */
 } madipm_info;
 int32_t madipm_get_info(const madipm_handle* h, madipm_info* out);
 

@@ -50,7 +50,8 @@ class Info(C.Structure):
                 + [(n, C.c_int64) for n in "nnzh nnzj kkt_nnz aug_coo_len nnz_L nnz_stored".split()]
                 + [("factor_flops", C.c_double)]
                 + [(n, C.c_int32) for n in "nsuper max_height max_width n_subtrees n_levels".split()]
-                + [("n_products", C.c_int64), ("kkt_vec_len", C.c_int64)])
+                + [("n_products", C.c_int64), ("kkt_vec_len", C.c_int64), ("n_subtrees_small", C.c_int32),
+                   ("subtree_max_panel", C.c_int32)])
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -142,6 +142,8 @@ int32_t madipm_get_info(const madipm_handle* h, madipm_info* out) {
     out->aug_coo_len = static_cast<int64_t>(p.aug_csc_map.size());
     out->n_products = static_cast<int64_t>(p.prod_a.size());
     out->kkt_vec_len = static_cast<int64_t>(p.n_tot) + p.m + h->nlb + h->nub;
+    out->n_subtrees_small = h->analyzed ? h->sym.n_subtrees_small : 0;
+    out->subtree_max_panel = h->analyzed ? h->sym.subtree_max_panel : 0;
     if (h->analyzed) {
         const Symbolic& s = h->sym;
         out->nnz_L = s.nnz_L;

@@ -23,8 +23,10 @@ struct DeviceState {
     int n = 0, m = 0, nlb = 0, nub = 0, N = 0, kind = 0;
     int64_t L = 0;
     int64_t nnzA = 0, nnzQ = 0, nnzh = 0, nnzj = 0, nnzJfull = 0, kkt_nnz = 0, lx_stride = 0;
-    int nsuper = 0, n_subtrees = 0, n_levels = 0, h_cap = 0;
-    size_t factor_smem = 0;
+    int nsuper = 0, n_subtrees = 0, n_levels = 0;
+    int cap_sub = 0, cap_sub_big = 0, cap_top = 0, tri_cap = 0;   // shared-memory panel capacities (doubles)
+    int n_sub_small = 0;
+    size_t smem_sub = 0, smem_sub_big = 0, smem_top = 0, smem_tri = 0;
     std::vector<int> level_ptr;
 
     std::vector<void*> allocs;
@@ -40,6 +42,8 @@ struct DeviceState {
 
     int *sn_first = nullptr, *sn_rows = nullptr, *sn_of = nullptr;
     int64_t *sn_rowptr = nullptr, *sn_xoff = nullptr, *asm_map = nullptr, *diag_pos = nullptr;
+    int64_t *row_colbase = nullptr, *row_relbase = nullptr;
+    int* rel = nullptr;
     double *Lx = nullptr, *xw = nullptr;
     int *perm = nullptr, *iperm = nullptr, *sub_first = nullptr, *sub_last = nullptr, *level_sn = nullptr;
     int* fail = nullptr;
@@ -123,12 +127,15 @@ VecView make_view(const DeviceState& d) {
     return V;
 }
 
-FactorView make_factor_view(const DeviceState& d) {
+FactorView make_factor_view(const DeviceState& d, int panel_cap) {
     FactorView F;
     F.sn_first = d.sn_first; F.sn_rowptr = d.sn_rowptr; F.sn_rows = d.sn_rows; F.sn_xoff = d.sn_xoff;
-    F.sn_of = d.sn_of; F.Lx = d.Lx; F.lx_stride = d.lx_stride; F.fail = d.fail; F.h_cap = d.h_cap;
+    F.sn_of = d.sn_of; F.row_colbase = d.row_colbase; F.row_relbase = d.row_relbase; F.rel = d.rel;
+    F.Lx = d.Lx; F.lx_stride = d.lx_stride; F.fail = d.fail; F.panel_cap = panel_cap; F.scratch_rows = panel_cap;
     return F;
 }
+
+inline size_t factor_smem_bytes(int cap) { return (static_cast<size_t>(cap) + cap / 2 + 64 + 256) * sizeof(double); }
 
 struct Timer {
     madipm_handle* h;
@@ -237,20 +244,21 @@ int32_t check(madipm_handle* h, bool need_values = false) {
 
 int32_t tri_solve(madipm_handle* h) {
     DeviceState* d = h->dev;
-    FactorView F = make_factor_view(*d);
+    FactorView F = make_factor_view(*d, 0);
     const int T = 128;
+    const int64_t N = d->N;
     if (d->n_subtrees > 0)
-        LAUNCH(h, k_forward_subtrees, dim3(d->n_subtrees, d->B), T, 0, F, d->xw, (int64_t)d->N, d->sub_first, d->sub_last);
+        LAUNCH(h, k_forward_subtrees, dim3(d->n_subtrees, d->B), T, d->smem_tri, F, d->xw, N, d->sub_first, d->sub_last, d->tri_cap);
     for (int l = 0; l < d->n_levels; ++l) {
         int cnt = d->level_ptr[l + 1] - d->level_ptr[l];
-        LAUNCH(h, k_forward_level, dim3(cnt, d->B), T, 0, F, d->xw, (int64_t)d->N, d->level_sn + d->level_ptr[l]);
+        LAUNCH(h, k_forward_level, dim3(cnt, d->B), T, d->smem_tri, F, d->xw, N, d->level_sn + d->level_ptr[l], d->tri_cap);
     }
     for (int l = d->n_levels - 1; l >= 0; --l) {
         int cnt = d->level_ptr[l + 1] - d->level_ptr[l];
-        LAUNCH(h, k_backward_level, dim3(cnt, d->B), T, 0, F, d->xw, (int64_t)d->N, d->level_sn + d->level_ptr[l]);
+        LAUNCH(h, k_backward_level, dim3(cnt, d->B), T, d->smem_tri, F, d->xw, N, d->level_sn + d->level_ptr[l], d->tri_cap);
     }
     if (d->n_subtrees > 0)
-        LAUNCH(h, k_backward_subtrees, dim3(d->n_subtrees, d->B), T, 0, F, d->xw, (int64_t)d->N, d->sub_first, d->sub_last);
+        LAUNCH(h, k_backward_subtrees, dim3(d->n_subtrees, d->B), T, d->smem_tri, F, d->xw, N, d->sub_first, d->sub_last, d->tri_cap);
     return MADIPM_OK;
 }
 
@@ -323,6 +331,7 @@ int32_t device_create(madipm_handle* h) {
     // factor structure
     UP(int, sn_first, s.sn_first); UP(int64_t, sn_rowptr, s.sn_rowptr); UP(int, sn_rows, s.sn_rows);
     UP(int64_t, sn_xoff, s.sn_xoff); UP(int, sn_of, s.sn_of); UP(int64_t, asm_map, s.asm_map);
+    UP(int64_t, row_colbase, s.row_colbase); UP(int64_t, row_relbase, s.row_relbase); UP(int, rel, s.rel);
     UP(int, perm, s.perm); UP(int, iperm, s.iperm);
     UP(int, sub_first, s.subtree_first); UP(int, sub_last, s.subtree_last); UP(int, level_sn, s.level_sn);
     std::vector<int64_t> diag_pos(d->N);
@@ -337,14 +346,31 @@ int32_t device_create(madipm_handle* h) {
     if ((rc = dev_alloc(h, &d->xw, static_cast<size_t>(B) * d->N))) return rc;
     if ((rc = dev_alloc(h, &d->fail, B))) return rc;
     d->h_fail.assign(B, 0);
-    d->h_cap = std::max(64, s.max_h);
-    d->factor_smem = static_cast<size_t>(d->h_cap) * 12 + 256 * 8;
-    if (d->factor_smem > 200 * 1024) {
-        h->error = "supernode height " + std::to_string(s.max_h) + " exceeds the single-block factor path";
-        return MADIPM_INTERNAL;
+    // shared-memory capacities: bottom subtrees keep many blocks per SM (small panels staged, the rare larger
+    // ones in place); the level kernels of the top part get a panel-sized allocation, one block per SM.
+    {
+        int64_t max_panel_top = 0, max_h_top = 0, max_h_sub = 0;
+        for (int sn = 0; sn < s.nsuper; ++sn) {
+            int64_t hs = s.sn_rowptr[sn + 1] - s.sn_rowptr[sn], ws = s.sn_first[sn + 1] - s.sn_first[sn];
+            if (s.sn_level[sn] > 0) { max_panel_top = std::max(max_panel_top, hs * ws); max_h_top = std::max(max_h_top, hs); }
+            else max_h_sub = std::max(max_h_sub, hs);
+        }
+        d->n_sub_small = s.n_subtrees_small;
+        d->cap_sub = 1280;
+        d->cap_sub_big = static_cast<int>(std::max<int64_t>(std::min<int64_t>(8192, s.subtree_max_panel), std::max<int64_t>(1280, max_h_sub)));
+        d->smem_sub_big = factor_smem_bytes(d->cap_sub_big);
+        d->cap_top = static_cast<int>(std::max<int64_t>(std::min<int64_t>(16384, std::max<int64_t>(max_panel_top, 256)), max_h_top));
+        d->smem_sub = factor_smem_bytes(d->cap_sub);
+        d->smem_top = factor_smem_bytes(d->cap_top);
+        if (d->smem_top > 220 * 1024 || d->smem_sub > 64 * 1024) {
+            h->error = "supernode height " + std::to_string(s.max_h) + " exceeds the single-block factor path";
+            return MADIPM_INTERNAL;
+        }
+        d->tri_cap = std::min(s.max_w * s.max_w, 4096);
+        d->smem_tri = (static_cast<size_t>(d->tri_cap) + 256) * sizeof(double);
     }
-    CUDA_OK(h, cudaFuncSetAttribute(k_factor_subtrees, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->factor_smem));
-    CUDA_OK(h, cudaFuncSetAttribute(k_factor_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->factor_smem));
+    CUDA_OK(h, cudaFuncSetAttribute(k_factor_subtrees, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(d->smem_sub, d->smem_sub_big)));
+    CUDA_OK(h, cudaFuncSetAttribute(k_factor_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_top));
 
     // vectors
     const int64_t n = d->n, m = d->m;
@@ -585,14 +611,17 @@ int32_t madipm_factorize(madipm_handle* h, int32_t* n_failed) {
         CUDA_OK(h, cudaMemsetAsync(d->fail, 0, sizeof(int) * B, d->stream));
         LAUNCH(h, k_assemble_panels, dim3(vec_blocks(d->kkt_nnz) * 4, B), kVecThreads, 0, d->kkt_nnz, d->asm_map,
                d->vec[MADIPM_VEC_KKT_NZVAL], d->kkt_nnz, d->Lx, d->lx_stride);
-        FactorView F = make_factor_view(*d);
         if (light) cudaEventRecord(d->ev2, d->stream);
-        if (d->n_subtrees > 0)
-            LAUNCH(h, k_factor_subtrees, dim3(d->n_subtrees, B), 128, d->factor_smem, F, d->sub_first, d->sub_last);
+        // big-panel subtrees first (fewer, longer blocks), then the high-occupancy launch fills in behind them
+        if (d->n_subtrees > d->n_sub_small)
+            LAUNCH(h, k_factor_subtrees, dim3(d->n_subtrees - d->n_sub_small, B), 256, d->smem_sub_big,
+                   make_factor_view(*d, d->cap_sub_big), d->sub_first + d->n_sub_small, d->sub_last + d->n_sub_small);
+        if (d->n_sub_small > 0)
+            LAUNCH(h, k_factor_subtrees, dim3(d->n_sub_small, B), 128, d->smem_sub, make_factor_view(*d, d->cap_sub), d->sub_first, d->sub_last);
         if (light) cudaEventRecord(d->ev3, d->stream);
         for (int l = 0; l < d->n_levels; ++l) {
             int cnt = d->level_ptr[l + 1] - d->level_ptr[l];
-            LAUNCH(h, k_factor_level, dim3(cnt, B), 256, d->factor_smem, F, d->level_sn + d->level_ptr[l]);
+            LAUNCH(h, k_factor_level, dim3(cnt, B), 256, d->smem_top, make_factor_view(*d, d->cap_top), d->level_sn + d->level_ptr[l]);
         }
         if (light) cudaEventRecord(d->ev1, d->stream);
         CUDA_OK(h, cudaMemcpyAsync(d->h_fail.data(), d->fail, sizeof(int) * B, cudaMemcpyDeviceToHost, d->stream));

@@ -91,17 +91,25 @@ __device__ void grid_reduce(RedVals<K> r, double* scratch, unsigned int* counter
     __syncthreads();
     if (is_last) {
         __threadfence();
-        if (threadIdx.x < K) {
-            const int k = threadIdx.x;
+        // warp k combines slot k: lane l walks blocks l, l+32, ... in order, then a fixed-order tree
+        if (warp < K) {
+            const int k = warp;
             const double* base = scratch + static_cast<size_t>(inst) * gridDim.x * K;
-            double v = __ldcg(base + k);
-            for (unsigned int b = 1; b < gridDim.x; ++b) {
+            double v = (ops[k] == RED_SUM) ? 0.0 : ((ops[k] == RED_MAX) ? -1.0 : __longlong_as_double(0x7ff0000000000000LL));
+            bool any = false;
+            for (unsigned int b = lane; b < gridDim.x; b += 32) {
                 double u = __ldcg(base + static_cast<size_t>(b) * K + k);
-                if (ops[k] == RED_SUM) v = v + u;
+                if (!any) { v = u; any = true; }
+                else if (ops[k] == RED_SUM) v = v + u;
                 else if (ops[k] == RED_MAX) v = nanmax(v, u);
                 else v = (u < v) ? u : v;
             }
-            out[static_cast<size_t>(inst) * K + k] = v;
+            // lanes without a block hold the neutral element of the op (0 for sums; -1 / +inf never win
+            // because the reduced quantities are >= 0 for MAX and <= +inf for MIN)
+            if (ops[k] == RED_SUM) v = warp_red<RED_SUM>(v);
+            else if (ops[k] == RED_MAX) v = warp_red<RED_MAX>(v);
+            else v = warp_red<RED_MIN>(v);
+            if (lane == 0) out[static_cast<size_t>(inst) * K + k] = v;
         }
         if (threadIdx.x == 0) counter[inst] = 0;   // ready for the next launch
     }
@@ -411,16 +419,30 @@ k_ratio_test(VecView V, const double* __restrict__ d, const double* __restrict__
     __syncthreads();
     if (is_last) {
         __threadfence();
-        if (threadIdx.x < 4) {
-            const int q = threadIdx.x;
+        if (warp < 4) {
+            // warp q combines slot q: lane l owns a contiguous run of blocks (order preserved), then the
+            // ordered tree; the reference's init element (1.0, 0) is applied last, as the leftmost element
+            const int q = warp;
             const double* base = scratch + static_cast<size_t>(inst) * gridDim.x * 8;
-            ArgMin r; r.v = 1.0; r.i = 0;   // the init element is the leftmost
-            for (unsigned int b = 0; b < gridDim.x; ++b) {
+            const unsigned int per = (gridDim.x + 31) / 32;
+            ArgMin r; r.v = inf; r.i = 0;
+            for (unsigned int b = lane * per; b < min(gridDim.x, (lane + 1) * per); ++b) {
                 ArgMin e; e.v = __ldcg(base + b * 8 + q); e.i = static_cast<int>(__ldcg(base + b * 8 + 4 + q));
                 if (e.i != 0) r = argmin_combine(r, e);   // blocks that saw no element report (+inf, 0)
             }
-            out[static_cast<size_t>(inst) * 8 + q] = r.v;
-            out[static_cast<size_t>(inst) * 8 + 4 + q] = static_cast<double>(r.i);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                ArgMin b2;
+                b2.v = __shfl_down_sync(0xffffffffu, r.v, o);
+                b2.i = __shfl_down_sync(0xffffffffu, r.i, o);
+                if (lane + o < 32 && ((lane & (2 * o - 1)) == 0) && b2.i != 0) r = argmin_combine(r, b2);
+            }
+            if (lane == 0) {
+                ArgMin init; init.v = 1.0; init.i = 0;
+                if (r.i != 0) init = argmin_combine(init, r);
+                out[static_cast<size_t>(inst) * 8 + q] = init.v;
+                out[static_cast<size_t>(inst) * 8 + 4 + q] = static_cast<double>(init.i);
+            }
         }
         if (threadIdx.x == 0) counter[inst] = 0;
     }

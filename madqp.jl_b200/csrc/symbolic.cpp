@@ -618,13 +618,63 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
             S.asm_map[p] = S.sn_xoff[s] + static_cast<int64_t>(c - S.sn_first[s]) * hs + (it - rb);
         }
 
+    // ---- 7b. scatter tables for the right-looking update
+    {
+        const size_t nr = S.sn_rows.size();
+        S.row_colbase.assign(nr, 0);
+        S.row_relbase.assign(nr, Symbolic::kRelSearch);
+        S.rel.assign(4096, 0);   // padding keeps every table base (size - jb, jb <= 4096) non-negative
+        std::vector<int32_t> pos;
+        for (int32_t s = 0; s < ns; ++s) {
+            const int64_t r0 = S.sn_rowptr[s];
+            const int32_t hs = static_cast<int32_t>(S.sn_rowptr[s + 1] - r0);
+            const int32_t ws = S.sn_first[s + 1] - S.sn_first[s];
+            const int32_t* rows = S.sn_rows.data() + r0;
+            int32_t jb = ws;
+            while (jb < hs) {
+                const int32_t t = S.sn_of[rows[jb]];
+                const int32_t fct = S.sn_first[t], lct = S.sn_first[t + 1];
+                const int32_t* trows = S.sn_rows.data() + S.sn_rowptr[t];
+                const int32_t ht = static_cast<int32_t>(S.sn_rowptr[t + 1] - S.sn_rowptr[t]);
+                int32_t je = jb;
+                while (je < hs && rows[je] < lct) ++je;
+                // positions of rows[jb..hs) in trows (both ascending)
+                pos.resize(hs - jb);
+                const int32_t* from = trows;
+                bool shift = true;
+                for (int32_t i = jb; i < hs; ++i) {
+                    const int32_t* it = std::lower_bound(from, trows + ht, rows[i]);
+                    if (it == trows + ht || *it != rows[i]) throw std::runtime_error("analyze: update row missing in ancestor");
+                    pos[i - jb] = static_cast<int32_t>(it - trows);
+                    if (pos[i - jb] - pos[0] != i - jb) shift = false;
+                    from = it + 1;
+                }
+                int64_t relbase;
+                if (shift) {
+                    const int64_t c = static_cast<int64_t>(pos[0]) - jb;     // position = i + c
+                    relbase = -(c + Symbolic::kRelShift) - 1;
+                } else if (hs <= 4096) {
+                    relbase = static_cast<int64_t>(S.rel.size()) - jb;      // rel[relbase + i]
+                    S.rel.insert(S.rel.end(), pos.begin(), pos.end());
+                } else {
+                    relbase = Symbolic::kRelSearch;
+                }
+                for (int32_t jj = jb; jj < je; ++jj) {
+                    S.row_colbase[r0 + jj] = S.sn_xoff[t] + static_cast<int64_t>(rows[jj] - fct) * ht;
+                    S.row_relbase[r0 + jj] = relbase;
+                }
+                jb = je;
+            }
+        }
+    }
+
     // ---- 8. schedule: bottom subtrees (one thread block each) + levels of the top part
     std::vector<double> work(ns), sub(ns);
     std::vector<int32_t> size(ns, 1);
     for (int32_t s = 0; s < ns; ++s) {
         double hs = static_cast<double>(S.sn_rowptr[s + 1] - S.sn_rowptr[s]);
         double ws = static_cast<double>(S.sn_first[s + 1] - S.sn_first[s]);
-        work[s] = ws * hs * hs + 64.0;
+        work[s] = ws * hs * hs + (hs - ws) * (hs - ws) * ws + static_cast<double>(opt.node_latency);
         sub[s] = work[s];
     }
     for (int32_t s = 0; s < ns; ++s)
@@ -633,17 +683,52 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
     S.subtree_first.clear();
     S.subtree_last.clear();
     const double budget = static_cast<double>(opt.subtree_work);
+    // heavy = handled level by level.  Tall supernodes never go into a single-block subtree (its
+    // shared-memory scratch is small); heaviness propagates to every ancestor.
+    std::vector<char> heavy(ns, 0);
     for (int32_t s = 0; s < ns; ++s) {
-        bool heavy = sub[s] > budget;
+        if (sub[s] > budget || (S.sn_rowptr[s + 1] - S.sn_rowptr[s]) > 512) heavy[s] = 1;
+        if (heavy[s] && S.sn_parent[s] != -1) heavy[S.sn_parent[s]] = 1;
+    }
+    for (int32_t s = 0; s < ns; ++s) {
         int32_t p = S.sn_parent[s];
-        if (heavy) {
+        if (heavy[s]) {
             S.sn_level[s] = 1;   // provisional: top part
-        } else if (p == -1 || sub[p] > budget) {
+        } else if (p == -1 || heavy[p]) {
             S.subtree_first.push_back(s - size[s] + 1);
             S.subtree_last.push_back(s);
         }
     }
     S.n_subtrees = static_cast<int32_t>(S.subtree_last.size());
+    {   // two launch classes by largest panel, heaviest subtree first inside each class
+        const int32_t nsub = S.n_subtrees;
+        std::vector<int64_t> maxpanel(nsub, 0);
+        std::vector<double> cost(nsub, 0.0);
+        S.subtree_max_panel = 0;
+        for (int32_t k = 0; k < nsub; ++k)
+            for (int32_t s = S.subtree_first[k]; s <= S.subtree_last[k]; ++s) {
+                int64_t hs = S.sn_rowptr[s + 1] - S.sn_rowptr[s], ws = S.sn_first[s + 1] - S.sn_first[s];
+                maxpanel[k] = std::max(maxpanel[k], hs * ws);
+                cost[k] += work[s];
+            }
+        std::vector<int32_t> idx(nsub);
+        std::iota(idx.begin(), idx.end(), 0);
+        std::stable_sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) {
+            bool sa = maxpanel[a] <= opt.small_panel, sb = maxpanel[b] <= opt.small_panel;
+            if (sa != sb) return sa;
+            return cost[a] > cost[b];
+        });
+        std::vector<int32_t> f(nsub), l(nsub);
+        S.n_subtrees_small = 0;
+        for (int32_t k = 0; k < nsub; ++k) {
+            f[k] = S.subtree_first[idx[k]];
+            l[k] = S.subtree_last[idx[k]];
+            if (maxpanel[idx[k]] <= opt.small_panel) ++S.n_subtrees_small;
+            S.subtree_max_panel = static_cast<int32_t>(std::max<int64_t>(S.subtree_max_panel, maxpanel[idx[k]]));
+        }
+        S.subtree_first.swap(f);
+        S.subtree_last.swap(l);
+    }
     S.n_levels = 0;
     for (int32_t s = 0; s < ns; ++s) {
         if (S.sn_level[s] == 0) continue;

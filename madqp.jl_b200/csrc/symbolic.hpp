@@ -36,7 +36,9 @@ struct SymbolicOptions {
     int32_t max_width = 64;        // cap on supernode width (columns)
     int32_t relax_small = 8;       // always merge a last child if the merged width <= this
     double relax_zeros[3] = {0.5, 0.2, 0.05};   // allowed zero fraction for merged width <= 16, <= 48, larger
-    int64_t subtree_work = 200000; // flop budget of a bottom subtree handled by one thread block
+    int64_t subtree_work = 200000; // cost budget of a bottom subtree handled by one thread block
+    int64_t node_latency = 20000;  // fixed cost of one supernode in flop equivalents (dependent memory round trips)
+    int32_t small_panel = 1280;    // panels up to this many doubles are staged by the high-occupancy subtree launch
     double dense_factor = 10.0;
 };
 
@@ -61,11 +63,25 @@ struct Symbolic {
 
     std::vector<int64_t> asm_map;    // [nnz_lower] CSC nz -> slot in Lx
 
+    // scatter tables of the right-looking update, indexed like sn_rows (entries of a supernode's own
+    // columns are unused).  For below-row jj of supernode s, owned as a column by supernode t:
+    //   row_colbase[jj] = slot of (row 0 of t's panel, column rows[jj]) in Lx
+    //   row_relbase[jj] >= 0: position of rows[i] (i >= jj) in t's row list is rel[row_relbase[jj] + i]
+    //                   <  0: it is i + c with c = -(row_relbase[jj] + 1) - 2^40   (contiguous match)
+    //                   == kRelSearch: not tabulated (very tall supernode), binary search at run time
+    std::vector<int64_t> row_colbase, row_relbase;
+    std::vector<int32_t> rel;
+    static constexpr int64_t kRelShift = int64_t(1) << 40;
+    static constexpr int64_t kRelSearch = INT64_MIN;
+
     // schedule
     std::vector<int32_t> sn_level;       // [nsuper] 0 = inside a bottom subtree, >= 1 level of the top part
     int32_t n_subtrees = 0;
     std::vector<int32_t> subtree_first;  // [n_subtrees] first supernode of the subtree (postorder => contiguous)
     std::vector<int32_t> subtree_last;   // [n_subtrees] root supernode of the subtree (inclusive)
+    int32_t n_subtrees_small = 0;        // subtrees [0, n_subtrees_small) only hold panels <= small_panel doubles;
+                                         // inside each class the subtrees are sorted heaviest first
+    int32_t subtree_max_panel = 0;       // largest panel (doubles) inside any subtree
     int32_t n_levels = 0;                // number of top levels
     std::vector<int32_t> level_ptr;      // [n_levels+1] into level_sn
     std::vector<int32_t> level_sn;       // top supernodes grouped by level

@@ -87,7 +87,7 @@ class IPMOptions:
     # backend options (the linear-solver options of the reference's `opt_linear_solver`)
     ordering: int = _lib.ORDER_ND
     max_width: int = 64
-    subtree_work: int = 2_000_000
+    subtree_work: int = 4_000_000
     nd_leaf: int = 0
     device: int = 0
 

