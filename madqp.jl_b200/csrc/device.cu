@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "handle.hpp"
+#include "kernels_big.cuh"
 #include "kernels_factor.cuh"
 #include "kernels_vec.cuh"
 
@@ -27,7 +28,13 @@ struct DeviceState {
     int cap_sub = 0, cap_sub_big = 0, cap_top = 0, tri_cap = 0;   // shared-memory panel capacities (doubles)
     int n_sub_small = 0;
     size_t smem_sub = 0, smem_sub_big = 0, smem_top = 0, smem_tri = 0;
-    std::vector<int> level_ptr;
+    std::vector<int> level_ptr;        // small (single-block) supernodes of the top part, per level
+    std::vector<int> big_ptr;          // big (multi-block) supernodes, per level
+    std::vector<int> big_rowblocks, big_rowblocks512, big_tiles;   // per level: grid sizes (max over its big supernodes)
+    int* big_sn = nullptr;
+    double *big_ybuf = nullptr, *big_tbuf = nullptr;
+    int big_max_per_level = 0;
+    size_t smem_big_diag = 0, smem_big_trsm = 0, smem_big_update = 0;
 
     std::vector<void*> allocs;
 
@@ -250,12 +257,28 @@ int32_t tri_solve(madipm_handle* h) {
     if (d->n_subtrees > 0)
         LAUNCH(h, k_forward_subtrees, dim3(d->n_subtrees, d->B), T, d->smem_tri, F, d->xw, N, d->sub_first, d->sub_last, d->tri_cap);
     for (int l = 0; l < d->n_levels; ++l) {
-        int cnt = d->level_ptr[l + 1] - d->level_ptr[l];
-        LAUNCH(h, k_forward_level, dim3(cnt, d->B), T, d->smem_tri, F, d->xw, N, d->level_sn + d->level_ptr[l], d->tri_cap);
+        const int cnt = d->level_ptr[l + 1] - d->level_ptr[l];
+        if (cnt > 0)
+            LAUNCH(h, k_forward_level, dim3(cnt, d->B), T, d->smem_tri, F, d->xw, N, d->level_sn + d->level_ptr[l], d->tri_cap);
+        const int nbig = d->big_ptr[l + 1] - d->big_ptr[l];
+        if (nbig > 0) {
+            const int* list = d->big_sn + d->big_ptr[l];
+            LAUNCH(h, k_big_fwd_diag, dim3(nbig, d->B), 256, d->smem_tri, F, list, d->big_ybuf, 256, d->xw, N, d->tri_cap);
+            if (d->big_rowblocks[l] > 0)
+                LAUNCH(h, k_big_fwd_below, dim3(d->big_rowblocks[l], nbig, d->B), kTrsmRows, 0, F, list, d->big_ybuf, 256, d->xw, N);
+        }
     }
     for (int l = d->n_levels - 1; l >= 0; --l) {
-        int cnt = d->level_ptr[l + 1] - d->level_ptr[l];
-        LAUNCH(h, k_backward_level, dim3(cnt, d->B), T, d->smem_tri, F, d->xw, N, d->level_sn + d->level_ptr[l], d->tri_cap);
+        const int nbig = d->big_ptr[l + 1] - d->big_ptr[l];
+        if (nbig > 0) {
+            const int* list = d->big_sn + d->big_ptr[l];
+            if (d->big_rowblocks512[l] > 0)
+                LAUNCH(h, k_big_bwd_below, dim3(d->big_rowblocks512[l], nbig, d->B), 256, 0, F, list, d->big_tbuf, 256, d->xw, N);
+            LAUNCH(h, k_big_bwd_diag, dim3(nbig, d->B), 256, d->smem_tri, F, list, d->big_tbuf, 256, d->xw, N, d->tri_cap);
+        }
+        const int cnt = d->level_ptr[l + 1] - d->level_ptr[l];
+        if (cnt > 0)
+            LAUNCH(h, k_backward_level, dim3(cnt, d->B), T, d->smem_tri, F, d->xw, N, d->level_sn + d->level_ptr[l], d->tri_cap);
     }
     if (d->n_subtrees > 0)
         LAUNCH(h, k_backward_subtrees, dim3(d->n_subtrees, d->B), T, d->smem_tri, F, d->xw, N, d->sub_first, d->sub_last, d->tri_cap);
@@ -301,7 +324,31 @@ int32_t device_create(madipm_handle* h) {
     d->kkt_nnz = p.kkt_colptr.back();
     d->lx_stride = s.nnz_stored;
     d->nsuper = s.nsuper; d->n_subtrees = s.n_subtrees; d->n_levels = s.n_levels;
-    d->level_ptr.assign(s.level_ptr.begin(), s.level_ptr.end());
+    // split every level of the top part into single-block and multi-block (big) supernodes
+    std::vector<int> small_sn, big_sn_host;
+    {
+        const int64_t kBigPanel = 16384;
+        d->level_ptr.assign(1, 0);
+        d->big_ptr.assign(1, 0);
+        for (int l = 0; l < s.n_levels; ++l) {
+            int rb = 0, rb512 = 0, tiles = 0;
+            for (int q = s.level_ptr[l]; q < s.level_ptr[l + 1]; ++q) {
+                int sn = s.level_sn[q];
+                int64_t hs = s.sn_rowptr[sn + 1] - s.sn_rowptr[sn], ws = s.sn_first[sn + 1] - s.sn_first[sn];
+                if (hs * ws > kBigPanel) {
+                    big_sn_host.push_back(sn);
+                    int64_t nb = hs - ws, nt = (nb + kBigTile - 1) / kBigTile;
+                    rb = std::max<int>(rb, static_cast<int>((nb + kTrsmRows - 1) / kTrsmRows));
+                    rb512 = std::max<int>(rb512, static_cast<int>((nb + 511) / 512));
+                    tiles = std::max<int>(tiles, static_cast<int>(nt * (nt + 1) / 2));
+                } else small_sn.push_back(sn);
+            }
+            d->level_ptr.push_back(static_cast<int>(small_sn.size()));
+            d->big_ptr.push_back(static_cast<int>(big_sn_host.size()));
+            d->big_rowblocks.push_back(rb); d->big_rowblocks512.push_back(rb512); d->big_tiles.push_back(tiles);
+            d->big_max_per_level = std::max(d->big_max_per_level, d->big_ptr[l + 1] - d->big_ptr[l]);
+        }
+    }
     const int B = d->B;
     int32_t rc;
 #define UP(T, dst, src) if ((rc = upload_as<T>(h, &d->dst, src))) return rc
@@ -333,7 +380,8 @@ int32_t device_create(madipm_handle* h) {
     UP(int64_t, sn_xoff, s.sn_xoff); UP(int, sn_of, s.sn_of); UP(int64_t, asm_map, s.asm_map);
     UP(int64_t, row_colbase, s.row_colbase); UP(int64_t, row_relbase, s.row_relbase); UP(int, rel, s.rel);
     UP(int, perm, s.perm); UP(int, iperm, s.iperm);
-    UP(int, sub_first, s.subtree_first); UP(int, sub_last, s.subtree_last); UP(int, level_sn, s.level_sn);
+    UP(int, sub_first, s.subtree_first); UP(int, sub_last, s.subtree_last); UP(int, level_sn, small_sn);
+    UP(int, big_sn, big_sn_host);
     std::vector<int64_t> diag_pos(d->N);
     for (int sn = 0; sn < s.nsuper; ++sn) {
         int64_t hs = s.sn_rowptr[sn + 1] - s.sn_rowptr[sn];
@@ -352,8 +400,9 @@ int32_t device_create(madipm_handle* h) {
         int64_t max_panel_top = 0, max_h_top = 0, max_h_sub = 0;
         for (int sn = 0; sn < s.nsuper; ++sn) {
             int64_t hs = s.sn_rowptr[sn + 1] - s.sn_rowptr[sn], ws = s.sn_first[sn + 1] - s.sn_first[sn];
-            if (s.sn_level[sn] > 0) { max_panel_top = std::max(max_panel_top, hs * ws); max_h_top = std::max(max_h_top, hs); }
-            else max_h_sub = std::max(max_h_sub, hs);
+            if (s.sn_level[sn] > 0) {
+                if (hs * ws <= 16384) { max_panel_top = std::max(max_panel_top, hs * ws); max_h_top = std::max(max_h_top, hs); }
+            } else max_h_sub = std::max(max_h_sub, hs);
         }
         d->n_sub_small = s.n_subtrees_small;
         d->cap_sub = 1280;
@@ -371,6 +420,22 @@ int32_t device_create(madipm_handle* h) {
     }
     CUDA_OK(h, cudaFuncSetAttribute(k_factor_subtrees, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(d->smem_sub, d->smem_sub_big)));
     CUDA_OK(h, cudaFuncSetAttribute(k_factor_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_top));
+    {
+        const size_t mw = static_cast<size_t>(s.max_w);
+        d->smem_big_diag = (mw * mw + mw) * sizeof(double);
+        d->smem_big_trsm = (mw * mw + mw + mw * kTrsmLd) * sizeof(double);
+        d->smem_big_update = 2 * mw * kBigTileLd * sizeof(double) + 2 * kBigTile * sizeof(int64_t);
+        if (!big_sn_host.empty()) {
+            if (d->smem_big_trsm > 220 * 1024) { h->error = "max_width too large for the big-front kernels"; return MADIPM_BAD_ARGUMENT; }
+            CUDA_OK(h, cudaFuncSetAttribute(k_big_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_big_diag));
+            CUDA_OK(h, cudaFuncSetAttribute(k_big_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_big_trsm));
+            CUDA_OK(h, cudaFuncSetAttribute(k_big_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_big_update));
+            const size_t nbuf = static_cast<size_t>(B) * d->big_max_per_level * 256;
+            if ((rc = dev_alloc(h, &d->big_ybuf, nbuf))) return rc;
+            if ((rc = dev_alloc(h, &d->big_tbuf, nbuf))) return rc;
+            CUDA_OK(h, cudaMemsetAsync(d->big_tbuf, 0, nbuf * sizeof(double), d->stream));
+        }
+    }
 
     // vectors
     const int64_t n = d->n, m = d->m;
@@ -620,8 +685,19 @@ int32_t madipm_factorize(madipm_handle* h, int32_t* n_failed) {
             LAUNCH(h, k_factor_subtrees, dim3(d->n_sub_small, B), 128, d->smem_sub, make_factor_view(*d, d->cap_sub), d->sub_first, d->sub_last);
         if (light) cudaEventRecord(d->ev3, d->stream);
         for (int l = 0; l < d->n_levels; ++l) {
-            int cnt = d->level_ptr[l + 1] - d->level_ptr[l];
-            LAUNCH(h, k_factor_level, dim3(cnt, B), 256, d->smem_top, make_factor_view(*d, d->cap_top), d->level_sn + d->level_ptr[l]);
+            const int cnt = d->level_ptr[l + 1] - d->level_ptr[l];
+            if (cnt > 0)
+                LAUNCH(h, k_factor_level, dim3(cnt, B), 256, d->smem_top, make_factor_view(*d, d->cap_top), d->level_sn + d->level_ptr[l]);
+            const int nbig = d->big_ptr[l + 1] - d->big_ptr[l];
+            if (nbig > 0) {
+                const FactorView F = make_factor_view(*d, 0);
+                const int* list = d->big_sn + d->big_ptr[l];
+                LAUNCH(h, k_big_diag, dim3(nbig, B), 256, d->smem_big_diag, F, list);
+                if (d->big_rowblocks[l] > 0) {
+                    LAUNCH(h, k_big_trsm, dim3(d->big_rowblocks[l], nbig, B), kTrsmRows, d->smem_big_trsm, F, list);
+                    LAUNCH(h, k_big_update, dim3(d->big_tiles[l], nbig, B), 128, d->smem_big_update, F, list);
+                }
+            }
         }
         if (light) cudaEventRecord(d->ev1, d->stream);
         CUDA_OK(h, cudaMemcpyAsync(d->h_fail.data(), d->fail, sizeof(int) * B, cudaMemcpyDeviceToHost, d->stream));

@@ -1,0 +1,311 @@
+// Large fronts: supernodes whose panel does not fit one block's shared memory are factorised by
+// three grid-wide kernels per level (all big supernodes of the level batched in blockIdx.y):
+//
+//   k_big_diag    one block per supernode: dense LDL' of the w x w diagonal block in shared memory
+//   k_big_trsm    row blocks of 128: L21 = A21 L11^-T D^-1
+//   k_big_update  64 x 64 tiles of the Schur complement S = L21 D L21' on the FP64 tensor cores
+//                 (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4), operands staged k-major in shared memory
+//                 with a leading dimension = 4 mod 16 doubles (bank-conflict-free fragment loads),
+//                 scattered into the ancestors' panels through the symbolic tables.
+//
+// tcgen05 has no f64 kind (ptxas rejects it), so DMMA is the FP64 tensor path on sm_100a.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "kernels_factor.cuh"
+
+namespace madipm {
+
+constexpr int kBigTile = 64;          // output tile edge of k_big_update
+constexpr int kBigTileLd = 68;        // 64 + 4: leading dimension = 4 mod 16 doubles
+constexpr int kTrsmRows = 128;
+constexpr int kTrsmLd = 132;
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// ---- diagonal block -----------------------------------------------------------------------------
+// shared: [w*w doubles block][w doubles ucol]
+__global__ void k_big_diag(FactorView F, const int* __restrict__ big_sn) {
+    const int inst = blockIdx.y;
+    const int s = big_sn[blockIdx.x];
+    double* Lx = F.Lx + inst * F.lx_stride;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+    const int w = F.sn_first[s + 1] - F.sn_first[s];
+    const int64_t ld = F.sn_rowptr[s + 1] - F.sn_rowptr[s];
+    double* P = Lx + F.sn_xoff[s];
+    double* Bs = madipm_smem;
+    double* ucol = Bs + w * w;
+    for (int idx = tid; idx < w * w; idx += T) {
+        const int i = idx % w, j = idx / w;
+        Bs[idx] = ldcg(&P[i + j * ld]);
+    }
+    __syncthreads();
+    for (int j = 0; j < w; ++j) {
+        const double d = Bs[j * (w + 1)];
+        if (tid == 0 && bad_pivot(d)) atomicExch(F.fail + inst, 1);
+        for (int i = j + 1 + tid; i < w; i += T) {
+            const double u = Bs[i + j * w];
+            ucol[i] = u;
+            Bs[i + j * w] = u / d;
+        }
+        __syncthreads();
+        for (int k = j + 1 + warp; k < w; k += nwarp) {
+            const double lk = Bs[k + j * w];
+            for (int i = k + lane; i < w; i += 32) Bs[i + k * w] -= ucol[i] * lk;
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < w * w; idx += T) {
+        const int i = idx % w, j = idx / w;
+        if (i >= j) P[i + j * ld] = Bs[idx];
+    }
+}
+
+// ---- L21 = A21 L11^-T D^-1 ----------------------------------------------------------------------
+// One thread per row.  shared: [w*w doubles M = unit-lower L11 scaled by D (M[j',j] = d_j L11[j',j])]
+//                              [w doubles 1/d][w * kTrsmLd doubles row tile, k-major]
+__global__ void k_big_trsm(FactorView F, const int* __restrict__ big_sn) {
+    const int inst = blockIdx.z;
+    const int s = big_sn[blockIdx.y];
+    double* Lx = F.Lx + inst * F.lx_stride;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int w = F.sn_first[s + 1] - F.sn_first[s];
+    const int h = static_cast<int>(F.sn_rowptr[s + 1] - F.sn_rowptr[s]);
+    const int64_t ld = h;
+    const int r0 = w + blockIdx.x * kTrsmRows;
+    if (r0 >= h) return;
+    const int nr = min(kTrsmRows, h - r0);
+    double* P = Lx + F.sn_xoff[s];
+    double* M = madipm_smem;
+    double* dinv = M + w * w;
+    double* tile = dinv + w;
+    for (int idx = tid; idx < w * w; idx += T) {
+        const int i = idx % w, j = idx / w;
+        if (i > j) M[idx] = P[i + j * ld] * P[j + j * ld];      // d_j * L11[i, j]
+    }
+    for (int j = tid; j < w; j += T) dinv[j] = 1.0 / P[j + j * ld];
+    for (int idx = tid; idx < w * nr; idx += T) {
+        const int r = idx % nr, j = idx / nr;
+        tile[j * kTrsmLd + r] = ldcg(&P[r0 + r + j * ld]);
+    }
+    __syncthreads();
+    if (tid < nr) {
+        for (int j = 0; j < w; ++j) {
+            const double a = tile[j * kTrsmLd + tid];
+            const double l = a * dinv[j];                        // l_j = a_j / d_j
+            tile[j * kTrsmLd + tid] = l;
+            for (int jp = j + 1; jp < w; ++jp) tile[jp * kTrsmLd + tid] -= l * M[jp + j * w];   // a_j' -= l_j d_j L11[j', j]
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < w * nr; idx += T) {
+        const int r = idx % nr, j = idx / nr;
+        P[r0 + r + j * ld] = tile[j * kTrsmLd + r];
+    }
+}
+
+// ---- Schur complement on the FP64 tensor cores ----------------------------------------------------
+// grid.x = linear index of a lower-triangular 64 x 64 tile (ti >= tj) of the (h-w) x (h-w) update,
+// grid.y = big supernode of the level, grid.z = instance.  128 threads = 4 warps, each 32 x 32.
+// shared: [w * 68 doubles A (rows of tile ti)][w * 68 doubles B = D L21' (rows of tile tj)]
+//         [64 int64 colbase][64 int64 relbase]
+__global__ void __launch_bounds__(128)
+k_big_update(FactorView F, const int* __restrict__ big_sn) {
+    const int inst = blockIdx.z;
+    const int s = big_sn[blockIdx.y];
+    double* Lx = F.Lx + inst * F.lx_stride;
+    const int tid = threadIdx.x;
+    const int w = F.sn_first[s + 1] - F.sn_first[s];
+    const int h = static_cast<int>(F.sn_rowptr[s + 1] - F.sn_rowptr[s]);
+    const int nb = h - w;
+    const int nt = (nb + kBigTile - 1) / kBigTile;
+    // decode the linear tile index t -> (ti, tj), ti >= tj
+    const int t = blockIdx.x;
+    if (t >= nt * (nt + 1) / 2) return;
+    int ti = static_cast<int>((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    while (ti * (ti + 1) / 2 > t) --ti;
+    const int tj = t - ti * (ti + 1) / 2;
+    const int64_t ld = h;
+    const double* P = Lx + F.sn_xoff[s];
+    const int* rows = F.sn_rows + F.sn_rowptr[s];
+    double* As = madipm_smem;
+    double* Bs = As + w * kBigTileLd;
+    int64_t* colb = reinterpret_cast<int64_t*>(Bs + w * kBigTileLd);
+    int64_t* relb = colb + kBigTile;
+    const int i0 = w + ti * kBigTile, j0 = w + tj * kBigTile;
+    const int ni = min(kBigTile, h - i0), nj = min(kBigTile, h - j0);
+    for (int idx = tid; idx < w * kBigTile; idx += 128) {
+        const int r = idx % kBigTile, k = idx / kBigTile;
+        As[k * kBigTileLd + r] = (r < ni) ? ldcg(&P[i0 + r + k * ld]) : 0.0;
+        Bs[k * kBigTileLd + r] = (r < nj) ? ldcg(&P[j0 + r + k * ld]) * P[k + k * ld] : 0.0;
+    }
+    if (tid < kBigTile) {
+        const int jj = j0 + tid;
+        colb[tid] = (tid < nj) ? F.row_colbase[F.sn_rowptr[s] + jj] : 0;
+        relb[tid] = (tid < nj) ? F.row_relbase[F.sn_rowptr[s] + jj] : 0;
+    }
+    __syncthreads();
+    const int lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;     // warp's 32 x 32 corner inside the tile
+    const int fr = lane >> 2, fk = lane & 3;                   // fragment row / k (A), n / k (B)
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    for (int k0 = 0; k0 < w; k0 += 4) {
+        double af[4], bf[4];
+        const int kk = k0 + fk;
+        const bool kin = kk < w;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) af[a] = kin ? As[kk * kBigTileLd + wm + a * 8 + fr] : 0.0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bf[b] = kin ? Bs[kk * kBigTileLd + wn + b * 8 + fr] : 0.0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+    }
+    // scatter: lane holds C[row = lane/4][col = 2*(lane%4) + {0,1}] of every 8 x 8 tile
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int li = wm + a * 8 + fr;            // row inside the tile
+                const int lj = wn + b * 8 + 2 * fk + e;    // column inside the tile
+                const int i = i0 + li, jj = j0 + lj;
+                if (li < ni && lj < nj && i >= jj) {
+                    const int pos = target_pos(F, relb[lj], i, rows, jj);
+                    atomicAdd(Lx + colb[lj] + pos, -acc[a][b][e]);
+                }
+            }
+}
+
+// ---- multi-block triangular-solve helpers for tall panels ------------------------------------------
+// forward, below rows:  xw[rows[i]] -= sum_j L[i,j] y[j]   (y = xw[fc .. fc+w) already holds the solved block, UNSCALED by D)
+__global__ void k_big_fwd_below(FactorView F, const int* __restrict__ big_sn, const double* __restrict__ ybuf, int ystride,
+                                double* xw, int64_t xw_stride) {
+    const int inst = blockIdx.z;
+    const int b = blockIdx.y;
+    const int s = big_sn[b];
+    const double* Lx = F.Lx + inst * F.lx_stride;
+    xw += inst * xw_stride;
+    const int w = F.sn_first[s + 1] - F.sn_first[s];
+    const int h = static_cast<int>(F.sn_rowptr[s + 1] - F.sn_rowptr[s]);
+    const int64_t ld = h;
+    const double* P = Lx + F.sn_xoff[s];
+    const int* rows = F.sn_rows + F.sn_rowptr[s];
+    __shared__ double sy[256];
+    const double* y = ybuf + (static_cast<int64_t>(inst) * gridDim.y + b) * ystride;
+    for (int j = threadIdx.x; j < w; j += blockDim.x) sy[j] = y[j];
+    __syncthreads();
+    const int i = w + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < h) {
+        double acc = 0.0;
+        for (int j = 0; j < w; ++j) acc = fma(P[i + j * ld], sy[j], acc);
+        atomicAdd(&xw[rows[i]], -acc);
+    }
+}
+
+// forward, diagonal block of big supernodes: y = L11^-1 b, ybuf <- y, xw[fc+j] <- y_j / d_j
+__global__ void k_big_fwd_diag(FactorView F, const int* __restrict__ big_sn, double* __restrict__ ybuf, int ystride,
+                               double* xw, int64_t xw_stride, int tri_cap) {
+    double* tri = madipm_smem;
+    double* sy = tri + tri_cap;
+    const int inst = blockIdx.y;
+    const int b = blockIdx.x;
+    const int s = big_sn[b];
+    const double* Lx = F.Lx + inst * F.lx_stride;
+    xw += inst * xw_stride;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int fc = F.sn_first[s];
+    const int w = F.sn_first[s + 1] - fc;
+    const int64_t ld = F.sn_rowptr[s + 1] - F.sn_rowptr[s];
+    const double* P = Lx + F.sn_xoff[s];
+    for (int j = tid; j < w; j += T) sy[j] = ldcg(&xw[fc + j]);
+    for (int idx = tid; idx < w * w; idx += T) {
+        const int i = idx % w, j = idx / w;
+        if (i > j) tri[idx] = P[i + j * ld];
+    }
+    for (int j = 0; j + 1 < w; ++j) {
+        __syncthreads();
+        const double yj = sy[j];
+        for (int i = j + 1 + tid; i < w; i += T) sy[i] -= tri[i + j * w] * yj;
+    }
+    __syncthreads();
+    double* y = ybuf + (static_cast<int64_t>(inst) * gridDim.x + b) * ystride;
+    for (int j = tid; j < w; j += T) {
+        y[j] = sy[j];
+        xw[fc + j] = sy[j] / P[j + j * ld];
+    }
+}
+
+// backward, below rows: tbuf[j] += sum_{i in row block} L[i,j] x[rows[i]]  (one warp per column chunk)
+__global__ void k_big_bwd_below(FactorView F, const int* __restrict__ big_sn, double* __restrict__ tbuf, int tstride,
+                                const double* xw, int64_t xw_stride) {
+    const int inst = blockIdx.z;
+    const int b = blockIdx.y;
+    const int s = big_sn[b];
+    const double* Lx = F.Lx + inst * F.lx_stride;
+    xw += inst * xw_stride;
+    const int w = F.sn_first[s + 1] - F.sn_first[s];
+    const int h = static_cast<int>(F.sn_rowptr[s + 1] - F.sn_rowptr[s]);
+    const int64_t ld = h;
+    const double* P = Lx + F.sn_xoff[s];
+    const int* rows = F.sn_rows + F.sn_rowptr[s];
+    const int i0 = w + blockIdx.x * 512;
+    if (i0 >= h) return;
+    const int i1 = min(h, i0 + 512);
+    __shared__ double sx[512];
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) sx[i - i0] = ldcg(&xw[rows[i]]);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    double* tb = tbuf + (static_cast<int64_t>(inst) * gridDim.y + b) * tstride;
+    for (int j = warp; j < w; j += nwarp) {
+        double acc = 0.0;
+        for (int i = i0 + lane; i < i1; i += 32) acc = fma(P[i + j * ld], sx[i - i0], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if (lane == 0) atomicAdd(&tb[j], acc);
+    }
+}
+
+// backward, diagonal block: x = L11^-T (z - tbuf); clears tbuf for the next solve
+__global__ void k_big_bwd_diag(FactorView F, const int* __restrict__ big_sn, double* __restrict__ tbuf, int tstride,
+                               double* xw, int64_t xw_stride, int tri_cap) {
+    double* tri = madipm_smem;
+    double* st = tri + tri_cap;
+    const int inst = blockIdx.y;
+    const int b = blockIdx.x;
+    const int s = big_sn[b];
+    const double* Lx = F.Lx + inst * F.lx_stride;
+    xw += inst * xw_stride;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int fc = F.sn_first[s];
+    const int w = F.sn_first[s + 1] - fc;
+    const int64_t ld = F.sn_rowptr[s + 1] - F.sn_rowptr[s];
+    const double* P = Lx + F.sn_xoff[s];
+    double* tb = tbuf + (static_cast<int64_t>(inst) * gridDim.x + b) * tstride;
+    for (int j = tid; j < w; j += T) { st[j] = ldcg(&xw[fc + j]) - ldcg(&tb[j]); tb[j] = 0.0; }
+    for (int idx = tid; idx < w * w; idx += T) {
+        const int i = idx % w, j = idx / w;
+        if (i > j) tri[idx] = P[i + j * ld];
+    }
+    for (int j = w - 1; j > 0; --j) {
+        __syncthreads();
+        const double xj = st[j];
+        for (int k = tid; k < j; k += T) st[k] -= tri[j + k * w] * xj;
+    }
+    __syncthreads();
+    for (int j = tid; j < w; j += T) xw[fc + j] = st[j];
+}
+
+}  // namespace madipm

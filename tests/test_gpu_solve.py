@@ -107,6 +107,21 @@ def test_orderings_give_the_same_answer(ordering):
     compare(qp, regularization=FixedRegularization(1e-8, -1e-8), ordering=ordering, nd_leaf=80, subtree_work=20000)
 
 
+@pytest.mark.parametrize("maker,kw", [
+    (P.transportation_lp, dict(n_src=700, n_dst=700, n_arcs=30000)),      # C4 shape: dense trailing front
+    (P.sparse_lp, dict(n=40000, m=20000)),                                # C2 shape: tall panels
+])
+def test_big_front_path_matches_oracle(maker, kw):
+    """Fronts too large for one block go through k_big_diag / k_big_trsm / k_big_update (DMMA)."""
+    qp = maker(**kw)
+    s = MPCSolver(qp, kkt_system="NORMAL", regularization=FixedRegularization(1e-8, -1e-8))
+    first, rp, lev = s.h.symbolic("SUPER_FIRST"), s.h.symbolic("SUPER_ROWPTR"), s.h.symbolic("SUPER_LEVEL")
+    big = (np.diff(first) * np.diff(rp) > 16384) & (lev > 0)
+    assert big.any(), "the instance must exercise the multi-block path"
+    s.close()
+    compare(qp, kkt_system="NORMAL", regularization=FixedRegularization(1e-8, -1e-8))
+
+
 def test_max_iter_status():
     qp = P.maros_meszaros_like(seed=2, n=200, m=100, nnz=800)
     st, ref = compare(qp, max_iter=3, regularization=FixedRegularization(1e-8, -1e-8))
