@@ -32,7 +32,8 @@ struct DeviceState {
     std::vector<int> big_ptr;          // big (multi-block) supernodes, per level
     std::vector<int> big_rowblocks, big_rowblocks512, big_tiles;   // per level: grid sizes (max over its big supernodes)
     int* big_sn = nullptr;
-    double *big_ybuf = nullptr, *big_tbuf = nullptr;
+    double *big_ybuf = nullptr, *big_tbuf = nullptr, *big_zbuf = nullptr;
+    int big_zstride = 0;
     int big_max_per_level = 0;
     size_t smem_big_diag = 0, smem_big_trsm = 0, smem_big_update = 0;
 
@@ -265,7 +266,7 @@ int32_t tri_solve(madipm_handle* h) {
             const int* list = d->big_sn + d->big_ptr[l];
             LAUNCH(h, k_big_fwd_diag, dim3(nbig, d->B), 256, d->smem_tri, F, list, d->big_ybuf, 256, d->xw, N, d->tri_cap);
             if (d->big_rowblocks[l] > 0)
-                LAUNCH(h, k_big_fwd_below, dim3(d->big_rowblocks[l], nbig, d->B), kTrsmRows, 0, F, list, d->big_ybuf, 256, d->xw, N);
+                LAUNCH(h, k_big_fwd_below, dim3((d->big_rowblocks[l] + 1) / 2, nbig, d->B), 128, 0, F, list, d->big_ybuf, 256, d->xw, N);
         }
     }
     for (int l = d->n_levels - 1; l >= 0; --l) {
@@ -335,10 +336,10 @@ int32_t device_create(madipm_handle* h) {
             for (int q = s.level_ptr[l]; q < s.level_ptr[l + 1]; ++q) {
                 int sn = s.level_sn[q];
                 int64_t hs = s.sn_rowptr[sn + 1] - s.sn_rowptr[sn], ws = s.sn_first[sn + 1] - s.sn_first[sn];
-                if (hs * ws > kBigPanel) {
+                if (hs * ws > kBigPanel || hs - ws > 384) {
                     big_sn_host.push_back(sn);
                     int64_t nb = hs - ws, nt = (nb + kBigTile - 1) / kBigTile;
-                    rb = std::max<int>(rb, static_cast<int>((nb + kTrsmRows - 1) / kTrsmRows));
+                    rb = std::max<int>(rb, static_cast<int>(nt));
                     rb512 = std::max<int>(rb512, static_cast<int>((nb + 511) / 512));
                     tiles = std::max<int>(tiles, static_cast<int>(nt * (nt + 1) / 2));
                 } else small_sn.push_back(sn);
@@ -401,7 +402,7 @@ int32_t device_create(madipm_handle* h) {
         for (int sn = 0; sn < s.nsuper; ++sn) {
             int64_t hs = s.sn_rowptr[sn + 1] - s.sn_rowptr[sn], ws = s.sn_first[sn + 1] - s.sn_first[sn];
             if (s.sn_level[sn] > 0) {
-                if (hs * ws <= 16384) { max_panel_top = std::max(max_panel_top, hs * ws); max_h_top = std::max(max_h_top, hs); }
+                if (hs * ws <= 16384 && hs - ws <= 384) { max_panel_top = std::max(max_panel_top, hs * ws); max_h_top = std::max(max_h_top, hs); }
             } else max_h_sub = std::max(max_h_sub, hs);
         }
         d->n_sub_small = s.n_subtrees_small;
@@ -422,9 +423,9 @@ int32_t device_create(madipm_handle* h) {
     CUDA_OK(h, cudaFuncSetAttribute(k_factor_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_top));
     {
         const size_t mw = static_cast<size_t>(s.max_w);
-        d->smem_big_diag = (mw * mw + mw) * sizeof(double);
-        d->smem_big_trsm = (mw * mw + mw + mw * kTrsmLd) * sizeof(double);
-        d->smem_big_update = 2 * mw * kBigTileLd * sizeof(double) + 2 * kBigTile * sizeof(int64_t);
+        d->smem_big_diag = (2 * mw * mw + mw) * sizeof(double);
+        d->smem_big_trsm = 2 * mw * kBigTileLd * sizeof(double);
+        d->smem_big_update = std::max<size_t>(2 * mw, kBigTile) * kBigTileLd * sizeof(double) + 2 * kBigTile * sizeof(int64_t);
         if (!big_sn_host.empty()) {
             if (d->smem_big_trsm > 220 * 1024) { h->error = "max_width too large for the big-front kernels"; return MADIPM_BAD_ARGUMENT; }
             CUDA_OK(h, cudaFuncSetAttribute(k_big_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_big_diag));
@@ -433,6 +434,8 @@ int32_t device_create(madipm_handle* h) {
             const size_t nbuf = static_cast<size_t>(B) * d->big_max_per_level * 256;
             if ((rc = dev_alloc(h, &d->big_ybuf, nbuf))) return rc;
             if ((rc = dev_alloc(h, &d->big_tbuf, nbuf))) return rc;
+            if ((rc = dev_alloc(h, &d->big_zbuf, static_cast<size_t>(B) * d->big_max_per_level * mw * mw))) return rc;
+            d->big_zstride = static_cast<int>(mw * mw);
             CUDA_OK(h, cudaMemsetAsync(d->big_tbuf, 0, nbuf * sizeof(double), d->stream));
         }
     }
@@ -686,16 +689,17 @@ int32_t madipm_factorize(madipm_handle* h, int32_t* n_failed) {
         if (light) cudaEventRecord(d->ev3, d->stream);
         for (int l = 0; l < d->n_levels; ++l) {
             const int cnt = d->level_ptr[l + 1] - d->level_ptr[l];
-            if (cnt > 0)
-                LAUNCH(h, k_factor_level, dim3(cnt, B), 256, d->smem_top, make_factor_view(*d, d->cap_top), d->level_sn + d->level_ptr[l]);
             const int nbig = d->big_ptr[l + 1] - d->big_ptr[l];
+            const int exclusive = (cnt + nbig == 1) ? 1 : 0;
+            if (cnt > 0)
+                LAUNCH(h, k_factor_level, dim3(cnt, B), 256, d->smem_top, make_factor_view(*d, d->cap_top), d->level_sn + d->level_ptr[l], exclusive);
             if (nbig > 0) {
                 const FactorView F = make_factor_view(*d, 0);
                 const int* list = d->big_sn + d->big_ptr[l];
-                LAUNCH(h, k_big_diag, dim3(nbig, B), 256, d->smem_big_diag, F, list);
+                LAUNCH(h, k_big_diag, dim3(nbig, B), 256, d->smem_big_diag, F, list, d->big_zbuf, d->big_zstride);
                 if (d->big_rowblocks[l] > 0) {
-                    LAUNCH(h, k_big_trsm, dim3(d->big_rowblocks[l], nbig, B), kTrsmRows, d->smem_big_trsm, F, list);
-                    LAUNCH(h, k_big_update, dim3(d->big_tiles[l], nbig, B), 128, d->smem_big_update, F, list);
+                    LAUNCH(h, k_big_trsm, dim3(d->big_rowblocks[l], nbig, B), 128, d->smem_big_trsm, F, list, d->big_zbuf, d->big_zstride);
+                    LAUNCH(h, k_big_update, dim3(d->big_tiles[l], nbig, B), 128, d->smem_big_update, F, list, exclusive);
                 }
             }
         }

@@ -2,7 +2,7 @@
 // three grid-wide kernels per level (all big supernodes of the level batched in blockIdx.y):
 //
 //   k_big_diag    one block per supernode: dense LDL' of the w x w diagonal block in shared memory
-//   k_big_trsm    row blocks of 128: L21 = A21 L11^-T D^-1
+//   k_big_trsm    row blocks of 64: L21 = A21 Z, Z = L11^-T D^-1 from k_big_diag (a DMMA GEMM)
 //   k_big_update  64 x 64 tiles of the Schur complement S = L21 D L21' on the FP64 tensor cores
 //                 (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4), operands staged k-major in shared memory
 //                 with a leading dimension = 4 mod 16 doubles (bank-conflict-free fragment loads),
@@ -19,8 +19,6 @@ namespace madipm {
 
 constexpr int kBigTile = 64;          // output tile edge of k_big_update
 constexpr int kBigTileLd = 68;        // 64 + 4: leading dimension = 4 mod 16 doubles
-constexpr int kTrsmRows = 128;
-constexpr int kTrsmLd = 132;
 
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -28,8 +26,10 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 }
 
 // ---- diagonal block -----------------------------------------------------------------------------
-// shared: [w*w doubles block][w doubles ucol]
-__global__ void k_big_diag(FactorView F, const int* __restrict__ big_sn) {
+// Factors the w x w diagonal block and also writes Z = L11^-T D^-1 (k-major, ld = w) to zbuf so that the
+// triangular solve of the rows below becomes a GEMM on the tensor cores (k_big_trsm).
+// shared: [w*w doubles block][w*w doubles inverse][w doubles ucol]
+__global__ void k_big_diag(FactorView F, const int* __restrict__ big_sn, double* __restrict__ zbuf, int zstride) {
     const int inst = blockIdx.y;
     const int s = big_sn[blockIdx.x];
     double* Lx = F.Lx + inst * F.lx_stride;
@@ -39,7 +39,8 @@ __global__ void k_big_diag(FactorView F, const int* __restrict__ big_sn) {
     const int64_t ld = F.sn_rowptr[s + 1] - F.sn_rowptr[s];
     double* P = Lx + F.sn_xoff[s];
     double* Bs = madipm_smem;
-    double* ucol = Bs + w * w;
+    double* Xs = Bs + w * w;
+    double* ucol = Xs + w * w;
     for (int idx = tid; idx < w * w; idx += T) {
         const int i = idx % w, j = idx / w;
         Bs[idx] = ldcg(&P[i + j * ld]);
@@ -64,48 +65,88 @@ __global__ void k_big_diag(FactorView F, const int* __restrict__ big_sn) {
         const int i = idx % w, j = idx / w;
         if (i >= j) P[i + j * ld] = Bs[idx];
     }
-}
-
-// ---- L21 = A21 L11^-T D^-1 ----------------------------------------------------------------------
-// One thread per row.  shared: [w*w doubles M = unit-lower L11 scaled by D (M[j',j] = d_j L11[j',j])]
-//                              [w doubles 1/d][w * kTrsmLd doubles row tile, k-major]
-__global__ void k_big_trsm(FactorView F, const int* __restrict__ big_sn) {
-    const int inst = blockIdx.z;
-    const int s = big_sn[blockIdx.y];
-    double* Lx = F.Lx + inst * F.lx_stride;
-    const int tid = threadIdx.x, T = blockDim.x;
-    const int w = F.sn_first[s + 1] - F.sn_first[s];
-    const int h = static_cast<int>(F.sn_rowptr[s + 1] - F.sn_rowptr[s]);
-    const int64_t ld = h;
-    const int r0 = w + blockIdx.x * kTrsmRows;
-    if (r0 >= h) return;
-    const int nr = min(kTrsmRows, h - r0);
-    double* P = Lx + F.sn_xoff[s];
-    double* M = madipm_smem;
-    double* dinv = M + w * w;
-    double* tile = dinv + w;
-    for (int idx = tid; idx < w * w; idx += T) {
-        const int i = idx % w, j = idx / w;
-        if (i > j) M[idx] = P[i + j * ld] * P[j + j * ld];      // d_j * L11[i, j]
-    }
-    for (int j = tid; j < w; j += T) dinv[j] = 1.0 / P[j + j * ld];
-    for (int idx = tid; idx < w * nr; idx += T) {
-        const int r = idx % nr, j = idx / nr;
-        tile[j * kTrsmLd + r] = ldcg(&P[r0 + r + j * ld]);
-    }
-    __syncthreads();
-    if (tid < nr) {
-        for (int j = 0; j < w; ++j) {
-            const double a = tile[j * kTrsmLd + tid];
-            const double l = a * dinv[j];                        // l_j = a_j / d_j
-            tile[j * kTrsmLd + tid] = l;
-            for (int jp = j + 1; jp < w; ++jp) tile[jp * kTrsmLd + tid] -= l * M[jp + j * w];   // a_j' -= l_j d_j L11[j', j]
+    // X = L11^-1 (unit lower), one thread per column c: x_i = -sum_{k=c}^{i-1} L[i,k] x_k
+    for (int c = tid; c < w; c += T) {
+        Xs[c + c * w] = 1.0;
+        for (int i = c + 1; i < w; ++i) {
+            double v = 0.0;
+            for (int k = c; k < i; ++k) v = fma(Bs[i + k * w], Xs[k + c * w], v);
+            Xs[i + c * w] = -v;
         }
     }
     __syncthreads();
-    for (int idx = tid; idx < w * nr; idx += T) {
-        const int r = idx % nr, j = idx / nr;
-        P[r0 + r + j * ld] = tile[j * kTrsmLd + r];
+    // Z[k][n] = X[n][k] / d_n for k <= n, 0 otherwise
+    double* Z = zbuf + (static_cast<int64_t>(inst) * gridDim.x + blockIdx.x) * zstride;
+    for (int idx = tid; idx < w * w; idx += T) {
+        const int n = idx % w, k = idx / w;
+        Z[k * w + n] = (k <= n) ? Xs[n + k * w] / Bs[n * (w + 1)] : 0.0;
+    }
+}
+
+// ---- L21 = A21 Z,  Z = L11^-T D^-1  (GEMM on the FP64 tensor cores) --------------------------------
+// grid.x = block of 64 rows below the diagonal block, grid.y = big supernode, grid.z = instance.
+// 128 threads = 4 warps, each 32 rows x 32 output columns per pass over the (up to w) output columns.
+// shared: [w * 68 doubles A rows, k-major][w * 68 doubles Z chunk, k-major]
+__global__ void __launch_bounds__(128)
+k_big_trsm(FactorView F, const int* __restrict__ big_sn, const double* __restrict__ zbuf, int zstride) {
+    const int inst = blockIdx.z;
+    const int s = big_sn[blockIdx.y];
+    double* Lx = F.Lx + inst * F.lx_stride;
+    const int tid = threadIdx.x;
+    const int w = F.sn_first[s + 1] - F.sn_first[s];
+    const int h = static_cast<int>(F.sn_rowptr[s + 1] - F.sn_rowptr[s]);
+    const int64_t ld = h;
+    const int r0 = w + blockIdx.x * kBigTile;
+    if (r0 >= h) return;
+    const int nr = min(kBigTile, h - r0);
+    double* P = Lx + F.sn_xoff[s];
+    const double* Z = zbuf + (static_cast<int64_t>(inst) * gridDim.y + blockIdx.y) * zstride;
+    double* As = madipm_smem;
+    double* Zs = As + w * kBigTileLd;
+    for (int idx = tid; idx < w * kBigTile; idx += 128) {
+        const int r = idx % kBigTile, k = idx / kBigTile;
+        As[k * kBigTileLd + r] = (r < nr) ? ldcg(&P[r0 + r + k * ld]) : 0.0;
+    }
+    const int lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    const int fr = lane >> 2, fk = lane & 3;
+    for (int n0 = 0; n0 < w; n0 += kBigTile) {           // output column chunk
+        const int nn = min(kBigTile, w - n0);
+        __syncthreads();
+        for (int idx = tid; idx < w * kBigTile; idx += 128) {
+            const int n = idx % kBigTile, k = idx / kBigTile;
+            Zs[k * kBigTileLd + n] = (n < nn) ? Z[k * w + n0 + n] : 0.0;
+        }
+        __syncthreads();
+        double acc[4][4][2];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+        const int kmax = min(w, n0 + nn);                 // Z is upper triangular: k <= n
+        for (int k0 = 0; k0 < kmax; k0 += 4) {
+            double af[4], bf[4];
+            const int kk = k0 + fk;
+            const bool kin = kk < w;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) af[a] = kin ? As[kk * kBigTileLd + wm + a * 8 + fr] : 0.0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) bf[b] = kin ? Zs[kk * kBigTileLd + wn + b * 8 + fr] : 0.0;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int li = wm + a * 8 + fr;
+                    const int lj = wn + b * 8 + 2 * fk + e;
+                    if (li < nr && lj < nn) P[r0 + li + static_cast<int64_t>(n0 + lj) * ld] = acc[a][b][e];
+                }
     }
 }
 
@@ -115,7 +156,7 @@ __global__ void k_big_trsm(FactorView F, const int* __restrict__ big_sn) {
 // shared: [w * 68 doubles A (rows of tile ti)][w * 68 doubles B = D L21' (rows of tile tj)]
 //         [64 int64 colbase][64 int64 relbase]
 __global__ void __launch_bounds__(128)
-k_big_update(FactorView F, const int* __restrict__ big_sn) {
+k_big_update(FactorView F, const int* __restrict__ big_sn, int exclusive) {
     const int inst = blockIdx.z;
     const int s = big_sn[blockIdx.y];
     double* Lx = F.Lx + inst * F.lx_stride;
@@ -136,7 +177,7 @@ k_big_update(FactorView F, const int* __restrict__ big_sn) {
     const int* rows = F.sn_rows + F.sn_rowptr[s];
     double* As = madipm_smem;
     double* Bs = As + w * kBigTileLd;
-    int64_t* colb = reinterpret_cast<int64_t*>(Bs + w * kBigTileLd);
+    int64_t* colb = reinterpret_cast<int64_t*>(As + max(2 * w, kBigTile) * kBigTileLd);   // past the operands AND the epilogue tile
     int64_t* relb = colb + kBigTile;
     const int i0 = w + ti * kBigTile, j0 = w + tj * kBigTile;
     const int ni = min(kBigTile, h - i0), nj = min(kBigTile, h - j0);
@@ -172,21 +213,44 @@ k_big_update(FactorView F, const int* __restrict__ big_sn) {
 #pragma unroll
             for (int b = 0; b < 4; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
     }
-    // scatter: lane holds C[row = lane/4][col = 2*(lane%4) + {0,1}] of every 8 x 8 tile
+    // epilogue: transpose the tile through shared memory (reusing the operand space) so that consecutive
+    // lanes own consecutive rows of one target column: coalesced RMW / RED instead of 8-row fragments.
+    __syncthreads();
+    double* Cs = madipm_smem;                                  // [64 columns][kBigTileLd rows]
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int li = wm + a * 8 + fr;            // row inside the tile
-                const int lj = wn + b * 8 + 2 * fk + e;    // column inside the tile
-                const int i = i0 + li, jj = j0 + lj;
-                if (li < ni && lj < nj && i >= jj) {
-                    const int pos = target_pos(F, relb[lj], i, rows, jj);
-                    atomicAdd(Lx + colb[lj] + pos, -acc[a][b][e]);
-                }
+            for (int e = 0; e < 2; ++e)
+                Cs[(wn + b * 8 + 2 * fk + e) * kBigTileLd + wm + a * 8 + fr] = acc[a][b][e];
+    __syncthreads();
+    const int li = tid & 63;                                   // row inside the tile
+    const int i = i0 + li;
+    const int cpar = tid >> 6;                                 // this thread takes columns cpar, cpar + 2, ...
+    if (li < ni) {
+        for (int c0 = 0; c0 < kBigTile; c0 += 16) {            // 8 columns per thread per batch
+            double* q[8];
+            double old[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int lj = c0 + 2 * u + cpar;
+                const int jj = j0 + lj;
+                q[u] = (lj < nj && i >= jj) ? Lx + colb[lj] + target_pos(F, relb[lj], i, rows, jj) : nullptr;
             }
+            if (exclusive) {                                   // single supernode in this level: no other writer
+#pragma unroll
+                for (int u = 0; u < 8; ++u) old[u] = q[u] ? ldcg(q[u]) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (q[u]) *q[u] = old[u] - Cs[(c0 + 2 * u + cpar) * kBigTileLd + li];
+            } else {
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (q[u]) atomicAdd(q[u], -Cs[(c0 + 2 * u + cpar) * kBigTileLd + li]);
+            }
+        }
+    }
 }
 
 // ---- multi-block triangular-solve helpers for tall panels ------------------------------------------

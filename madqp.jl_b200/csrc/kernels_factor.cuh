@@ -67,15 +67,19 @@ __device__ __forceinline__ int target_pos(const FactorView& F, int64_t rb, int i
 
 // Schur complement S(i, jj) = sum_k L(i,k) d_k L(jj,k), i >= jj >= w, pushed into the ancestors.
 // Lp: the factored panel (shared or global), ld = h.  Warps own columns jj, lanes own rows i.
+// excl_cols: target columns below this index are owned exclusively by the calling block right now (the
+// rest of its subtree, walked sequentially), so the update is a plain read-modify-write; FP64 atomics
+// (which sustain only ~4e10 updates/s chip-wide) are kept for targets other blocks may also be updating.
 template <bool SHARED>
 __device__ __forceinline__ void push_update(const FactorView& F, int s, double* Lx, const double* Lp, const double* dk,
-                                            int w, int h, const int* rows) {
+                                            int w, int h, const int* rows, int excl_cols) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int64_t* colb = F.row_colbase + F.sn_rowptr[s];
     const int64_t* relb = F.row_relbase + F.sn_rowptr[s];
     for (int jj = w + warp; jj < h; jj += nwarp) {
         const int64_t cb = __ldg(colb + jj);
         const int64_t rb = __ldg(relb + jj);
+        const bool excl = __ldg(rows + jj) < excl_cols;
         double* dst = Lx + cb;
         for (int i = jj + lane; i < h; i += 32) {
             double acc = 0.0;
@@ -86,13 +90,15 @@ __device__ __forceinline__ void push_update(const FactorView& F, int s, double* 
                 for (int k = 0; k < w; ++k)
                     acc = fma(ldcg(&Lp[i + static_cast<int64_t>(k) * h]), dk[k] * ldcg(&Lp[jj + static_cast<int64_t>(k) * h]), acc);
             }
-            atomicAdd(dst + target_pos(F, rb, i, rows, jj), -acc);
+            double* q = dst + target_pos(F, rb, i, rows, jj);
+            if (excl) *q = ldcg(q) - acc;
+            else atomicAdd(q, -acc);
         }
     }
 }
 
 // ---- staged path: the panel lives in shared memory for the whole column loop -------------------
-__device__ void factor_supernode_staged(const FactorView& F, int s, double* Lx, int* fail, double* Ps, double* ucol, double* dk) {
+__device__ void factor_supernode_staged(const FactorView& F, int s, double* Lx, int* fail, double* Ps, double* ucol, double* dk, int excl_cols) {
     const int tid = threadIdx.x, T = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
     const int fc = F.sn_first[s];
@@ -128,11 +134,11 @@ __device__ void factor_supernode_staged(const FactorView& F, int s, double* Lx, 
     if (h == w) return;
     for (int k = tid; k < w; k += T) dk[k] = Ps[k * (h + 1)];
     __syncthreads();
-    push_update<true>(F, s, Lx, Ps, dk, w, h, rows);
+    push_update<true>(F, s, Lx, Ps, dk, w, h, rows, excl_cols);
 }
 
 // ---- in-place path: panel stays in global memory (L2); only the pivot column is staged ----------
-__device__ void factor_supernode_inplace(const FactorView& F, int s, double* Lx, int* fail, double* su, double* sl) {
+__device__ void factor_supernode_inplace(const FactorView& F, int s, double* Lx, int* fail, double* su, double* sl, int excl_cols) {
     const int tid = threadIdx.x, T = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
     const int fc = F.sn_first[s];
@@ -165,37 +171,39 @@ __device__ void factor_supernode_inplace(const FactorView& F, int s, double* Lx,
     if (h == w) return;
     for (int k = tid; k < w; k += T) sl[k] = ldcg(&P[k + k * ld]);   // D
     __syncthreads();
-    push_update<false>(F, s, Lx, P, sl, w, h, rows);
+    push_update<false>(F, s, Lx, P, sl, w, h, rows, excl_cols);
 }
 
 extern __shared__ double madipm_smem[];
 
 // shared layout: [panel_cap doubles: panel | pivot column of the in-place path]
 //                [panel_cap / 2 + 64 doubles: ucol][256 doubles: dk / sl]
-__device__ __forceinline__ void factor_dispatch(const FactorView& F, int s, double* Lx, int* fail) {
+__device__ __forceinline__ void factor_dispatch(const FactorView& F, int s, double* Lx, int* fail, int excl_cols) {
     double* Ps = madipm_smem;
     double* ucol = Ps + F.panel_cap;
     double* dk = ucol + F.panel_cap / 2 + 64;
     const int w = F.sn_first[s + 1] - F.sn_first[s];
     const int h = static_cast<int>(F.sn_rowptr[s + 1] - F.sn_rowptr[s]);
     const bool fits = static_cast<int64_t>(h) * w <= F.panel_cap && (w == 1 || h <= F.panel_cap / 2 + 64);
-    if (fits) factor_supernode_staged(F, s, Lx, fail, Ps, ucol, dk);
-    else factor_supernode_inplace(F, s, Lx, fail, Ps, dk);
+    if (fits) factor_supernode_staged(F, s, Lx, fail, Ps, ucol, dk, excl_cols);
+    else factor_supernode_inplace(F, s, Lx, fail, Ps, dk, excl_cols);
 }
 
 __global__ void k_factor_subtrees(FactorView F, const int* __restrict__ sub_first, const int* __restrict__ sub_last) {
     const int inst = blockIdx.y;
     double* Lx = F.Lx + inst * F.lx_stride;
     const int first = sub_first[blockIdx.x], last = sub_last[blockIdx.x];
+    const int excl_cols = F.sn_first[last + 1];     // columns of this subtree: nobody else touches their panels now
     for (int s = first; s <= last; ++s) {
-        factor_dispatch(F, s, Lx, F.fail + inst);
+        factor_dispatch(F, s, Lx, F.fail + inst, excl_cols);
         __threadfence();
     }
 }
 
-__global__ void k_factor_level(FactorView F, const int* __restrict__ level_sn) {
+// exclusive != 0: the level holds a single supernode, so every target is exclusively ours
+__global__ void k_factor_level(FactorView F, const int* __restrict__ level_sn, int exclusive) {
     const int inst = blockIdx.y;
-    factor_dispatch(F, level_sn[blockIdx.x], F.Lx + inst * F.lx_stride, F.fail + inst);
+    factor_dispatch(F, level_sn[blockIdx.x], F.Lx + inst * F.lx_stride, F.fail + inst, exclusive ? INT32_MAX : 0);
 }
 
 // Lx[asm_map[k]] = nzval[k]  (after a memset of Lx): the KKT values enter the panels through

@@ -50,3 +50,9 @@ if "prof" in which:
         print("   %-16s %9.2f ms  %6d calls  %8.3f ms/call  %6.2f ms/iter" % (k, ms, calls, ms / max(calls, 1), ms / st.iter[0]))
     print("   sum classes %.1f ms" % sum(v[0] for k, v in pr.items() if k != "factor_subtrees"))
     s.close()
+if "c2" in which:
+    run(P.sparse_lp(), "C2", ok=False, kkt_system="NORMAL", regularization=FixedRegularization(1e-8, -1e-8))
+if "c4" in which:
+    run(P.transportation_lp(), "C4", ok=False, kkt_system="NORMAL", regularization=FixedRegularization(1e-8, -1e-8))
+if "c4h" in which:
+    run(P.transportation_lp(n_src=12500, n_dst=12500, n_arcs=1000000), "C4half", ok=False, kkt_system="NORMAL", regularization=FixedRegularization(1e-8, -1e-8))
