@@ -193,10 +193,12 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     qps, kkt, wname = make_workload(args.workload, args.scale)
+    from madqp_jl_b200 import batch
     sharded = args.workload == "C5" and world > 1
+    n_items = len(qps)
     if sharded:   # independent instances: rank r takes a contiguous slice, no data-path collective
-        per = (len(qps) + world - 1) // world
-        qps = qps[rank * per:(rank + 1) * per]
+        lo, hi = batch.shard_range(n_items, rank, world)
+        qps = qps[lo:hi]
     solver = MPCSolver(qps if len(qps) > 1 else qps[0], kkt_system=kkt, device=local, **solver_options())
     solver.keep_snapshot = True
     h = solver.h
@@ -248,10 +250,11 @@ def run_ours(args):
 
     # ---- gather per-instance status (the only collective on the path)
     if world > 1:
-        status_code = torch.tensor([1.0 if s == "SOLVE_SUCCEEDED" else 0.0 for s in res["stats"].status], dtype=torch.float64, device="cuda")
-        gathered = [torch.zeros_like(status_code) for _ in range(world)]
-        dist.all_gather(gathered, status_code)
-        ok = ok and bool(torch.cat(gathered).min().item() == 1.0)
+        st = res["stats"]
+        rec = batch.make_records(st.status, st.iter, st.objective, st.inf_pr, st.inf_du, np.full(len(st.status), res["sec"]))
+        table = batch.gather_records(rec, n_items if sharded else len(st.status) * world, device="cuda") if sharded else \
+            batch.gather_records(rec, len(st.status) * world, device="cuda")
+        ok = ok and bool(np.all(table[:, 0] == batch.STATUS_CODES["SOLVE_SUCCEEDED"]))
 
     if rank == 0:
         peaks = {}

@@ -22,6 +22,7 @@ a Julia caller would pass.
 """
 from __future__ import annotations
 
+import functools
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -252,6 +253,7 @@ def transportation_lp(seed=0, n_src=25_000, n_dst=25_000, n_arcs=2_000_000):
                    meta=dict(config="C4", seed=seed, n_src=n_src, n_dst=n_dst))
 
 
+@functools.lru_cache(maxsize=8)
 def small_qp_pattern(seed=0, n=200, m=100, nnz=2000):
     """Pattern shared by the C5 batch (10% dense A, tridiagonal Q)."""
     rng = np.random.default_rng(seed)

@@ -1,0 +1,69 @@
+"""Isolated roofline measurement of the streaming kernels (SpMV, assembly, vector phases) on config C3.
+
+Each kernel is timed alone with CUDA events on the solver's stream, cold (L2 flushed by writing a 512 MB
+buffer between repetitions) and warm (back to back), against the algorithmic bytes of SURVEY 8d and the
+measured HBM peak of MEASURED_PEAKS.json.  Output: one JSON line per kernel (kept under profiles/).
+"""
+import json, os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from madqp_jl_b200 import _lib
+from madqp_jl_b200.mpc import MPCSolver, FixedRegularization
+
+wl = sys.argv[1] if len(sys.argv) > 1 else "C3"
+qps, kkt, name = bench.make_workload(wl)
+qp = qps[0]
+s = MPCSolver(qp, kkt_system=kkt, regularization=FixedRegularization(1e-8, -1e-8))
+s.prepare_host(); s.upload(); s.start(); s._update_regularization()
+h = s.h
+h.set_aug_diagonal_reg(s.del_w, s.del_c); h.build_kkt(); h.factorize(); h.set_predictive_rhs(); h.solve_system("D", "P")
+info = s.info
+peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) \
+    if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
+stream = torch.cuda.ExternalStream(h.stream())
+flush = torch.empty(128 * 1024 * 1024, dtype=torch.float32, device="cuda")
+n, m, nlb, nub = s.n, s.m, s.nlb, s.nub
+nnzA, nnzQ = qp.nnzj + s.ns, (2 * qp.nnzh - int(np.sum(qp.H_rows == qp.H_cols))) if qp.nnzh else 0
+L = n + m + nlb + nub
+
+def spmv_bytes(nnz, rows, cols):
+    return 12 * nnz + 4 * (rows + 1) + 8 * cols + 8 * rows
+
+KERNELS = {
+    "spmv_A   (k_spmv, y = A x)": (lambda: h.spmv(_lib.OP_A, "C", "X"), spmv_bytes(nnzA, m, n)),
+    "spmv_AT  (k_spmv, y = A'x)": (lambda: h.spmv(_lib.OP_AT, "JACL", "Y"), spmv_bytes(nnzA, n, m)),
+    "spmv_Q   (k_spmv, y = Q x)": (lambda: h.spmv(_lib.OP_Q, "F", "X"), spmv_bytes(nnzQ, n, n)) if nnzQ else None,
+    "assembly K1 (k_set_aug_diagonal_reg)": (lambda: h.set_aug_diagonal_reg(1e-8, -1e-8), 8 * (5 * (nlb + nub) + 2 * n + m) + 8 * (nlb + nub) + 8 * n),
+    "assembly K2a (k_build_kkt_k2)": (lambda: h.build_kkt(), 28 * (n + m)) if kkt == "K2" else (lambda: h.build_kkt(), 12 * nnzA + 8 * n + 12 * info["kkt_nnz"] + 12 * info["n_products"]),
+    "rhs K9 (k_set_rhs predictive)": (lambda: h.set_predictive_rhs(), 8 * (5 * n + 2 * m + 4 * (nlb + nub)) + 4 * (nlb + nub)),
+    "kkt_mul K5 (3 spmv + tail)": (lambda: h.kkt_mul("W1", "D", -1.0, 1.0), spmv_bytes(nnzA, m, n) + spmv_bytes(nnzA, n, m) + (spmv_bytes(nnzQ, n, n) if nnzQ else 0) + 8 * 4 * L),
+    "eval_model K8 (k_eval_model)": (lambda: h.eval_model(0.0, want_obj=False), spmv_bytes(nnzA, m, n) + spmv_bytes(nnzQ, n, n) + 8 * (2 * n + m)),
+    "update K14 (k_update_iterate)": (lambda: h.update_iterate(0.0, 0.0, 1e-3), 8 * (9 * n + 2 * m) + 8 * (nlb + nub)),
+}
+
+def timed(fn, cold, reps=20):
+    ts = []
+    for _ in range(reps):
+        if cold:
+            flush.zero_()
+            torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream); fn(); e1.record(stream)
+        h.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts)) * 1e-3
+
+for kname, spec in KERNELS.items():
+    if spec is None:
+        continue
+    fn, nbytes = spec
+    for _ in range(3):
+        fn()
+    h.synchronize()
+    tc, tw = timed(fn, True), timed(fn, False)
+    print(json.dumps(dict(workload=wl, kernel=kname, algorithmic_MB=nbytes / 1e6, cold_us=tc * 1e6, warm_us=tw * 1e6,
+                          cold_GBs=nbytes / tc / 1e9, warm_GBs=nbytes / tw / 1e9, peak_GBs=peak,
+                          frac_cold=nbytes / tc / 1e9 / peak, frac_warm=nbytes / tw / 1e9 / peak)), flush=True)
+s.close()
