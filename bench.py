@@ -203,6 +203,7 @@ def run_ours(args):
     solver.keep_snapshot = True
     h = solver.h
     info = solver.info
+    c_doubles = int(solver.h.symbolic("SUPER_COFF")[-1])     # packed contribution blocks of the small supernodes
 
     # ---- warm-up (full end-to-end solves)
     stats = None
@@ -264,16 +265,16 @@ def run_ours(args):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
-        # dominant kernel: k_factor_subtrees.  Algorithmic bytes per launch:
-        # every panel entry is read and written once (16 B), the KKT values enter once (8 B + 8 B map).
+        # dominant kernel: k_tree<0> (the persistent numeric-factorisation kernel).  Algorithmic bytes per launch
+        # (DESIGN.md section 4): every panel entry and every contribution-block entry is read once and written once.
         prof = res["prof"]
-        sub_ms, sub_calls = prof["factor_subtrees"]
+        sub_ms, sub_calls = prof["factor_tree"]
         fac_ms, fac_calls = prof["factor"]
         B = len(qps)
-        alg_bytes = 16.0 * info["nnz_stored"] * B
+        alg_bytes = 16.0 * (info["nnz_stored"] + c_doubles) * B
         sub_avg_s = (sub_ms / max(sub_calls, 1)) / 1e3
         achieved = alg_bytes / sub_avg_s / 1e9 if sub_avg_s > 0 else 0.0
-        roofline = dict(bound="hbm", kernel="k_factor_subtrees", achieved=achieved, peak=hbm_peak, unit="GB/s",
+        roofline = dict(bound="hbm", kernel="k_tree<0> (factor)", achieved=achieved, peak=hbm_peak, unit="GB/s",
                         frac=achieved / hbm_peak, traffic=None, peak_source=peak_src,
                         algorithmic_bytes_per_launch=alg_bytes, avg_launch_ms=sub_avg_s * 1e3, launches=sub_calls,
                         share_of_step=sub_ms / 1e3 / res["sec"] if res["sec"] > 0 else None,
@@ -281,7 +282,7 @@ def run_ours(args):
                         factor_tflops=info["factor_flops"] * B / ((fac_ms / max(fac_calls, 1)) / 1e3) / 1e12 if fac_ms > 0 else None)
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            roofline["traffic"] = traffic.get("k_factor_subtrees_dram_bytes_per_launch")
+            roofline["traffic"] = traffic.get("k_tree_factor_dram_bytes_per_launch")
         except (OSError, ValueError):
             pass
         cpu = None
@@ -295,7 +296,7 @@ def run_ours(args):
             scaling="strong" if sharded else "weak", vs_baseline=None, dtype="f64", data="synthetic",
             config=dict(workload=wname, kkt=kkt, n=qps[0].nvar, m=qps[0].ncon, nnz_A=qps[0].nnzj, nnz_Q=qps[0].nnzh,
                         instances_per_gpu=len(qps), replicas=n_rep, kkt_order=info["kkt_order"], nnz_L=info["nnz_L"],
-                        factor_flops=info["factor_flops"], nsuper=info["nsuper"], n_subtrees=info["n_subtrees"],
+                        factor_flops=info["factor_flops"], nsuper=info["nsuper"], n_block_tasks=info["n_block_tasks"], n_warp_tasks=info["n_warp_tasks"], n_big=info["n_big"],
                         n_levels=info["n_levels"], ordering="nested dissection + AMD leaves, constraints delayed",
                         options="tol=1e-8 max_iter=300 AdaptiveStep(0.995) FixedRegularization(1e-8,-1e-8) scaling max_ncorr=0",
                         l2="inputs larger than L2: factor panels %.0f MB + operators, no flush" % (info["nnz_stored"] * 8 / 1e6),

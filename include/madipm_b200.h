@@ -50,7 +50,8 @@ typedef struct {
     int32_t max_width;      /* supernode width cap */
     int32_t relax_small;    /* relaxed amalgamation, see csrc/symbolic.hpp */
     double relax_zeros[3];
-    int64_t subtree_work;   /* flop budget of one bottom subtree */
+    int64_t block_panel;    /* largest panel (doubles) one thread block factorises in shared memory; larger
+                               supernodes take the multi-block (DMMA) path.  See csrc/symbolic.hpp */
     int32_t device;         /* CUDA device ordinal */
     int32_t batch;          /* instances sharing one pattern (config C5); 1 for a single solve */
     int32_t nd_leaf;        /* nested dissection leaf size, 0 = automatic */
@@ -89,11 +90,12 @@ typedef struct {
     int64_t nnz_stored;      /* doubles of supernodal panel storage */
     double factor_flops;     /* sum_j colcount_j^2 */
     int32_t nsuper, max_height, max_width;
-    int32_t n_subtrees, n_levels;
+    int32_t n_warp_tasks;    /* supernodes handled by one warp */
+    int32_t n_levels;        /* heights of the supernodal elimination tree = phases of the factor / solve kernels */
     int64_t n_products;      /* normal equations: length of the product lists */
     int64_t kkt_vec_len;     /* n_tot + ncon + nlb + nub: length of an UnreducedKKTVector */
-    int32_t n_subtrees_small;   /* subtrees whose panels all fit the high-occupancy launch */
-    int32_t subtree_max_panel;  /* largest panel (doubles) inside a subtree */
+    int32_t n_block_tasks;   /* supernodes handled by one thread block */
+    int32_t n_big;           /* supernodes on the multi-block path */
 } madipm_info;
 int32_t madipm_get_info(const madipm_handle* h, madipm_info* out);
 
@@ -115,11 +117,19 @@ enum {
     MADIPM_SYM_A_ROWPTR = 12,     /* CSR of A incl. slack columns */
     MADIPM_SYM_A_COLIND = 13,
     MADIPM_SYM_A_CSR_MAP = 14,    /* CSR slot -> COO index (0-based A_csr_map, normalkkt.jl:83-88) */
-    MADIPM_SYM_SUPER_LEVEL = 15,
+    MADIPM_SYM_SUPER_LEVEL = 15,  /* height of the supernode in the supernodal elimination tree (0 = leaf) */
     MADIPM_SYM_PROD_PTR = 16,     /* normal equations product lists */
     MADIPM_SYM_PROD_A = 17,
     MADIPM_SYM_PROD_B = 18,
-    MADIPM_SYM_PROD_K = 19
+    MADIPM_SYM_PROD_K = 19,
+    MADIPM_SYM_CHILD_PTR = 20,    /* nsuper + 1: children lists of the supernodal elimination tree */
+    MADIPM_SYM_CHILD_IDX = 21,
+    MADIPM_SYM_SUPER_KIND = 22,   /* 0 small (parent pulls its contribution block), 1 small under a big parent, 2 big */
+    MADIPM_SYM_PAR_POS = 23,      /* like SUPER_ROWS: position of a below-row in the parent's row list */
+    MADIPM_SYM_SUPER_COFF = 24,   /* nsuper + 1: offsets of the packed contribution blocks */
+    MADIPM_SYM_TASK_SN = 25,      /* small supernodes in schedule order */
+    MADIPM_SYM_PHASE_PTR = 26,    /* n_levels + 1 into TASK_SN */
+    MADIPM_SYM_PHASE_NBLOCK = 27  /* n_levels: leading tasks of a phase that take a whole thread block */
 };
 int32_t madipm_get_symbolic(const madipm_handle* h, int32_t which, int64_t* out, int64_t cap, int64_t* len);
 
@@ -244,9 +254,9 @@ int64_t madipm_launch_count(const madipm_handle* h);
 /* accumulated device milliseconds per kernel class since the last reset (CUDA events on the
  * handle's stream; enabled by madipm_profile(h, 1)) */
 enum { MADIPM_T_ASSEMBLY = 0, MADIPM_T_FACTOR, MADIPM_T_SOLVE, MADIPM_T_SPMV, MADIPM_T_VECTOR,
-       MADIPM_T_FACTOR_SUBTREES /* the k_factor_subtrees launch alone */, MADIPM_T_COUNT };
+       MADIPM_T_FACTOR_TREE /* the k_tree_factor launches alone */, MADIPM_T_COUNT };
 /* enable = 1: every class, with a stream synchronisation per call (diagnostic runs only);
- * enable = 2: only the factorisation (classes FACTOR and FACTOR_SUBTREES), read at the synchronisation
+ * enable = 2: only the factorisation (classes FACTOR and FACTOR_TREE), read at the synchronisation
  *             madipm_factorize performs anyway -- cheap enough to leave on inside a timed region. */
 int32_t madipm_profile(madipm_handle* h, int32_t enable);
 int32_t madipm_profile_read(madipm_handle* h, double* ms, int64_t* calls, int32_t reset);

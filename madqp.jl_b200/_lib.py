@@ -28,9 +28,10 @@ VEC = {name: i for i, name in enumerate(VEC_NAMES)}
 
 SYM = dict(PERM=0, ETREE_PARENT=1, COLCOUNT=2, SUPER_FIRST=3, SUPER_PARENT=4, SUPER_ROWPTR=5, SUPER_ROWS=6,
            SUPER_XOFF=7, ASM_MAP=8, KKT_COLPTR=9, KKT_ROWVAL=10, AUG_CSC_MAP=11, A_ROWPTR=12, A_COLIND=13,
-           A_CSR_MAP=14, SUPER_LEVEL=15, PROD_PTR=16, PROD_A=17, PROD_B=18, PROD_K=19)
+           A_CSR_MAP=14, SUPER_LEVEL=15, PROD_PTR=16, PROD_A=17, PROD_B=18, PROD_K=19, CHILD_PTR=20, CHILD_IDX=21,
+           SUPER_KIND=22, PAR_POS=23, SUPER_COFF=24, TASK_SN=25, PHASE_PTR=26, PHASE_NBLOCK=27)
 
-T_CLASSES = ["assembly", "factor", "solve", "spmv", "vector", "factor_subtrees"]
+T_CLASSES = ["assembly", "factor", "solve", "spmv", "vector", "factor_tree"]
 
 
 class MadIPMError(RuntimeError):
@@ -41,7 +42,7 @@ class MadIPMError(RuntimeError):
 
 class Config(C.Structure):
     _fields_ = [("kkt_kind", C.c_int32), ("ordering", C.c_int32), ("max_width", C.c_int32), ("relax_small", C.c_int32),
-                ("relax_zeros", C.c_double * 3), ("subtree_work", C.c_int64), ("device", C.c_int32), ("batch", C.c_int32),
+                ("relax_zeros", C.c_double * 3), ("block_panel", C.c_int64), ("device", C.c_int32), ("batch", C.c_int32),
                 ("nd_leaf", C.c_int32), ("reserved", C.c_int32)]
 
 
@@ -49,9 +50,9 @@ class Info(C.Structure):
     _fields_ = ([(n, C.c_int32) for n in "kkt_kind nvar n_slack n_tot ncon nlb nub batch kkt_order".split()]
                 + [(n, C.c_int64) for n in "nnzh nnzj kkt_nnz aug_coo_len nnz_L nnz_stored".split()]
                 + [("factor_flops", C.c_double)]
-                + [(n, C.c_int32) for n in "nsuper max_height max_width n_subtrees n_levels".split()]
-                + [("n_products", C.c_int64), ("kkt_vec_len", C.c_int64), ("n_subtrees_small", C.c_int32),
-                   ("subtree_max_panel", C.c_int32)])
+                + [(n, C.c_int32) for n in "nsuper max_height max_width n_warp_tasks n_levels".split()]
+                + [("n_products", C.c_int64), ("kkt_vec_len", C.c_int64), ("n_block_tasks", C.c_int32),
+                   ("n_big", C.c_int32)])
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -36,7 +36,7 @@ void madipm_default_config(madipm_config* cfg) {
     cfg->max_width = o.max_width;
     cfg->relax_small = o.relax_small;
     for (int i = 0; i < 3; ++i) cfg->relax_zeros[i] = o.relax_zeros[i];
-    cfg->subtree_work = o.subtree_work;
+    cfg->block_panel = o.block_panel;
     cfg->device = 0;
     cfg->batch = 1;
 }
@@ -111,7 +111,7 @@ int32_t madipm_analyze(madipm_handle* h) {
     o.max_width = h->cfg.max_width;
     o.relax_small = h->cfg.relax_small;
     for (int i = 0; i < 3; ++i) o.relax_zeros[i] = h->cfg.relax_zeros[i];
-    o.subtree_work = h->cfg.subtree_work;
+    if (h->cfg.block_panel > 0) o.block_panel = h->cfg.block_panel;
     std::vector<uint8_t> delayed;
     if (h->pat.kind == 0) {   // K2: constraint rows wait for a neighbouring variable (see symbolic.hpp)
         delayed.assign(h->pat.N, 0);
@@ -142,8 +142,6 @@ int32_t madipm_get_info(const madipm_handle* h, madipm_info* out) {
     out->aug_coo_len = static_cast<int64_t>(p.aug_csc_map.size());
     out->n_products = static_cast<int64_t>(p.prod_a.size());
     out->kkt_vec_len = static_cast<int64_t>(p.n_tot) + p.m + h->nlb + h->nub;
-    out->n_subtrees_small = h->analyzed ? h->sym.n_subtrees_small : 0;
-    out->subtree_max_panel = h->analyzed ? h->sym.subtree_max_panel : 0;
     if (h->analyzed) {
         const Symbolic& s = h->sym;
         out->nnz_L = s.nnz_L;
@@ -152,7 +150,9 @@ int32_t madipm_get_info(const madipm_handle* h, madipm_info* out) {
         out->nsuper = s.nsuper;
         out->max_height = s.max_h;
         out->max_width = s.max_w;
-        out->n_subtrees = s.n_subtrees;
+        out->n_warp_tasks = s.n_warp_tasks;
+        out->n_block_tasks = s.n_block_tasks;
+        out->n_big = s.n_big;
         out->n_levels = s.n_levels;
     }
     return MADIPM_OK;
@@ -184,6 +184,14 @@ int32_t madipm_get_symbolic(const madipm_handle* h, int32_t which, int64_t* out,
         case MADIPM_SYM_PROD_A: return copy_out(p.prod_a, out, cap, len);
         case MADIPM_SYM_PROD_B: return copy_out(p.prod_b, out, cap, len);
         case MADIPM_SYM_PROD_K: return copy_out(p.prod_k, out, cap, len);
+        case MADIPM_SYM_CHILD_PTR: return copy_out(s.child_ptr, out, cap, len);
+        case MADIPM_SYM_CHILD_IDX: return copy_out(s.child_idx, out, cap, len);
+        case MADIPM_SYM_SUPER_KIND: return copy_out(s.sn_kind, out, cap, len);
+        case MADIPM_SYM_PAR_POS: return copy_out(s.par_pos, out, cap, len);
+        case MADIPM_SYM_SUPER_COFF: return copy_out(s.sn_coff, out, cap, len);
+        case MADIPM_SYM_TASK_SN: return copy_out(s.task_sn, out, cap, len);
+        case MADIPM_SYM_PHASE_PTR: return copy_out(s.phase_ptr, out, cap, len);
+        case MADIPM_SYM_PHASE_NBLOCK: return copy_out(s.phase_nblock, out, cap, len);
         default: return MADIPM_BAD_ARGUMENT;
     }
 }

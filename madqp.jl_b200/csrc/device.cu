@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -13,6 +14,7 @@
 #include "handle.hpp"
 #include "kernels_big.cuh"
 #include "kernels_factor.cuh"
+#include "kernels_tree.cuh"
 #include "kernels_vec.cuh"
 
 namespace madipm {
@@ -24,13 +26,26 @@ struct DeviceState {
     int n = 0, m = 0, nlb = 0, nub = 0, N = 0, kind = 0;
     int64_t L = 0;
     int64_t nnzA = 0, nnzQ = 0, nnzh = 0, nnzj = 0, nnzJfull = 0, kkt_nnz = 0, lx_stride = 0;
-    int nsuper = 0, n_subtrees = 0, n_levels = 0;
-    int cap_sub = 0, cap_sub_big = 0, cap_top = 0, tri_cap = 0;   // shared-memory panel capacities (doubles)
-    int n_sub_small = 0;
-    size_t smem_sub = 0, smem_sub_big = 0, smem_top = 0, smem_tri = 0;
-    std::vector<int> level_ptr;        // small (single-block) supernodes of the top part, per level
-    std::vector<int> big_ptr;          // big (multi-block) supernodes, per level
-    std::vector<int> big_rowblocks, big_rowblocks512, big_tiles;   // per level: grid sizes (max over its big supernodes)
+    int nsuper = 0, n_levels = 0;
+    int tri_cap = 0;
+    size_t smem_tri = 0;
+    // small supernodes: persistent height-scheduled kernels (kernels_tree.cuh)
+    struct TreeSeg { int ph0, ph1, grid[3]; };   // heights [ph0, ph1) in one cooperative launch; grid per kernel
+    std::vector<TreeSeg> segs;
+    int tree_cap_block = 0, tree_maxh_block = 0, tree_cap_warp = 0, tree_maxh_warp = 0, tree_warp_stride = 0, tree_maxw = 0;
+    size_t smem_tree = 0;
+    int tree_occ[3] = {0, 0, 0};
+    int num_sms = 0;
+    unsigned bar_base = 0;             // value of *bar before the next launch (barriers only ever add to it)
+    int *child_ptr = nullptr, *par_pos = nullptr, *task_sn = nullptr;
+    SnMeta* sn_meta = nullptr;
+    ChildRec* child_rec = nullptr;
+    int4* phases = nullptr;
+    double *Cx = nullptr, *cvec = nullptr;
+    int64_t cx_stride = 0, cv_stride = 0;
+    unsigned* bar = nullptr;
+    std::vector<int> big_ptr;          // big (multi-block) supernodes, per height
+    std::vector<int> big_rowblocks, big_rowblocks512, big_tiles;   // per height: grid sizes (max over its big supernodes)
     int* big_sn = nullptr;
     double *big_ybuf = nullptr, *big_tbuf = nullptr, *big_zbuf = nullptr;
     int big_zstride = 0;
@@ -53,7 +68,7 @@ struct DeviceState {
     int64_t *row_colbase = nullptr, *row_relbase = nullptr;
     int* rel = nullptr;
     double *Lx = nullptr, *xw = nullptr;
-    int *perm = nullptr, *iperm = nullptr, *sub_first = nullptr, *sub_last = nullptr, *level_sn = nullptr;
+    int *perm = nullptr, *iperm = nullptr;
     int* fail = nullptr;
     std::vector<int> h_fail;
 
@@ -135,15 +150,25 @@ VecView make_view(const DeviceState& d) {
     return V;
 }
 
-FactorView make_factor_view(const DeviceState& d, int panel_cap) {
+FactorView make_factor_view(const DeviceState& d, int = 0) {
     FactorView F;
     F.sn_first = d.sn_first; F.sn_rowptr = d.sn_rowptr; F.sn_rows = d.sn_rows; F.sn_xoff = d.sn_xoff;
     F.sn_of = d.sn_of; F.row_colbase = d.row_colbase; F.row_relbase = d.row_relbase; F.rel = d.rel;
-    F.Lx = d.Lx; F.lx_stride = d.lx_stride; F.fail = d.fail; F.panel_cap = panel_cap; F.scratch_rows = panel_cap;
+    F.Lx = d.Lx; F.lx_stride = d.lx_stride; F.fail = d.fail;
     return F;
 }
 
-inline size_t factor_smem_bytes(int cap) { return (static_cast<size_t>(cap) + cap / 2 + 64 + 256) * sizeof(double); }
+TreeView make_tree_view(const DeviceState& d) {
+    TreeView T;
+    T.F = make_factor_view(d, 0);
+    T.meta = d.sn_meta; T.crec = d.child_rec; T.child_ptr = d.child_ptr; T.par_pos = d.par_pos;
+    T.task_sn = d.task_sn; T.Cx = d.Cx; T.cx_stride = d.cx_stride; T.cvec = d.cvec; T.cv_stride = d.cv_stride;
+    T.xw = d.xw; T.xw_stride = d.N; T.bar = d.bar; T.B = d.B;
+    T.cap_block = d.tree_cap_block; T.maxh_block = d.tree_maxh_block; T.cap_warp = d.tree_cap_warp; T.maxh_warp = d.tree_maxh_warp;
+    T.warp_stride = d.tree_warp_stride; T.maxw = d.tree_maxw;
+    { const char* e = std::getenv("MADIPM_DBG_SN"); T.dbg_sn = e ? std::atoi(e) : -1; }
+    return T;
+}
 
 struct Timer {
     madipm_handle* h;
@@ -250,17 +275,31 @@ int32_t check(madipm_handle* h, bool need_values = false) {
     return MADIPM_OK;
 }
 
+template <int OP>
+int32_t launch_tree(madipm_handle* h, const DeviceState::TreeSeg& sg) {
+    DeviceState* d = h->dev;
+    if (sg.grid[OP] <= 0) return MADIPM_OK;                 // no small supernode in these heights
+    TreeView T = make_tree_view(*d);
+    const int4* ph = d->phases;
+    const bool reverse = OP == 2;
+    int b = reverse ? sg.ph1 - 1 : sg.ph0, e = reverse ? sg.ph0 - 1 : sg.ph1, step = reverse ? -1 : 1;
+    unsigned base = d->bar_base;
+    void* args[] = {&T, &ph, &b, &e, &step, &base};
+    CUDA_OK(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_tree<OP>), dim3(sg.grid[OP]), dim3(kTreeThreads), args,
+                                           d->smem_tree, d->stream));
+    d->bar_base += static_cast<unsigned>(sg.grid[OP]) * static_cast<unsigned>(sg.ph1 - sg.ph0 - 1);
+    ++h->launches;
+    return MADIPM_OK;
+}
+
 int32_t tri_solve(madipm_handle* h) {
     DeviceState* d = h->dev;
     FactorView F = make_factor_view(*d, 0);
-    const int T = 128;
     const int64_t N = d->N;
-    if (d->n_subtrees > 0)
-        LAUNCH(h, k_forward_subtrees, dim3(d->n_subtrees, d->B), T, d->smem_tri, F, d->xw, N, d->sub_first, d->sub_last, d->tri_cap);
-    for (int l = 0; l < d->n_levels; ++l) {
-        const int cnt = d->level_ptr[l + 1] - d->level_ptr[l];
-        if (cnt > 0)
-            LAUNCH(h, k_forward_level, dim3(cnt, d->B), T, d->smem_tri, F, d->xw, N, d->level_sn + d->level_ptr[l], d->tri_cap);
+    int32_t rc;
+    for (const DeviceState::TreeSeg& sg : d->segs) {
+        if ((rc = launch_tree<1>(h, sg))) return rc;
+        const int l = sg.ph1 - 1;
         const int nbig = d->big_ptr[l + 1] - d->big_ptr[l];
         if (nbig > 0) {
             const int* list = d->big_sn + d->big_ptr[l];
@@ -269,7 +308,8 @@ int32_t tri_solve(madipm_handle* h) {
                 LAUNCH(h, k_big_fwd_below, dim3((d->big_rowblocks[l] + 1) / 2, nbig, d->B), 128, 0, F, list, d->big_ybuf, 256, d->xw, N);
         }
     }
-    for (int l = d->n_levels - 1; l >= 0; --l) {
+    for (auto it = d->segs.rbegin(); it != d->segs.rend(); ++it) {
+        const int l = it->ph1 - 1;
         const int nbig = d->big_ptr[l + 1] - d->big_ptr[l];
         if (nbig > 0) {
             const int* list = d->big_sn + d->big_ptr[l];
@@ -277,12 +317,8 @@ int32_t tri_solve(madipm_handle* h) {
                 LAUNCH(h, k_big_bwd_below, dim3(d->big_rowblocks512[l], nbig, d->B), 256, 0, F, list, d->big_tbuf, 256, d->xw, N);
             LAUNCH(h, k_big_bwd_diag, dim3(nbig, d->B), 256, d->smem_tri, F, list, d->big_tbuf, 256, d->xw, N, d->tri_cap);
         }
-        const int cnt = d->level_ptr[l + 1] - d->level_ptr[l];
-        if (cnt > 0)
-            LAUNCH(h, k_backward_level, dim3(cnt, d->B), T, d->smem_tri, F, d->xw, N, d->level_sn + d->level_ptr[l], d->tri_cap);
+        if ((rc = launch_tree<2>(h, *it))) return rc;
     }
-    if (d->n_subtrees > 0)
-        LAUNCH(h, k_backward_subtrees, dim3(d->n_subtrees, d->B), T, d->smem_tri, F, d->xw, N, d->sub_first, d->sub_last, d->tri_cap);
     return MADIPM_OK;
 }
 
@@ -324,31 +360,21 @@ int32_t device_create(madipm_handle* h) {
     d->nnzh = p.nnzh; d->nnzj = p.nnzj; d->nnzJfull = p.nnzj + p.n_slack;
     d->kkt_nnz = p.kkt_colptr.back();
     d->lx_stride = s.nnz_stored;
-    d->nsuper = s.nsuper; d->n_subtrees = s.n_subtrees; d->n_levels = s.n_levels;
-    // split every level of the top part into single-block and multi-block (big) supernodes
-    std::vector<int> small_sn, big_sn_host;
-    {
-        const int64_t kBigPanel = 16384;
-        d->level_ptr.assign(1, 0);
-        d->big_ptr.assign(1, 0);
-        for (int l = 0; l < s.n_levels; ++l) {
-            int rb = 0, rb512 = 0, tiles = 0;
-            for (int q = s.level_ptr[l]; q < s.level_ptr[l + 1]; ++q) {
-                int sn = s.level_sn[q];
-                int64_t hs = s.sn_rowptr[sn + 1] - s.sn_rowptr[sn], ws = s.sn_first[sn + 1] - s.sn_first[sn];
-                if (hs * ws > kBigPanel || hs - ws > 384) {
-                    big_sn_host.push_back(sn);
-                    int64_t nb = hs - ws, nt = (nb + kBigTile - 1) / kBigTile;
-                    rb = std::max<int>(rb, static_cast<int>(nt));
-                    rb512 = std::max<int>(rb512, static_cast<int>((nb + 511) / 512));
-                    tiles = std::max<int>(tiles, static_cast<int>(nt * (nt + 1) / 2));
-                } else small_sn.push_back(sn);
-            }
-            d->level_ptr.push_back(static_cast<int>(small_sn.size()));
-            d->big_ptr.push_back(static_cast<int>(big_sn_host.size()));
-            d->big_rowblocks.push_back(rb); d->big_rowblocks512.push_back(rb512); d->big_tiles.push_back(tiles);
-            d->big_max_per_level = std::max(d->big_max_per_level, d->big_ptr[l + 1] - d->big_ptr[l]);
+    d->nsuper = s.nsuper; d->n_levels = s.n_levels;
+    // grid sizes of the multi-block kernels, per height (max over the big supernodes of that height)
+    d->big_ptr.assign(s.big_ptr.begin(), s.big_ptr.end());
+    for (int l = 0; l < s.n_levels; ++l) {
+        int rb = 0, rb512 = 0, tiles = 0;
+        for (int q = s.big_ptr[l]; q < s.big_ptr[l + 1]; ++q) {
+            const int sn = s.big_sn[q];
+            const int64_t hs = s.sn_rowptr[sn + 1] - s.sn_rowptr[sn], ws = s.sn_first[sn + 1] - s.sn_first[sn];
+            const int64_t nb = hs - ws, nt = (nb + kBigTile - 1) / kBigTile;
+            rb = std::max<int>(rb, static_cast<int>(nt));
+            rb512 = std::max<int>(rb512, static_cast<int>((nb + 511) / 512));
+            tiles = std::max<int>(tiles, static_cast<int>(nt * (nt + 1) / 2));
         }
+        d->big_rowblocks.push_back(rb); d->big_rowblocks512.push_back(rb512); d->big_tiles.push_back(tiles);
+        d->big_max_per_level = std::max(d->big_max_per_level, s.big_ptr[l + 1] - s.big_ptr[l]);
     }
     const int B = d->B;
     int32_t rc;
@@ -381,8 +407,43 @@ int32_t device_create(madipm_handle* h) {
     UP(int64_t, sn_xoff, s.sn_xoff); UP(int, sn_of, s.sn_of); UP(int64_t, asm_map, s.asm_map);
     UP(int64_t, row_colbase, s.row_colbase); UP(int64_t, row_relbase, s.row_relbase); UP(int, rel, s.rel);
     UP(int, perm, s.perm); UP(int, iperm, s.iperm);
-    UP(int, sub_first, s.subtree_first); UP(int, sub_last, s.subtree_last); UP(int, level_sn, small_sn);
-    UP(int, big_sn, big_sn_host);
+    UP(int, big_sn, s.big_sn);
+    UP(int, child_ptr, s.child_ptr); UP(int, par_pos, s.par_pos); UP(int, task_sn, s.task_sn);
+    {
+        std::vector<SnMeta> meta(std::max(1, s.nsuper));
+        std::vector<ChildRec> crec(std::max<size_t>(1, s.child_idx.size()));
+        std::memset(meta.data(), 0, meta.size() * sizeof(SnMeta));
+        std::memset(crec.data(), 0, crec.size() * sizeof(ChildRec));
+        for (int sn = 0; sn < s.nsuper; ++sn) {
+            SnMeta& m = meta[sn];
+            m.xoff = s.sn_xoff[sn]; m.coff = s.sn_coff[sn]; m.rowptr = static_cast<int32_t>(s.sn_rowptr[sn]);
+            m.fc = s.sn_first[sn]; m.h = static_cast<int32_t>(s.sn_rowptr[sn + 1] - s.sn_rowptr[sn]);
+            m.w = static_cast<uint16_t>(s.sn_first[sn + 1] - s.sn_first[sn]); m.kind = s.sn_kind[sn];
+            for (int q = s.child_ptr[sn]; q < s.child_ptr[sn + 1]; ++q) {
+                const int c = s.child_idx[q];
+                const int wc = s.sn_first[c + 1] - s.sn_first[c];
+                ChildRec& r = crec[q];
+                r.coff = s.sn_coff[c];
+                r.below = static_cast<int32_t>(s.sn_rowptr[c] + wc);
+                r.nb = static_cast<int32_t>(s.sn_rowptr[c + 1] - s.sn_rowptr[c]) - wc;
+                r.pull = s.sn_kind[c] == 0;
+                r.nbp = 0;
+                while (r.nbp < r.nb && s.par_pos[r.below + r.nbp] < m.w) ++r.nbp;
+            }
+        }
+        if (s.max_w > 65535) { h->error = "max_width too large"; return MADIPM_BAD_ARGUMENT; }
+        if ((rc = dev_alloc(h, &d->sn_meta, meta.size()))) return rc;
+        CUDA_OK(h, cudaMemcpy(d->sn_meta, meta.data(), meta.size() * sizeof(SnMeta), cudaMemcpyHostToDevice));
+        if ((rc = dev_alloc(h, &d->child_rec, crec.size()))) return rc;
+        CUDA_OK(h, cudaMemcpy(d->child_rec, crec.data(), crec.size() * sizeof(ChildRec), cudaMemcpyHostToDevice));
+    }
+    {
+        std::vector<int4> ph(std::max(1, s.n_levels));
+        for (int l = 0; l < s.n_levels; ++l)
+            ph[l] = make_int4(s.phase_ptr[l], s.phase_ptr[l] + s.phase_nblock[l], s.phase_ptr[l + 1], 0);
+        if ((rc = dev_alloc(h, &d->phases, ph.size()))) return rc;
+        CUDA_OK(h, cudaMemcpy(d->phases, ph.data(), ph.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    }
     std::vector<int64_t> diag_pos(d->N);
     for (int sn = 0; sn < s.nsuper; ++sn) {
         int64_t hs = s.sn_rowptr[sn + 1] - s.sn_rowptr[sn];
@@ -395,38 +456,67 @@ int32_t device_create(madipm_handle* h) {
     if ((rc = dev_alloc(h, &d->xw, static_cast<size_t>(B) * d->N))) return rc;
     if ((rc = dev_alloc(h, &d->fail, B))) return rc;
     d->h_fail.assign(B, 0);
-    // shared-memory capacities: bottom subtrees keep many blocks per SM (small panels staged, the rare larger
-    // ones in place); the level kernels of the top part get a panel-sized allocation, one block per SM.
+    // contribution blocks, contribution vectors, grid barrier
+    d->cx_stride = s.sn_coff.empty() ? 0 : s.sn_coff.back();
+    d->cv_stride = static_cast<int64_t>(s.sn_rows.size());
+    if ((rc = dev_alloc(h, &d->Cx, static_cast<size_t>(B) * d->cx_stride + 4))) return rc;
+    if ((rc = dev_alloc(h, &d->cvec, static_cast<size_t>(B) * d->cv_stride))) return rc;
+    if ((rc = dev_alloc(h, &d->bar, 1))) return rc;
+    CUDA_OK(h, cudaMemsetAsync(d->bar, 0, sizeof(unsigned), d->stream));
+    d->bar_base = 0;
+    d->num_sms = prop.multiProcessorCount;
     {
-        int64_t max_panel_top = 0, max_h_top = 0, max_h_sub = 0;
-        for (int sn = 0; sn < s.nsuper; ++sn) {
-            int64_t hs = s.sn_rowptr[sn + 1] - s.sn_rowptr[sn], ws = s.sn_first[sn + 1] - s.sn_first[sn];
-            if (s.sn_level[sn] > 0) {
-                if (hs * ws <= 16384 && hs - ws <= 384) { max_panel_top = std::max(max_panel_top, hs * ws); max_h_top = std::max(max_h_top, hs); }
-            } else max_h_sub = std::max(max_h_sub, hs);
-        }
-        d->n_sub_small = s.n_subtrees_small;
-        d->cap_sub = 1280;
-        d->cap_sub_big = static_cast<int>(std::max<int64_t>(std::min<int64_t>(8192, s.subtree_max_panel), std::max<int64_t>(1280, max_h_sub)));
-        d->smem_sub_big = factor_smem_bytes(d->cap_sub_big);
-        d->cap_top = static_cast<int>(std::max<int64_t>(std::min<int64_t>(16384, std::max<int64_t>(max_panel_top, 256)), max_h_top));
-        d->smem_sub = factor_smem_bytes(d->cap_sub);
-        d->smem_top = factor_smem_bytes(d->cap_top);
-        if (d->smem_top > 220 * 1024 || d->smem_sub > 64 * 1024) {
-            h->error = "supernode height " + std::to_string(s.max_h) + " exceeds the single-block factor path";
-            return MADIPM_INTERNAL;
+        // shared memory of the tree kernels: one block task [panel | h doubles | w doubles] or eight warp tasks
+        auto even = [](int v) { return (v + 3) & ~1; };     // room for the odd-length tail chunk and the 4-column tile overrun
+        d->tree_maxw = std::max(s.max_w, 1);
+        d->tree_cap_block = even(std::max(s.small_max_panel, 2));
+        d->tree_maxh_block = even(std::max(s.small_max_h, 2));
+        d->tree_cap_warp = even(std::max(s.warp_max_panel, 2));
+        d->tree_maxh_warp = even(std::max(s.warp_max_h, 2));
+        const int crec_doubles = kChildChunk * static_cast<int>(sizeof(ChildRec) / sizeof(double));
+        d->tree_warp_stride = d->tree_cap_warp + d->tree_maxh_warp + even(d->tree_maxw) + crec_doubles;
+        const size_t blk = static_cast<size_t>(d->tree_cap_block) + d->tree_maxh_block + even(d->tree_maxw) + crec_doubles;
+        d->smem_tree = std::max(blk, static_cast<size_t>(kTreeWarps) * d->tree_warp_stride) * sizeof(double);
+        if (d->smem_tree > 220 * 1024) { h->error = "block_panel too large for the shared memory of one block"; return MADIPM_BAD_ARGUMENT; }
+        if (!prop.cooperativeLaunch) { h->error = "device does not support cooperative launches"; return MADIPM_CUDA_ERROR; }
+        CUDA_OK(h, cudaFuncSetAttribute(k_tree<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_tree));
+        CUDA_OK(h, cudaFuncSetAttribute(k_tree<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_tree));
+        CUDA_OK(h, cudaFuncSetAttribute(k_tree<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_tree));
+        CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->tree_occ[0], k_tree<0>, kTreeThreads, d->smem_tree));
+        CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->tree_occ[1], k_tree<1>, kTreeThreads, d->smem_tree));
+        CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->tree_occ[2], k_tree<2>, kTreeThreads, d->smem_tree));
+        for (int op = 0; op < 3; ++op)
+            if (d->tree_occ[op] < 1) { h->error = "tree kernel does not fit on an SM"; return MADIPM_INTERNAL; }
+        // launch plan: consecutive heights share one cooperative launch; a height with big supernodes ends it
+        // (MADIPM_TREE_SPLIT=1 gives every height its own launch: a per-height launch list for the profiler)
+        const char* split_env = std::getenv("MADIPM_TREE_SPLIT");
+        const bool split = split_env && split_env[0] == '1';
+        int l0 = 0;
+        for (int l = 0; l < s.n_levels; ++l) {
+            const bool last = l + 1 == s.n_levels;
+            if (s.big_ptr[l + 1] > s.big_ptr[l] || last || split) {
+                DeviceState::TreeSeg sg;
+                sg.ph0 = l0; sg.ph1 = l + 1;
+                int64_t need = 0;
+                for (int q = l0; q <= l; ++q) {
+                    const int64_t nblk = s.phase_nblock[q], nwrp = s.phase_ptr[q + 1] - s.phase_ptr[q] - nblk;
+                    need = std::max(need, nblk * B + (nwrp * B + kTreeWarps - 1) / kTreeWarps);
+                }
+                for (int op = 0; op < 3; ++op)
+                    sg.grid[op] = static_cast<int>(std::min<int64_t>(need, static_cast<int64_t>(d->tree_occ[op]) * d->num_sms));
+                d->segs.push_back(sg);
+                l0 = l + 1;
+            }
         }
         d->tri_cap = std::min(s.max_w * s.max_w, 4096);
         d->smem_tri = (static_cast<size_t>(d->tri_cap) + 256) * sizeof(double);
     }
-    CUDA_OK(h, cudaFuncSetAttribute(k_factor_subtrees, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(d->smem_sub, d->smem_sub_big)));
-    CUDA_OK(h, cudaFuncSetAttribute(k_factor_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_top));
     {
         const size_t mw = static_cast<size_t>(s.max_w);
         d->smem_big_diag = (2 * mw * mw + mw) * sizeof(double);
         d->smem_big_trsm = 2 * mw * kBigTileLd * sizeof(double);
         d->smem_big_update = std::max<size_t>(2 * mw, kBigTile) * kBigTileLd * sizeof(double) + 2 * kBigTile * sizeof(int64_t);
-        if (!big_sn_host.empty()) {
+        if (!s.big_sn.empty()) {
             if (d->smem_big_trsm > 220 * 1024) { h->error = "max_width too large for the big-front kernels"; return MADIPM_BAD_ARGUMENT; }
             CUDA_OK(h, cudaFuncSetAttribute(k_big_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_big_diag));
             CUDA_OK(h, cudaFuncSetAttribute(k_big_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_big_trsm));
@@ -672,6 +762,7 @@ int32_t madipm_factorize(madipm_handle* h, int32_t* n_failed) {
     DeviceState* d = h->dev;
     const int B = d->B;
     const bool light = d->profiling == 2;
+    bool first_tree = true;
     {
         Timer t(h, MADIPM_T_FACTOR);
         if (light) cudaEventRecord(d->ev0, d->stream);
@@ -679,23 +770,16 @@ int32_t madipm_factorize(madipm_handle* h, int32_t* n_failed) {
         CUDA_OK(h, cudaMemsetAsync(d->fail, 0, sizeof(int) * B, d->stream));
         LAUNCH(h, k_assemble_panels, dim3(vec_blocks(d->kkt_nnz) * 4, B), kVecThreads, 0, d->kkt_nnz, d->asm_map,
                d->vec[MADIPM_VEC_KKT_NZVAL], d->kkt_nnz, d->Lx, d->lx_stride);
-        if (light) cudaEventRecord(d->ev2, d->stream);
-        // big-panel subtrees first (fewer, longer blocks), then the high-occupancy launch fills in behind them
-        if (d->n_subtrees > d->n_sub_small)
-            LAUNCH(h, k_factor_subtrees, dim3(d->n_subtrees - d->n_sub_small, B), 256, d->smem_sub_big,
-                   make_factor_view(*d, d->cap_sub_big), d->sub_first + d->n_sub_small, d->sub_last + d->n_sub_small);
-        if (d->n_sub_small > 0)
-            LAUNCH(h, k_factor_subtrees, dim3(d->n_sub_small, B), 128, d->smem_sub, make_factor_view(*d, d->cap_sub), d->sub_first, d->sub_last);
-        if (light) cudaEventRecord(d->ev3, d->stream);
-        for (int l = 0; l < d->n_levels; ++l) {
-            const int cnt = d->level_ptr[l + 1] - d->level_ptr[l];
+        for (const DeviceState::TreeSeg& sg : d->segs) {
+            if (light && first_tree) cudaEventRecord(d->ev2, d->stream);
+            if ((rc = launch_tree<0>(h, sg))) return rc;
+            if (light && first_tree) { cudaEventRecord(d->ev3, d->stream); first_tree = false; }
+            const int l = sg.ph1 - 1;
             const int nbig = d->big_ptr[l + 1] - d->big_ptr[l];
-            const int exclusive = (cnt + nbig == 1) ? 1 : 0;
-            if (cnt > 0)
-                LAUNCH(h, k_factor_level, dim3(cnt, B), 256, d->smem_top, make_factor_view(*d, d->cap_top), d->level_sn + d->level_ptr[l], exclusive);
             if (nbig > 0) {
                 const FactorView F = make_factor_view(*d, 0);
                 const int* list = d->big_sn + d->big_ptr[l];
+                const int exclusive = nbig == 1 ? 1 : 0;     // the only writer of its targets during these launches
                 LAUNCH(h, k_big_diag, dim3(nbig, B), 256, d->smem_big_diag, F, list, d->big_zbuf, d->big_zstride);
                 if (d->big_rowblocks[l] > 0) {
                     LAUNCH(h, k_big_trsm, dim3(d->big_rowblocks[l], nbig, B), 128, d->smem_big_trsm, F, list, d->big_zbuf, d->big_zstride);
@@ -710,8 +794,10 @@ int32_t madipm_factorize(madipm_handle* h, int32_t* n_failed) {
             float ms = 0;
             cudaEventElapsedTime(&ms, d->ev0, d->ev1);
             d->t_ms[MADIPM_T_FACTOR] += ms; d->t_calls[MADIPM_T_FACTOR] += 1;
-            cudaEventElapsedTime(&ms, d->ev2, d->ev3);
-            d->t_ms[MADIPM_T_FACTOR_SUBTREES] += ms; d->t_calls[MADIPM_T_FACTOR_SUBTREES] += 1;
+            if (!first_tree) {
+                cudaEventElapsedTime(&ms, d->ev2, d->ev3);
+                d->t_ms[MADIPM_T_FACTOR_TREE] += ms; d->t_calls[MADIPM_T_FACTOR_TREE] += 1;
+            }
         }
     }
     CUDA_OK(h, cudaGetLastError());

@@ -1,0 +1,532 @@
+// Height-scheduled supernodal LDL' and triangular solves for the "small" supernodes (north-star part (b)).
+//
+// All supernodes of one height of the supernodal elimination tree are independent.  The three kernels below
+// are persistent: one cooperative launch walks a range of heights, with a grid-wide barrier between two
+// heights, so a factorisation or a triangular sweep of a tree whose panels all fit one block is ONE launch.
+// Inside a height every supernode is a task: a whole 256-thread block for the larger panels, one warp for
+// the small ones (eight independent warp tasks per block), each with the panel staged in shared memory by
+// cp.async (16-byte, L2 only).
+//
+// The factorisation is multifrontal in its data flow, supernodal in its storage:
+//   * a task loads its h x w panel (original KKT entries, put there by k_assemble_panels, plus whatever big
+//     descendants pushed), adds the parts of its children's contribution blocks that land in the panel,
+//     factorises it (dense LDL', D on the diagonal, unit-lower L), and stores it;
+//   * it then writes its own contribution block C = sum(children's pass-through parts) - L21 D L21' (packed
+//     lower triangle) for the parent to pull.  Nothing is shared between concurrent tasks: no atomics, and
+//     the summation order is fixed, so the factor is bit-reproducible from run to run.
+//   * only where a small supernode sits under a big (multi-block) parent does it scatter C into the
+//     ancestors' panels itself (kind 1, FP64 atomics through the tables of kernels_factor.cuh).
+// The forward sweep moves contribution VECTORS the same way (parent pulls), the backward sweep only reads.
+//
+// Everything another block may have written during the same launch (panels, C, cvec, xw) is read with
+// ld.global.cg / cp.async.cg; index tables are read-only and go through the read-only path.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#include "kernels_factor.cuh"
+
+namespace madipm {
+
+constexpr int kTreeThreads = 256;
+constexpr int kTreeWarps = kTreeThreads / 32;
+
+constexpr int kChildChunk = 16;  // child records staged per pass
+
+// Everything a task needs to know about its supernode, in one 32-byte record (one memory round trip
+// instead of a chain of dependent index loads: the tasks are latency-bound, not bandwidth-bound).
+struct __align__(16) SnMeta {
+    int64_t xoff;      // panel offset in Lx
+    int64_t coff;      // contribution-block offset in Cx
+    int32_t rowptr;    // offset of the row list in sn_rows / par_pos / cvec
+    int32_t fc;        // first column
+    int32_t h;         // rows of the panel
+    uint16_t w;        // columns of the panel
+    uint8_t kind;      // 0 small (parent pulls), 1 small under a big parent, 2 big
+    uint8_t pad;
+};
+// One (parent, child) edge, stored in child_ptr order.
+struct __align__(16) ChildRec {
+    int64_t coff;      // the child's contribution block
+    int32_t below;     // offset of the child's first below-row in sn_rows / par_pos / cvec
+    int32_t nb;        // number of below rows of the child
+    int32_t nbp;       // ... of which fall inside the parent's own columns (they come first)
+    int32_t pull;      // 1: the child left a contribution block / vector for the parent (kind 0)
+    int32_t pad[2];
+};
+
+struct TreeView {
+    FactorView F;
+    const SnMeta* meta;          // [nsuper]
+    const ChildRec* crec;        // [nsuper - #roots], grouped by parent
+    const int* child_ptr;        // [nsuper+1] into crec
+    const int* par_pos;          // indexed like sn_rows
+    const int* task_sn;
+    double* Cx;                  // [batch][cx_stride] contribution blocks
+    int64_t cx_stride;
+    double* cvec;                // [batch][cv_stride] forward-sweep contribution vectors, indexed like sn_rows
+    int64_t cv_stride;
+    double* xw;                  // [batch][xw_stride] permuted right-hand side / solution
+    int64_t xw_stride;
+    unsigned* bar;               // grid barrier counter (monotone; the host passes the value it has before a launch)
+    int B;
+    int cap_block, maxh_block;   // shared-memory panel capacity (doubles) and row capacity of a block task
+    int cap_warp, maxh_warp;     // the same for one warp task
+    int warp_stride;             // doubles between the warp slices
+    int maxw;
+    int dbg_sn;                  // MADIPM_TREE_TIMING builds: supernode whose stage clocks are printed
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int G>
+__device__ __forceinline__ void gsync() {
+    if (G == 32) __syncwarp();
+    else __syncthreads();
+}
+
+// offset of column b inside a packed lower triangle of order nb, shifted so that [a] addresses row a >= b
+__device__ __forceinline__ int packed_col(int b, int nb) { return b * nb - ((b * (b + 1)) >> 1); }
+
+template <class T>
+__device__ __forceinline__ T ldg32(const T* p) {          // 32-byte record through the read-only path (two 16-byte loads)
+    static_assert(sizeof(T) == 32, "record size");
+    union { int4 v[2]; T t; } u;
+    u.v[0] = __ldg(reinterpret_cast<const int4*>(p));
+    u.v[1] = __ldg(reinterpret_cast<const int4*>(p) + 1);
+    return u.t;
+}
+
+// stage the child records [c0 + base, c0 + base + n) of a task into shared memory (n <= kChildChunk)
+template <int G>
+__device__ __forceinline__ int stage_children(const TreeView& T, ChildRec* cs, int c0, int c1, int base, int t) {
+    const int n = min(kChildChunk, c1 - c0 - base);
+    if (base > 0) gsync<G>();                              // everyone is done with the previous chunk
+    if (t < n) cs[t] = ldg32(T.crec + c0 + base + t);
+    gsync<G>();
+    return n;
+}
+
+// ---- dense LDL' of an h x w panel in shared memory (ld = h), left-looking, blocked by 4 columns ------------------
+// The panel is small and every task is latency-bound on its pivot chain, so the loop is organised to keep that
+// chain short rather than to save flops.  Thread t owns row t (rows t, t + G, ... for tall panels).  Per block of
+// four columns:
+//   1. each row subtracts the contributions of all columns to the left from its four entries (registers; the
+//      operand U = L D of the pivot rows is kept in the otherwise unused upper triangle of the diagonal block, so
+//      the inner loop is one strided own-row load, four broadcast loads and four independent FMAs),
+//   2. the four pivot rows publish their entries, one barrier,
+//   3. every thread factorises the 4 x 4 diagonal block redundantly in registers and solves its own row against
+//      it (no communication; reciprocals by rcp.approx + two Newton steps), writes L (pivot rows also U), one barrier.
+__device__ __forceinline__ double fast_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    return fma(r, e, r);
+}
+
+#ifndef LDL_PROBE
+#define LDL_PROBE(k)
+#endif
+template <int G>
+__device__ __forceinline__ void dense_ldl(double* Ps, int h, int w, int* fail, int t) {
+    constexpr int NB = 4;
+    for (int jb = 0; jb < w; jb += NB) {
+        const int bw = min(NB, w - jb);
+        const int o1 = bw > 1 ? h : 0, o2 = bw > 2 ? 2 * h : 0, o3 = bw > 3 ? 3 * h : 0;   // missing columns alias column 0
+        // 1. left-looking update of this block's entries of my rows (the first row stays in registers)
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        const double* U = Ps + jb * h;                     // U[k + c * h] = L[jb + c][k] * d_k for k < jb (upper triangle)
+        for (int i = jb + t; i < h; i += G) {
+            const double* li = Ps + i;
+            double* row = Ps + i + jb * h;
+            double c0 = row[0], c1 = row[o1], c2 = row[o2], c3 = row[o3];
+#pragma unroll 4
+            for (int k = 0; k < jb; ++k) {
+                const double l = li[k * h];
+                c0 = fma(-l, U[k], c0);
+                c1 = fma(-l, U[k + o1], c1);
+                c2 = fma(-l, U[k + o2], c2);
+                c3 = fma(-l, U[k + o3], c3);
+            }
+            if (i == jb + t) { a0 = c0; a1 = c1; a2 = c2; a3 = c3; }
+            if (i < jb + bw || i != jb + t) {              // pivot rows publish the diagonal block; further rows of a
+                row[0] = c0;                               // tall panel park their values (entries right of the diagonal
+                if (bw > 1) row[h] = c1;                   // are scratch: the upper triangle is rewritten in step 3)
+                if (bw > 2) row[2 * h] = c2;
+                if (bw > 3) row[3 * h] = c3;
+            }
+        }
+        LDL_PROBE(0);
+        gsync<G>();
+        LDL_PROBE(1);
+        // 2. diagonal block (identity-padded when fewer than 4 columns are left), redundantly in every thread
+        const double* Db = Ps + jb * (h + 1);
+        const double d0 = Db[0];
+        double a10 = bw > 1 ? Db[1] : 0.0, d1 = bw > 1 ? Db[h + 1] : 1.0;
+        double a20 = bw > 2 ? Db[2] : 0.0, a21 = bw > 2 ? Db[h + 2] : 0.0, d2 = bw > 2 ? Db[2 * h + 2] : 1.0;
+        double a30 = bw > 3 ? Db[3] : 0.0, a31 = bw > 3 ? Db[h + 3] : 0.0, a32 = bw > 3 ? Db[2 * h + 3] : 0.0,
+               d3 = bw > 3 ? Db[3 * h + 3] : 1.0;
+        const double r0 = fast_rcp(d0);
+        const double l10 = a10 * r0, l20 = a20 * r0, l30 = a30 * r0;
+        d1 = fma(-a10, l10, d1); a21 = fma(-a20, l10, a21); a31 = fma(-a30, l10, a31);
+        const double r1 = fast_rcp(d1);
+        const double l21 = a21 * r1, l31 = a31 * r1;
+        d2 = fma(-a21, l21, fma(-a20, l20, d2)); a32 = fma(-a31, l21, fma(-a30, l20, a32));
+        const double r2 = fast_rcp(d2);
+        const double l32 = a32 * r2;
+        LDL_PROBE(2);
+        LDL_PROBE(3);
+        gsync<G>();                                       // everyone has read the block before the pivot rows are rewritten
+        LDL_PROBE(4);
+        // 3. my rows against the block, one branch-free path for pivot rows and rows below: forward substitution
+        //    gives v = l D; column c gets v_c / d_c left of the row's diagonal and v_c (= d) on it.  Rows that
+        //    become pivot rows later also leave v in the upper triangle (entry (jb + c, i)).
+        //    (d3 = v3 of the fourth pivot row: its reciprocal is taken by the rows below from their own copy.)
+        const double d3f = fma(-a32, l32, fma(-a31, l31, fma(-a30, l30, d3)));
+        const double r3 = fast_rcp(d3f);
+        for (int i = jb + t; i < h; i += G) {
+            double* row = Ps + i + jb * h;
+            double* up = Ps + jb + i * h;
+            const int ri = i - jb;                        // 0..3 for a pivot row
+            double v0, v1, v2, v3;
+            if (i == jb + t) { v0 = a0; v1 = a1; v2 = a2; v3 = a3; }
+            else { v0 = row[0]; v1 = row[o1]; v2 = row[o2]; v3 = row[o3]; }
+            v1 = fma(-v0, l10, v1);
+            v2 = fma(-v1, l21, fma(-v0, l20, v2));
+            v3 = fma(-v2, l32, fma(-v1, l31, fma(-v0, l30, v3)));
+            row[0] = ri == 0 ? v0 : v0 * r0;
+            if (bw > 1 && ri >= 1) row[h] = ri == 1 ? v1 : v1 * r1;
+            if (bw > 2 && ri >= 2) row[2 * h] = ri == 2 ? v2 : v2 * r2;
+            if (bw > 3 && ri >= 3) row[3 * h] = ri == 3 ? v3 : v3 * r3;
+            if (i < w) {
+                if (ri > 0) up[0] = v0;
+                if (bw > 1 && ri > 1) up[1] = v1;
+                if (bw > 2 && ri > 2) up[2] = v2;
+                if (bw > 3 && ri > 3) up[3] = v3;
+            }
+        }
+        LDL_PROBE(5);
+        gsync<G>();
+        LDL_PROBE(6);
+    }
+    // pivots: a zero / non-finite one poisons everything after it, so one pass over D at the end is enough
+    bool bad = false;
+    for (int k = t; k < w; k += G) bad |= bad_pivot(Ps[k * (h + 1)]);
+    if (bad) atomicExch(fail, 1);
+}
+
+// ---- numeric factorisation of one small supernode ------------------------------------------------------
+// shared: [cap doubles panel][maxh doubles (unused by the blocked LDL')][maxw doubles D][kChildChunk child records]
+template <int G>
+__device__ __forceinline__ void tree_factor_task(const TreeView& T, int s, int inst, double* sm, int cap, int maxh) {
+    const FactorView& F = T.F;
+    constexpr int NW = G / 32;
+    const int t = (G == 32) ? (threadIdx.x & 31) : threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int gw = (G == 32) ? 0 : (threadIdx.x >> 5);
+    const SnMeta m = ldg32(T.meta + s);
+    const int c0 = __ldg(T.child_ptr + s), c1 = __ldg(T.child_ptr + s + 1);
+    const int w = m.w, h = m.h, nb = h - w;
+    double* Lx = F.Lx + inst * F.lx_stride;
+    double* P = Lx + m.xoff;
+    double* Cx = T.Cx + inst * T.cx_stride;
+    double* Ps = sm;
+    double* ucol = Ps + cap;
+    double* dk = ucol + maxh;
+    ChildRec* cs = reinterpret_cast<ChildRec*>(dk + ((T.maxw + 1) & ~1));
+    const int np = h * w;
+    const int nchunk = (np + 1) >> 1;
+#ifdef MADIPM_TREE_TIMING
+    long long tt[10];
+#define TT(k) do { if (s == T.dbg_sn && t == 0) tt[k] = clock64(); } while (0)
+#else
+#define TT(k)
+#endif
+    TT(0);
+    gsync<G>();                                           // the previous task of this group is done with the scratch
+    for (int c = t; c < nchunk; c += G) cp_async16(Ps + 2 * c, P + 2 * c);
+    // 1. extend-add: the parts of the children's contribution blocks that land in this panel
+    bool waited = false;
+    for (int base = 0; base < c1 - c0; base += kChildChunk) {
+        const int n = stage_children<G>(T, cs, c0, c1, base, t);
+        if (!waited) { cp_async_wait_all(); gsync<G>(); waited = true; }
+        for (int ci = 0; ci < n; ++ci) {
+            const ChildRec r = cs[ci];
+            if (!r.pull) continue;                        // that child scattered its block itself
+            const int* pos = T.par_pos + r.below;
+            const double* Cc = Cx + r.coff;
+            // work items = (column b, 32-row chunk); four items in flight per warp so the loads overlap
+            const int nch = (r.nb + 31) >> 5, nitems = r.nbp * nch;
+            for (int q0 = gw; q0 < nitems; q0 += 4 * NW) {
+                int dsti[4];
+                double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int q = q0 + u * NW;
+                    const int b = q / nch, a = ((q - b * nch) << 5) + lane;
+                    const bool ok = q < nitems && a >= b && a < r.nb;
+                    dsti[u] = ok ? __ldg(pos + a) + __ldg(pos + b) * h : -1;
+                    v[u] = ok ? __ldcg(Cc + packed_col(b, r.nb) + a) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (dsti[u] >= 0) Ps[dsti[u]] += v[u];
+            }
+            gsync<G>();
+        }
+    }
+    if (!waited) { cp_async_wait_all(); gsync<G>(); }
+    TT(1);
+    // 2. dense LDL' of the panel: D on the diagonal of the top w x w block, unit-lower L elsewhere
+    dense_ldl<G>(Ps, h, w, F.fail + inst, t);
+    TT(2);
+    gsync<G>();
+    for (int c = t; c < nchunk; c += G) reinterpret_cast<double2*>(P)[c] = reinterpret_cast<const double2*>(Ps)[c];
+    if (nb == 0) return;
+    for (int k = t; k < w; k += G) dk[k] = Ps[k * (h + 1)];
+    gsync<G>();
+    TT(3);
+    // 3. contribution block C = -L21 D L21' (packed lower triangle, 4 columns per warp pass, lanes over rows)
+    double* Cs = Cx + m.coff;
+    for (int b0 = 4 * gw; b0 < nb; b0 += 4 * NW) {
+        const double* Lb = Ps + w + b0;
+        for (int a = b0 + lane; a < nb; a += 32) {
+            const double* La = Ps + w + a;
+            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll 2
+            for (int k = 0; k < w; ++k) {
+                const double av = La[k * h] * dk[k];
+                acc0 = fma(av, Lb[k * h], acc0);
+                acc1 = fma(av, Lb[k * h + 1], acc1);          // columns past nb read scratch; never stored
+                acc2 = fma(av, Lb[k * h + 2], acc2);
+                acc3 = fma(av, Lb[k * h + 3], acc3);
+            }
+            Cs[packed_col(b0, nb) + a] = -acc0;
+            if (b0 + 1 < nb && a >= b0 + 1) Cs[packed_col(b0 + 1, nb) + a] = -acc1;
+            if (b0 + 2 < nb && a >= b0 + 2) Cs[packed_col(b0 + 2, nb) + a] = -acc2;
+            if (b0 + 3 < nb && a >= b0 + 3) Cs[packed_col(b0 + 3, nb) + a] = -acc3;
+        }
+    }
+    TT(4);
+    // 4. the children's pass-through parts (rows and columns beyond this supernode's own columns)
+    for (int base = 0; base < c1 - c0; base += kChildChunk) {
+        int n = min(kChildChunk, c1 - c0 - base);
+        if (c1 - c0 > kChildChunk) n = stage_children<G>(T, cs, c0, c1, base, t);   // else the records are still staged
+        for (int ci = 0; ci < n; ++ci) {
+            const ChildRec r = cs[ci];
+            if (!r.pull || r.nbp == r.nb) continue;
+            gsync<G>();                                   // C (or the previous child's additions) is in place
+            const int* pos = T.par_pos + r.below;
+            const double* Cc = Cx + r.coff;
+            const int nch = (r.nb + 31) >> 5, nitems = (r.nb - r.nbp) * nch;
+            for (int q0 = gw; q0 < nitems; q0 += 4 * NW) {
+                double* dst[4];
+                double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int q = q0 + u * NW;
+                    const int b = r.nbp + q / nch, a = ((q - (b - r.nbp) * nch) << 5) + lane;
+                    const bool ok = q < nitems && a >= b && a < r.nb;
+                    dst[u] = ok ? Cs + packed_col(__ldg(pos + b) - w, nb) + (__ldg(pos + a) - w) : nullptr;
+                    v[u] = ok ? __ldcg(Cc + packed_col(b, r.nb) + a) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (dst[u]) v[u] += __ldcg(dst[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (dst[u]) *dst[u] = v[u];
+            }
+        }
+    }
+    TT(5);
+#ifdef MADIPM_TREE_TIMING
+    if (s == T.dbg_sn && t == 0)
+        printf("sn %d G %d w %d h %d children %d | stage+extend %lld ldl %lld store %lld schur %lld pass %lld cycles\n", s, G, w, h,
+               c1 - c0, tt[1] - tt[0], tt[2] - tt[1], tt[3] - tt[2], tt[4] - tt[3], tt[5] - tt[4]);
+#endif
+    // 5. under a big parent: scatter C into the ancestors' panels (the big kernels read panels only)
+    if (m.kind == 1) {
+        gsync<G>();
+        const int64_t r0 = m.rowptr;
+        const int* rows = F.sn_rows + r0;
+        for (int b = gw; b < nb; b += NW) {
+            const int64_t cb = __ldg(F.row_colbase + r0 + w + b);
+            const int64_t rb = __ldg(F.row_relbase + r0 + w + b);
+            const double* col = Cs + packed_col(b, nb);
+            for (int a = b + lane; a < nb; a += 32)
+                atomicAdd(Lx + cb + target_pos(F, rb, w + a, rows, w + b), __ldcg(col + a));
+        }
+    }
+}
+
+// ---- forward sweep: y = L^-1 b, xw <- D^-1 y ---------------------------------------------------------------
+// shared: [cap doubles panel][maxh doubles pass-through][maxw doubles y][kChildChunk child records]
+template <int G>
+__device__ __forceinline__ void tree_forward_task(const TreeView& T, int s, int inst, double* sm, int cap, int maxh) {
+    const FactorView& F = T.F;
+    const int t = (G == 32) ? (threadIdx.x & 31) : threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int gw = (G == 32) ? 0 : (threadIdx.x >> 5);
+    const SnMeta m = ldg32(T.meta + s);
+    const int c0 = __ldg(T.child_ptr + s), c1 = __ldg(T.child_ptr + s + 1);
+    const int w = m.w, h = m.h, nb = h - w, fc = m.fc;
+    const double* P = F.Lx + inst * F.lx_stride + m.xoff;
+    double* xw = T.xw + inst * T.xw_stride;
+    double* cv = T.cvec + inst * T.cv_stride;
+    double* Ps = sm;
+    double* su = Ps + cap;
+    double* sy = su + maxh;
+    ChildRec* cs = reinterpret_cast<ChildRec*>(sy + ((T.maxw + 1) & ~1));
+    const int nchunk = (h * w + 1) >> 1;
+    gsync<G>();
+    for (int c = t; c < nchunk; c += G) cp_async16(Ps + 2 * c, P + 2 * c);
+    for (int j = t; j < w; j += G) sy[j] = __ldcg(xw + fc + j);
+    for (int i = t; i < nb; i += G) su[i] = 0.0;
+    for (int base = 0; base < c1 - c0; base += kChildChunk) {
+        const int n = stage_children<G>(T, cs, c0, c1, base, t);   // its barrier also publishes sy / su
+        for (int ci = 0; ci < n; ++ci) {
+            const ChildRec r = cs[ci];
+            if (!r.pull) continue;
+            const int* pos = T.par_pos + r.below;
+            const double* cc = cv + r.below;
+            for (int a = t; a < r.nb; a += G) {
+                const int pa = __ldg(pos + a);
+                const double v = __ldcg(cc + a);
+                if (pa < w) sy[pa] -= v;
+                else su[pa - w] += v;
+            }
+            gsync<G>();
+        }
+    }
+    cp_async_wait_all();
+    gsync<G>();
+    if (gw == 0) {                                        // unit-lower triangular solve, one warp
+        for (int j = 0; j + 1 < w; ++j) {
+            const double yj = sy[j];
+            for (int i = j + 1 + lane; i < w; i += 32) sy[i] -= Ps[i + j * h] * yj;
+            __syncwarp();
+        }
+    }
+    gsync<G>();
+    const bool pull = m.kind == 0;
+    const int* rows = F.sn_rows + m.rowptr + w;
+    for (int i = t; i < nb; i += G) {
+        double acc = su[i];
+        const double* Li = Ps + w + i;
+#pragma unroll 4
+        for (int j = 0; j < w; ++j) acc = fma(Li[j * h], sy[j], acc);
+        if (pull) cv[m.rowptr + w + i] = acc;
+        else atomicAdd(xw + __ldg(rows + i), -acc);
+    }
+    for (int j = t; j < w; j += G) xw[fc + j] = sy[j] / Ps[j * (h + 1)];
+}
+
+// ---- backward sweep: x = L^-T xw -----------------------------------------------------------------------------
+// shared: [cap doubles panel][maxh doubles x at the below rows][maxw doubles block solution]
+template <int G>
+__device__ __forceinline__ void tree_backward_task(const TreeView& T, int s, int inst, double* sm, int cap, int maxh) {
+    const FactorView& F = T.F;
+    constexpr int NW = G / 32;
+    const int t = (G == 32) ? (threadIdx.x & 31) : threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int gw = (G == 32) ? 0 : (threadIdx.x >> 5);
+    const SnMeta m = ldg32(T.meta + s);
+    const int w = m.w, h = m.h, nb = h - w, fc = m.fc;
+    const double* P = F.Lx + inst * F.lx_stride + m.xoff;
+    double* xw = T.xw + inst * T.xw_stride;
+    double* Ps = sm;
+    double* sx = Ps + cap;
+    double* st = sx + maxh;
+    const int nchunk = (h * w + 1) >> 1;
+    gsync<G>();
+    for (int c = t; c < nchunk; c += G) cp_async16(Ps + 2 * c, P + 2 * c);
+    const int* rows = F.sn_rows + m.rowptr + w;
+    for (int j = t; j < w; j += G) st[j] = __ldcg(xw + fc + j);
+    for (int i = t; i < nb; i += G) sx[i] = __ldcg(xw + __ldg(rows + i));
+    cp_async_wait_all();
+    gsync<G>();
+    for (int j = gw; j < w; j += NW) {
+        const double* Lj = Ps + w + j * h;
+        double acc = 0.0;
+        for (int i = lane; i < nb; i += 32) acc = fma(Lj[i], sx[i], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if (lane == 0) st[j] -= acc;
+    }
+    gsync<G>();
+    if (gw == 0) {
+        for (int j = w - 1; j > 0; --j) {
+            const double xj = st[j];
+            for (int k = lane; k < j; k += 32) st[k] -= Ps[j + k * h] * xj;
+            __syncwarp();
+        }
+    }
+    gsync<G>();
+    for (int j = t; j < w; j += G) xw[fc + j] = st[j];
+}
+
+// ---- grid barrier (cooperative launch: every block is resident) -------------------------------------------
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        } while (static_cast<int>(v - target) < 0);
+    }
+    __syncthreads();
+}
+
+template <int OP, int G>
+__device__ __forceinline__ void tree_task(const TreeView& T, int s, int inst, double* sm, int cap, int maxh) {
+    if (OP == 0) tree_factor_task<G>(T, s, inst, sm, cap, maxh);
+    else if (OP == 1) tree_forward_task<G>(T, s, inst, sm, cap, maxh);
+    else tree_backward_task<G>(T, s, inst, sm, cap, maxh);
+}
+
+// phases[k] = { first block task, first warp task, end of the warp tasks, unused } as indices into task_sn.
+// OP: 0 factor, 1 forward, 2 backward.  Heights ph_begin, ph_begin + step, ... (ph_end excluded).
+template <int OP>
+__global__ void __launch_bounds__(kTreeThreads, 4)
+k_tree(TreeView T, const int4* __restrict__ phases, int ph_begin, int ph_end, int step, unsigned bar_base) {
+    extern __shared__ double2 tree_smem2[];
+    double* smem = reinterpret_cast<double*>(tree_smem2);
+    const int warp = threadIdx.x >> 5;
+    unsigned target = bar_base;
+    for (int ph = ph_begin; ph != ph_end; ph += step) {
+        const int4 p = phases[ph];
+        const int nblk = p.y - p.x, nwrp = p.z - p.y;
+        const int64_t nbt = static_cast<int64_t>(nblk) * T.B;
+        for (int64_t q = blockIdx.x; q < nbt; q += gridDim.x) {
+            const int inst = static_cast<int>(q / nblk);
+            tree_task<OP, kTreeThreads>(T, __ldg(T.task_sn + p.x + static_cast<int>(q - static_cast<int64_t>(inst) * nblk)), inst,
+                                        smem, T.cap_block, T.maxh_block);
+        }
+        if (nwrp > 0) {
+            __syncthreads();
+            // blocks that had no block task in their first round take the first warp tasks
+            const int rot = static_cast<int>((blockIdx.x + gridDim.x - static_cast<unsigned>(nbt % gridDim.x)) % gridDim.x);
+            const int64_t nwt = static_cast<int64_t>(nwrp) * T.B;
+            double* sm = smem + warp * T.warp_stride;
+            for (int64_t q = static_cast<int64_t>(rot) * kTreeWarps + warp; q < nwt; q += static_cast<int64_t>(gridDim.x) * kTreeWarps) {
+                const int inst = static_cast<int>(q / nwrp);
+                tree_task<OP, 32>(T, __ldg(T.task_sn + p.y + static_cast<int>(q - static_cast<int64_t>(inst) * nwrp)), inst, sm,
+                                  T.cap_warp, T.maxh_warp);
+            }
+        }
+        if (ph + step != ph_end) grid_barrier(T.bar, target);
+    }
+}
+
+}  // namespace madipm

@@ -366,7 +366,7 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
     S = Symbolic();
     S.n = n;
     S.nnz_lower = colptr[n];
-    if (n == 0) { S.sn_first.assign(1, 0); S.sn_rowptr.assign(1, 0); S.sn_xoff.assign(1, 0); S.level_ptr.assign(1, 0); return; }
+    if (n == 0) { S.sn_first.assign(1, 0); S.sn_rowptr.assign(1, 0); S.sn_xoff.assign(1, 0); S.child_ptr.assign(1, 0); S.sn_coff.assign(1, 0); S.phase_ptr.assign(1, 0); S.big_ptr.assign(1, 0); return; }
 
     // ---- 1. fill-reducing permutation
     std::vector<int32_t> perm0;
@@ -668,84 +668,100 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
         }
     }
 
-    // ---- 8. schedule: bottom subtrees (one thread block each) + levels of the top part
-    std::vector<double> work(ns), sub(ns);
-    std::vector<int32_t> size(ns, 1);
-    for (int32_t s = 0; s < ns; ++s) {
-        double hs = static_cast<double>(S.sn_rowptr[s + 1] - S.sn_rowptr[s]);
-        double ws = static_cast<double>(S.sn_first[s + 1] - S.sn_first[s]);
-        work[s] = ws * hs * hs + (hs - ws) * (hs - ws) * ws + static_cast<double>(opt.node_latency);
-        sub[s] = work[s];
-    }
-    for (int32_t s = 0; s < ns; ++s)
-        if (S.sn_parent[s] != -1) { sub[S.sn_parent[s]] += sub[s]; size[S.sn_parent[s]] += size[s]; }
+    // ---- 8. schedule by height (see symbolic.hpp)
     S.sn_level.assign(ns, 0);
-    S.subtree_first.clear();
-    S.subtree_last.clear();
-    const double budget = static_cast<double>(opt.subtree_work);
-    // heavy = handled level by level.  Tall supernodes never go into a single-block subtree (its
-    // shared-memory scratch is small); heaviness propagates to every ancestor.
-    std::vector<char> heavy(ns, 0);
-    for (int32_t s = 0; s < ns; ++s) {
-        if (sub[s] > budget || (S.sn_rowptr[s + 1] - S.sn_rowptr[s]) > 512) heavy[s] = 1;
-        if (heavy[s] && S.sn_parent[s] != -1) heavy[S.sn_parent[s]] = 1;
-    }
     for (int32_t s = 0; s < ns; ++s) {
         int32_t p = S.sn_parent[s];
-        if (heavy[s]) {
-            S.sn_level[s] = 1;   // provisional: top part
-        } else if (p == -1 || heavy[p]) {
-            S.subtree_first.push_back(s - size[s] + 1);
-            S.subtree_last.push_back(s);
+        if (p != -1) {
+            if (p <= s) throw std::runtime_error("analyze: supernodal etree not topologically numbered");
+            S.sn_level[p] = std::max(S.sn_level[p], S.sn_level[s] + 1);
         }
-    }
-    S.n_subtrees = static_cast<int32_t>(S.subtree_last.size());
-    {   // two launch classes by largest panel, heaviest subtree first inside each class
-        const int32_t nsub = S.n_subtrees;
-        std::vector<int64_t> maxpanel(nsub, 0);
-        std::vector<double> cost(nsub, 0.0);
-        S.subtree_max_panel = 0;
-        for (int32_t k = 0; k < nsub; ++k)
-            for (int32_t s = S.subtree_first[k]; s <= S.subtree_last[k]; ++s) {
-                int64_t hs = S.sn_rowptr[s + 1] - S.sn_rowptr[s], ws = S.sn_first[s + 1] - S.sn_first[s];
-                maxpanel[k] = std::max(maxpanel[k], hs * ws);
-                cost[k] += work[s];
-            }
-        std::vector<int32_t> idx(nsub);
-        std::iota(idx.begin(), idx.end(), 0);
-        std::stable_sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) {
-            bool sa = maxpanel[a] <= opt.small_panel, sb = maxpanel[b] <= opt.small_panel;
-            if (sa != sb) return sa;
-            return cost[a] > cost[b];
-        });
-        std::vector<int32_t> f(nsub), l(nsub);
-        S.n_subtrees_small = 0;
-        for (int32_t k = 0; k < nsub; ++k) {
-            f[k] = S.subtree_first[idx[k]];
-            l[k] = S.subtree_last[idx[k]];
-            if (maxpanel[idx[k]] <= opt.small_panel) ++S.n_subtrees_small;
-            S.subtree_max_panel = static_cast<int32_t>(std::max<int64_t>(S.subtree_max_panel, maxpanel[idx[k]]));
-        }
-        S.subtree_first.swap(f);
-        S.subtree_last.swap(l);
     }
     S.n_levels = 0;
-    for (int32_t s = 0; s < ns; ++s) {
-        if (S.sn_level[s] == 0) continue;
-        int32_t p = S.sn_parent[s];
-        if (p != -1) S.sn_level[p] = std::max(S.sn_level[p], S.sn_level[s] + 1);
-        S.n_levels = std::max(S.n_levels, S.sn_level[s]);
-    }
-    S.level_ptr.assign(static_cast<size_t>(S.n_levels) + 1, 0);
+    for (int32_t s = 0; s < ns; ++s) S.n_levels = std::max(S.n_levels, S.sn_level[s] + 1);
+    S.child_ptr.assign(static_cast<size_t>(ns) + 1, 0);
     for (int32_t s = 0; s < ns; ++s)
-        if (S.sn_level[s] > 0) ++S.level_ptr[S.sn_level[s]];
-    for (int32_t l = 0; l < S.n_levels; ++l) S.level_ptr[l + 1] += S.level_ptr[l];
-    S.level_sn.assign(S.level_ptr[S.n_levels], 0);
+        if (S.sn_parent[s] != -1) ++S.child_ptr[S.sn_parent[s] + 1];
+    for (int32_t s = 0; s < ns; ++s) S.child_ptr[s + 1] += S.child_ptr[s];
+    S.child_idx.assign(S.child_ptr[ns], 0);
     {
-        std::vector<int32_t> at(S.level_ptr.begin(), S.level_ptr.end() - 1);
+        std::vector<int32_t> at(S.child_ptr.begin(), S.child_ptr.end() - 1);
         for (int32_t s = 0; s < ns; ++s)
-            if (S.sn_level[s] > 0) S.level_sn[at[S.sn_level[s] - 1]++] = s;
+            if (S.sn_parent[s] != -1) S.child_idx[at[S.sn_parent[s]]++] = s;
     }
+    auto is_big = [&](int32_t s) {
+        int64_t hs = S.sn_rowptr[s + 1] - S.sn_rowptr[s], ws = S.sn_first[s + 1] - S.sn_first[s];
+        return hs * ws > opt.block_panel || hs - ws > opt.block_below;
+    };
+    S.sn_kind.assign(ns, 0);
+    for (int32_t s = 0; s < ns; ++s) {
+        if (is_big(s)) S.sn_kind[s] = 2;
+        else if (S.sn_parent[s] != -1 && is_big(S.sn_parent[s])) S.sn_kind[s] = 1;
+    }
+    // position of every below-row inside the parent's row list (rows of a child below its own columns are a
+    // subset of the parent's rows; both lists ascend)
+    S.par_pos.assign(S.sn_rows.size(), 0);
+    for (int32_t s = 0; s < ns; ++s) {
+        const int32_t p = S.sn_parent[s];
+        if (p == -1) continue;
+        const int32_t ws = S.sn_first[s + 1] - S.sn_first[s];
+        const int32_t* prow = S.sn_rows.data() + S.sn_rowptr[p];
+        const int32_t hp = static_cast<int32_t>(S.sn_rowptr[p + 1] - S.sn_rowptr[p]);
+        int32_t q = 0;
+        for (int64_t k = S.sn_rowptr[s] + ws; k < S.sn_rowptr[s + 1]; ++k) {
+            while (q < hp && prow[q] < S.sn_rows[k]) ++q;
+            if (q == hp || prow[q] != S.sn_rows[k]) throw std::runtime_error("analyze: child row missing in parent");
+            S.par_pos[k] = q;
+        }
+    }
+    S.sn_coff.assign(static_cast<size_t>(ns) + 1, 0);
+    S.small_max_panel = S.small_max_h = S.warp_max_panel = S.warp_max_h = 0;
+    std::vector<char> warp_task(ns, 0);
+    for (int32_t s = 0; s < ns; ++s) {
+        int64_t hs = S.sn_rowptr[s + 1] - S.sn_rowptr[s], ws = S.sn_first[s + 1] - S.sn_first[s];
+        int64_t nb = hs - ws, sz = 0;
+        if (S.sn_kind[s] != 2) {
+            sz = (nb * (nb + 1) / 2 + 1) & ~int64_t(1);
+            S.small_max_panel = std::max<int32_t>(S.small_max_panel, static_cast<int32_t>(hs * ws));
+            S.small_max_h = std::max<int32_t>(S.small_max_h, static_cast<int32_t>(hs));
+            if (hs * ws <= opt.warp_panel && hs <= opt.warp_rows) {
+                warp_task[s] = 1;
+                S.warp_max_panel = std::max<int32_t>(S.warp_max_panel, static_cast<int32_t>(hs * ws));
+                S.warp_max_h = std::max<int32_t>(S.warp_max_h, static_cast<int32_t>(hs));
+            }
+        }
+        S.sn_coff[s + 1] = S.sn_coff[s] + sz;
+    }
+    S.phase_ptr.assign(static_cast<size_t>(S.n_levels) + 1, 0);
+    S.big_ptr.assign(static_cast<size_t>(S.n_levels) + 1, 0);
+    S.phase_nblock.assign(S.n_levels, 0);
+    for (int32_t s = 0; s < ns; ++s) {
+        if (S.sn_kind[s] == 2) ++S.big_ptr[S.sn_level[s] + 1];
+        else { ++S.phase_ptr[S.sn_level[s] + 1]; if (!warp_task[s]) ++S.phase_nblock[S.sn_level[s]]; }
+    }
+    for (int32_t l = 0; l < S.n_levels; ++l) { S.phase_ptr[l + 1] += S.phase_ptr[l]; S.big_ptr[l + 1] += S.big_ptr[l]; }
+    S.task_sn.assign(S.phase_ptr[S.n_levels], 0);
+    S.big_sn.assign(S.big_ptr[S.n_levels], 0);
+    {
+        std::vector<int32_t> at(S.phase_ptr.begin(), S.phase_ptr.end() - 1), bat(S.big_ptr.begin(), S.big_ptr.end() - 1);
+        for (int32_t s = 0; s < ns; ++s) {
+            if (S.sn_kind[s] == 2) S.big_sn[bat[S.sn_level[s]]++] = s;
+            else S.task_sn[at[S.sn_level[s]]++] = s;
+        }
+        auto cost = [&](int32_t s) {
+            double hs = static_cast<double>(S.sn_rowptr[s + 1] - S.sn_rowptr[s]), ws = static_cast<double>(S.sn_first[s + 1] - S.sn_first[s]);
+            return ws * hs * hs;
+        };
+        for (int32_t l = 0; l < S.n_levels; ++l)
+            std::stable_sort(S.task_sn.begin() + S.phase_ptr[l], S.task_sn.begin() + S.phase_ptr[l + 1], [&](int32_t a, int32_t b) {
+                if (warp_task[a] != warp_task[b]) return warp_task[a] < warp_task[b];
+                return cost(a) > cost(b);
+            });
+    }
+    S.n_big = static_cast<int32_t>(S.big_sn.size());
+    S.n_block_tasks = 0;
+    for (int32_t l = 0; l < S.n_levels; ++l) S.n_block_tasks += S.phase_nblock[l];
+    S.n_warp_tasks = static_cast<int32_t>(S.task_sn.size()) - S.n_block_tasks;
 }
 
 }  // namespace madipm

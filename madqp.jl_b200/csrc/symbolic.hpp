@@ -36,9 +36,10 @@ struct SymbolicOptions {
     int32_t max_width = 64;        // cap on supernode width (columns)
     int32_t relax_small = 8;       // always merge a last child if the merged width <= this
     double relax_zeros[3] = {0.5, 0.2, 0.05};   // allowed zero fraction for merged width <= 16, <= 48, larger
-    int64_t subtree_work = 200000; // cost budget of a bottom subtree handled by one thread block
-    int64_t node_latency = 20000;  // fixed cost of one supernode in flop equivalents (dependent memory round trips)
-    int32_t small_panel = 1280;    // panels up to this many doubles are staged by the high-occupancy subtree launch
+    int64_t block_panel = 12288;   // panels up to this many doubles (and at most block_below rows under the diagonal
+    int32_t block_below = 256;     //   block) are factorised by ONE thread block in shared memory; larger ones are "big"
+    int32_t warp_panel = 512;      // panels up to this many doubles and at most warp_rows rows are handled by one warp
+    int32_t warp_rows = 96;
     double dense_factor = 10.0;
 };
 
@@ -74,17 +75,27 @@ struct Symbolic {
     static constexpr int64_t kRelShift = int64_t(1) << 40;
     static constexpr int64_t kRelSearch = INT64_MIN;
 
-    // schedule
-    std::vector<int32_t> sn_level;       // [nsuper] 0 = inside a bottom subtree, >= 1 level of the top part
-    int32_t n_subtrees = 0;
-    std::vector<int32_t> subtree_first;  // [n_subtrees] first supernode of the subtree (postorder => contiguous)
-    std::vector<int32_t> subtree_last;   // [n_subtrees] root supernode of the subtree (inclusive)
-    int32_t n_subtrees_small = 0;        // subtrees [0, n_subtrees_small) only hold panels <= small_panel doubles;
-                                         // inside each class the subtrees are sorted heaviest first
-    int32_t subtree_max_panel = 0;       // largest panel (doubles) inside any subtree
-    int32_t n_levels = 0;                // number of top levels
-    std::vector<int32_t> level_ptr;      // [n_levels+1] into level_sn
-    std::vector<int32_t> level_sn;       // top supernodes grouped by level
+    // schedule: supernodes grouped by height in the supernodal elimination tree (0 = leaf); all supernodes of
+    // one height are independent, so a height is one phase of the persistent factor / solve kernels.
+    //   kind 0  "small": one block (or one warp) factorises it in shared memory, multifrontal style: its
+    //           contribution block C (packed lower triangle, (h-w)(h-w+1)/2 doubles at sn_coff) is pulled by the parent
+    //   kind 1  small, but the parent is big: it scatters C into the ancestors' panels itself (FP64 atomics)
+    //   kind 2  "big": multi-block right-looking kernels (diag / TRSM / DMMA update), pushes into the panels
+    std::vector<int32_t> sn_level;       // [nsuper] height
+    std::vector<uint8_t> sn_kind;        // [nsuper]
+    int32_t n_levels = 0;                // number of heights
+    std::vector<int32_t> child_ptr;      // [nsuper+1] into child_idx
+    std::vector<int32_t> child_idx;      // children of every supernode, ascending
+    std::vector<int32_t> par_pos;        // indexed like sn_rows: position of below-row i inside the PARENT's row list
+    std::vector<int64_t> sn_coff;        // [nsuper+1] offsets of the contribution blocks (kind 0 / 1 only)
+    std::vector<int32_t> task_sn;        // small supernodes ordered by (height, block tasks first, heaviest first)
+    std::vector<int32_t> phase_ptr;      // [n_levels+1] into task_sn
+    std::vector<int32_t> phase_nblock;   // [n_levels] the first phase_nblock[k] tasks of a phase take a whole block
+    std::vector<int32_t> big_ptr;        // [n_levels+1] into big_sn
+    std::vector<int32_t> big_sn;         // big supernodes grouped by height
+    int32_t n_block_tasks = 0, n_warp_tasks = 0, n_big = 0;
+    int32_t small_max_panel = 0, small_max_h = 0;   // over kind 0 / 1 (shared-memory sizing of the tree kernels)
+    int32_t warp_max_panel = 0, warp_max_h = 0;     // over the warp tasks
 
     int64_t nnz_L = 0;        // exact nnz(L) = sum colcount
     int64_t nnz_stored = 0;   // panel storage incl. relaxation zeros and the unused upper triangles

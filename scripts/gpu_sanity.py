@@ -20,7 +20,7 @@ def run(qp, name, ok=True, **kw):
     print(f"{name}: gpu {st.status[0]} it={int(st.iter[0])} obj={st.objective[0]:.10e} t={dt:.2f}s "
           f"solve={st.total_time:.3f}s analysis={s.analysis_time:.2f}s launches={s.h.launch_count()}"
           + (f" | oracle {ref.status} it={ref.k} obj={ref.objective:.10e} t={ref.total_time:.2f}s" if ref else ""), flush=True)
-    print("   info", {k: s.info[k] for k in ("kkt_order", "nnz_L", "factor_flops", "nsuper", "n_subtrees", "n_levels", "max_height")}, flush=True)
+    print("   info", {k: s.info[k] for k in ("kkt_order", "nnz_L", "factor_flops", "nsuper", "n_block_tasks", "n_warp_tasks", "n_big", "n_levels", "max_height")}, flush=True)
     if len(s.trace) > 1:
         print("   last", {k: (float(v[0]) if hasattr(v, '__len__') else v) for k, v in s.trace[-1].items()}, "resid", s.last_residual_ratio)
     s.close()
@@ -48,7 +48,7 @@ if "prof" in which:
     print("C3 profiled solve: %.3fs, %d iters" % (dt, int(st.iter[0])))
     for k, (ms, calls) in pr.items():
         print("   %-16s %9.2f ms  %6d calls  %8.3f ms/call  %6.2f ms/iter" % (k, ms, calls, ms / max(calls, 1), ms / st.iter[0]))
-    print("   sum classes %.1f ms" % sum(v[0] for k, v in pr.items() if k != "factor_subtrees"))
+    print("   sum classes %.1f ms" % sum(v[0] for k, v in pr.items() if k != "factor_tree"))
     s.close()
 if "c2" in which:
     run(P.sparse_lp(), "C2", ok=False, kkt_system="NORMAL", regularization=FixedRegularization(1e-8, -1e-8))

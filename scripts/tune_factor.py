@@ -7,11 +7,11 @@ from madqp_jl_b200.mpc import MPCSolver, FixedRegularization
 import bench
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "C3"
-budgets = [int(float(x)) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [2_000_000]
+budgets = [int(float(x)) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0]
 scale = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
 qps, kkt, name = bench.make_workload(wl, scale)
 for b in budgets:
-    s = MPCSolver(qps if len(qps) > 1 else qps[0], kkt_system=kkt, regularization=FixedRegularization(1e-8, -1e-8), subtree_work=b)
+    s = MPCSolver(qps if len(qps) > 1 else qps[0], kkt_system=kkt, regularization=FixedRegularization(1e-8, -1e-8), block_panel=b)
     s.prepare_host(); s.upload(); s.start()
     s._update_regularization()
     h = s.h
@@ -25,7 +25,7 @@ for b in budgets:
         h.kkt_solve("P")
     pr = h.profile_read()
     i = s.info
-    print(f"{wl} budget={b}: factor {pr['factor'][0]/10:.3f} ms  solve {pr['solve'][0]/10:.3f} ms | nsuper={i['nsuper']} subtrees={i['n_subtrees']} "
-          f"(small {i['n_subtrees_small']}) levels={i['n_levels']} maxpanel={i['subtree_max_panel']} nnzL={i['nnz_L']} "
+    print(f"{wl} block_panel={b}: factor {pr['factor'][0]/10:.3f} ms  solve {pr['solve'][0]/10:.3f} ms | nsuper={i['nsuper']} block/warp/big tasks={i['n_block_tasks']}/{i['n_warp_tasks']}/{i['n_big']} "
+          f"heights={i['n_levels']} nnzL={i['nnz_L']} "
           f"flops={i['factor_flops']:.3g} GF/s={i['factor_flops']*len(qps)/(pr['factor'][0]/10)/1e6:.1f}", flush=True)
     s.close()

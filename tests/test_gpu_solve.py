@@ -104,7 +104,7 @@ def test_config_shapes_match_oracle(maker, kw, opts):
 @pytest.mark.parametrize("ordering", [_lib.ORDER_AMD, _lib.ORDER_ND, _lib.ORDER_NATURAL])
 def test_orderings_give_the_same_answer(ordering):
     qp = P.banded_qp(n=3000, m=1500)
-    compare(qp, regularization=FixedRegularization(1e-8, -1e-8), ordering=ordering, nd_leaf=80, subtree_work=20000)
+    compare(qp, regularization=FixedRegularization(1e-8, -1e-8), ordering=ordering, nd_leaf=80)
 
 
 @pytest.mark.parametrize("maker,kw", [
@@ -116,7 +116,7 @@ def test_big_front_path_matches_oracle(maker, kw):
     qp = maker(**kw)
     s = MPCSolver(qp, kkt_system="NORMAL", regularization=FixedRegularization(1e-8, -1e-8))
     first, rp, lev = s.h.symbolic("SUPER_FIRST"), s.h.symbolic("SUPER_ROWPTR"), s.h.symbolic("SUPER_LEVEL")
-    big = (np.diff(first) * np.diff(rp) > 16384) & (lev > 0)
+    big = s.h.symbolic("SUPER_KIND") == 2
     assert big.any(), "the instance must exercise the multi-block path"
     s.close()
     compare(qp, kkt_system="NORMAL", regularization=FixedRegularization(1e-8, -1e-8))

@@ -169,14 +169,87 @@ def test_fill_is_comparable_to_scipy_minimum_degree():
 
 def test_schedule_covers_every_supernode_once():
     qp = P.banded_qp(n=6000, m=3000)
-    h, _ = analyze_handle(qp, "K2", subtree_work=50_000, nd_leaf=100)
-    level, parent = h.symbolic("SUPER_LEVEL"), h.symbolic("SUPER_PARENT")
+    h, _ = analyze_handle(qp, "K2", nd_leaf=100)
+    level, parent, kind = h.symbolic("SUPER_LEVEL"), h.symbolic("SUPER_PARENT"), h.symbolic("SUPER_KIND")
+    task, pptr, nblk = h.symbolic("TASK_SN"), h.symbolic("PHASE_PTR"), h.symbolic("PHASE_NBLOCK")
     info = h.info()
-    assert info["n_subtrees"] > 1 and info["n_levels"] >= 1
+    assert info["n_levels"] == level.max() + 1 == len(pptr) - 1
+    assert info["n_block_tasks"] + info["n_warp_tasks"] + info["n_big"] == info["nsuper"]
     for s, p in enumerate(parent):
         if p >= 0:
             assert p > s                                      # postorder
-            if level[s] > 0:
-                assert level[p] > level[s]                    # a top node's parent is on a later level
-            else:
-                assert level[p] >= 0
+            assert level[p] > level[s]                        # a parent is processed in a later phase
+    # every small supernode is exactly one task, in the phase of its height
+    assert sorted(task.tolist()) == np.flatnonzero(kind != 2).tolist()
+    for k in range(len(pptr) - 1):
+        assert (level[task[pptr[k]:pptr[k + 1]]] == k).all()
+        assert 0 <= nblk[k] <= pptr[k + 1] - pptr[k]
+
+
+def _multifrontal_emulation(h, K):
+    """numpy restatement of the data flow of kernels_tree.cuh (pull of packed contribution blocks through
+    PAR_POS / SUPER_COFF) on the dense permuted matrix K; returns (L, d) with K = L diag(d) L'."""
+    first, rp, rows = h.symbolic("SUPER_FIRST"), h.symbolic("SUPER_ROWPTR"), h.symbolic("SUPER_ROWS")
+    cptr, cidx, ppos, coff = h.symbolic("CHILD_PTR"), h.symbolic("CHILD_IDX"), h.symbolic("PAR_POS"), h.symbolic("SUPER_COFF")
+    task, pptr = h.symbolic("TASK_SN"), h.symbolic("PHASE_PTR")
+    N = K.shape[0]
+    Lf, dd = np.eye(N), np.zeros(N)
+    C = np.zeros(coff[-1])
+
+    def col(b, nb):
+        return b * nb - b * (b + 1) // 2
+
+    for k in range(len(pptr) - 1):
+        for s in task[pptr[k]:pptr[k + 1]]:
+            w = first[s + 1] - first[s]
+            r = rows[rp[s]:rp[s + 1]]
+            hh = len(r)
+            nb = hh - w
+            Pn = np.tril(K[np.ix_(r, r[:w])])                       # assembled panel (lower part of the diagonal block)
+            Cs = np.zeros((nb, nb))
+            for c in cidx[cptr[s]:cptr[s + 1]]:
+                wc = first[c + 1] - first[c]
+                nbc = rp[c + 1] - rp[c] - wc
+                pos = ppos[rp[c] + wc: rp[c + 1]]
+                assert (np.diff(pos) > 0).all() and pos[0] < w
+                assert (rows[rp[c] + wc: rp[c + 1]] == r[pos]).all()
+                for b in range(nbc):
+                    for a in range(b, nbc):
+                        v = C[coff[c] + col(b, nbc) + a]
+                        if pos[b] < w:
+                            Pn[pos[a], pos[b]] += v
+                        else:
+                            Cs[pos[a] - w, pos[b] - w] += v
+            for j in range(w):                                        # dense LDL' of the panel
+                d = Pn[j, j]
+                u = Pn[j + 1:, j].copy()
+                Pn[j + 1:, j] = u / d
+                for kk in range(j + 1, w):
+                    Pn[kk:, kk] -= u[kk - j - 1:] * Pn[kk, j]
+            dd[r[:w]] = np.diag(Pn[:w, :w])
+            for j in range(w):
+                Lf[r[j + 1:], r[j]] = Pn[j + 1:, j]
+            L21 = Pn[w:, :]
+            Cs -= np.tril(L21 @ np.diag(dd[r[:w]]) @ L21.T)
+            for b in range(nb):
+                C[coff[s] + col(b, nb) + b: coff[s] + col(b, nb) + nb] = Cs[b:, b]
+    return Lf, dd
+
+
+@pytest.mark.parametrize("ordering", [_lib.ORDER_ND, _lib.ORDER_AMD])
+def test_contribution_block_tables_reproduce_the_factor(ordering):
+    """PAR_POS, SUPER_COFF, CHILD_*, TASK_SN and PHASE_PTR carry a complete multifrontal factorisation."""
+    qp = P.banded_qp(n=120, m=60, half_width=8)
+    h, _ = analyze_handle(qp, "K2", ordering=ordering, nd_leaf=24)
+    assert (h.symbolic("SUPER_KIND") == 0).all()
+    cp, ri, perm = h.symbolic("KKT_COLPTR"), h.symbolic("KKT_ROWVAL"), h.symbolic("PERM")
+    N = h.info()["kkt_order"]
+    rng = np.random.default_rng(0)
+    col_of = np.repeat(np.arange(N), np.diff(cp))
+    vals = np.where(ri == col_of, np.where(col_of < qp.nvar, 4.0, -4.0), rng.uniform(-1, 1, len(ri)))
+    K = np.zeros((N, N))
+    K[ri, col_of] = vals
+    K = K + np.tril(K, -1).T
+    Kp = K[np.ix_(perm, perm)]
+    L, d = _multifrontal_emulation(h, Kp)
+    assert np.abs(L @ np.diag(d) @ L.T - Kp).max() <= 1e-10 * np.abs(Kp).max()
