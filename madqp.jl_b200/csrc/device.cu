@@ -30,17 +30,20 @@ struct DeviceState {
     int tri_cap = 0;
     size_t smem_tri = 0;
     // small supernodes: persistent height-scheduled kernels (kernels_tree.cuh)
-    struct TreeSeg { int ph0, ph1, grid[3]; };   // heights [ph0, ph1) in one cooperative launch; grid per kernel
+    // heights [ph0, split) in one cooperative launch of k_tree, heights [split, ph1) (at most one task per SM) in one
+    // launch of k_tree_top; a height with big supernodes ends a segment
+    struct TreeSeg { int ph0, split, ph1, grid[3], grid_top; };
     std::vector<TreeSeg> segs;
-    int tree_cap_block = 0, tree_maxh_block = 0, tree_cap_warp = 0, tree_maxh_warp = 0, tree_warp_stride = 0, tree_maxw = 0;
+    int tree_maxw = 0;
     size_t smem_tree = 0;
     int tree_occ[3] = {0, 0, 0};
+    int* tickets[3] = {nullptr, nullptr, nullptr};
+    int* phase_cls = nullptr;
     int num_sms = 0;
     unsigned bar_base = 0;             // value of *bar before the next launch (barriers only ever add to it)
     int *child_ptr = nullptr, *par_pos = nullptr, *task_sn = nullptr;
     SnMeta* sn_meta = nullptr;
     ChildRec* child_rec = nullptr;
-    int4* phases = nullptr;
     double *Cx = nullptr, *cvec = nullptr;
     int64_t cx_stride = 0, cv_stride = 0;
     unsigned* bar = nullptr;
@@ -84,6 +87,7 @@ struct DeviceState {
     unsigned long long* d_inertia = nullptr;
     double* h_out = nullptr;   // pinned
 
+    const Symbolic* sym = nullptr;
     bool values_set = false;
     int profiling = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
@@ -163,9 +167,9 @@ TreeView make_tree_view(const DeviceState& d) {
     T.F = make_factor_view(d, 0);
     T.meta = d.sn_meta; T.crec = d.child_rec; T.child_ptr = d.child_ptr; T.par_pos = d.par_pos;
     T.task_sn = d.task_sn; T.Cx = d.Cx; T.cx_stride = d.cx_stride; T.cvec = d.cvec; T.cv_stride = d.cv_stride;
-    T.xw = d.xw; T.xw_stride = d.N; T.bar = d.bar; T.B = d.B;
-    T.cap_block = d.tree_cap_block; T.maxh_block = d.tree_maxh_block; T.cap_warp = d.tree_cap_warp; T.maxh_warp = d.tree_maxh_warp;
-    T.warp_stride = d.tree_warp_stride; T.maxw = d.tree_maxw;
+    T.xw = d.xw; T.xw_stride = d.N; T.bar = d.bar; T.B = d.B; T.tickets = nullptr; T.phase_cls = d.phase_cls;
+    for (int c = 0; c < 4; ++c) { T.slice[c] = d.sym->tree_slice[c]; T.cap[c] = d.sym->tree_cap[c]; T.maxh[c] = d.sym->tree_maxh[c]; }
+    T.maxw = d.tree_maxw;
     { const char* e = std::getenv("MADIPM_DBG_SN"); T.dbg_sn = e ? std::atoi(e) : -1; }
     return T;
 }
@@ -278,18 +282,36 @@ int32_t check(madipm_handle* h, bool need_values = false) {
 template <int OP>
 int32_t launch_tree(madipm_handle* h, const DeviceState::TreeSeg& sg) {
     DeviceState* d = h->dev;
-    if (sg.grid[OP] <= 0) return MADIPM_OK;                 // no small supernode in these heights
     TreeView T = make_tree_view(*d);
-    const int4* ph = d->phases;
+    T.tickets = d->tickets[OP];
     const bool reverse = OP == 2;
-    int b = reverse ? sg.ph1 - 1 : sg.ph0, e = reverse ? sg.ph0 - 1 : sg.ph1, step = reverse ? -1 : 1;
-    unsigned base = d->bar_base;
-    void* args[] = {&T, &ph, &b, &e, &step, &base};
-    CUDA_OK(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_tree<OP>), dim3(sg.grid[OP]), dim3(kTreeThreads), args,
-                                           d->smem_tree, d->stream));
-    d->bar_base += static_cast<unsigned>(sg.grid[OP]) * static_cast<unsigned>(sg.ph1 - sg.ph0 - 1);
-    ++h->launches;
-    return MADIPM_OK;
+    auto bottom = [&]() -> int32_t {
+        if (sg.split <= sg.ph0 || sg.grid[OP] <= 0) return MADIPM_OK;
+        CUDA_OK(h, cudaMemsetAsync(d->tickets[OP] + 4 * sg.ph0, 0, sizeof(int) * 4 * (sg.split - sg.ph0), d->stream));
+        int b = reverse ? sg.split - 1 : sg.ph0, e = reverse ? sg.ph0 - 1 : sg.split, step = reverse ? -1 : 1;
+        unsigned base = d->bar_base;
+        void* args[] = {&T, &b, &e, &step, &base};
+        CUDA_OK(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_tree<OP>), dim3(sg.grid[OP]), dim3(kTreeThreads), args,
+                                               d->smem_tree, d->stream));
+        d->bar_base += static_cast<unsigned>(sg.grid[OP]) * static_cast<unsigned>(sg.split - sg.ph0 - 1);
+        ++h->launches;
+        return MADIPM_OK;
+    };
+    auto top = [&]() -> int32_t {
+        if (sg.ph1 <= sg.split || sg.grid_top <= 0) return MADIPM_OK;
+        int b = reverse ? sg.ph1 - 1 : sg.split, e = reverse ? sg.split - 1 : sg.ph1, step = reverse ? -1 : 1;
+        unsigned base = d->bar_base;
+        void* args[] = {&T, &b, &e, &step, &base};
+        CUDA_OK(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_tree_top<OP>), dim3(sg.grid_top), dim3(kTopThreads), args,
+                                               d->smem_tree, d->stream));
+        d->bar_base += static_cast<unsigned>(sg.grid_top) * static_cast<unsigned>(sg.ph1 - sg.split - 1);
+        ++h->launches;
+        return MADIPM_OK;
+    };
+    int32_t rc;
+    if (reverse) { if ((rc = top())) return rc; return bottom(); }
+    if ((rc = bottom())) return rc;
+    return top();
 }
 
 int32_t tri_solve(madipm_handle* h) {
@@ -340,6 +362,7 @@ int32_t device_create(madipm_handle* h) {
 
     DeviceState* d = new DeviceState();
     h->dev = d;
+    d->sym = &h->sym;
     d->device = h->cfg.device;
     CUDA_OK(h, cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
     CUDA_OK(h, cudaEventCreate(&d->ev0));
@@ -438,11 +461,13 @@ int32_t device_create(madipm_handle* h) {
         CUDA_OK(h, cudaMemcpy(d->child_rec, crec.data(), crec.size() * sizeof(ChildRec), cudaMemcpyHostToDevice));
     }
     {
-        std::vector<int4> ph(std::max(1, s.n_levels));
-        for (int l = 0; l < s.n_levels; ++l)
-            ph[l] = make_int4(s.phase_ptr[l], s.phase_ptr[l] + s.phase_nblock[l], s.phase_ptr[l + 1], 0);
-        if ((rc = dev_alloc(h, &d->phases, ph.size()))) return rc;
-        CUDA_OK(h, cudaMemcpy(d->phases, ph.data(), ph.size() * sizeof(int4), cudaMemcpyHostToDevice));
+        std::vector<int32_t> pc = s.phase_cls;
+        if (pc.empty()) pc.assign(5, 0);
+        UP(int, phase_cls, pc);
+        for (int op = 0; op < 3; ++op) {
+            if ((rc = dev_alloc(h, &d->tickets[op], static_cast<size_t>(4) * std::max(1, s.n_levels)))) return rc;
+            CUDA_OK(h, cudaMemsetAsync(d->tickets[op], 0, sizeof(int) * 4 * std::max(1, s.n_levels), d->stream));
+        }
     }
     std::vector<int64_t> diag_pos(d->N);
     for (int sn = 0; sn < s.nsuper; ++sn) {
@@ -466,44 +491,56 @@ int32_t device_create(madipm_handle* h) {
     d->bar_base = 0;
     d->num_sms = prop.multiProcessorCount;
     {
-        // shared memory of the tree kernels: one block task [panel | h doubles | w doubles] or eight warp tasks
-        auto even = [](int v) { return (v + 3) & ~1; };     // room for the odd-length tail chunk and the 4-column tile overrun
+        // shared memory of the tree kernels: one 256-thread group or 2 / 4 / 8 smaller ones (sizes: symbolic.cpp step 8)
         d->tree_maxw = std::max(s.max_w, 1);
-        d->tree_cap_block = even(std::max(s.small_max_panel, 2));
-        d->tree_maxh_block = even(std::max(s.small_max_h, 2));
-        d->tree_cap_warp = even(std::max(s.warp_max_panel, 2));
-        d->tree_maxh_warp = even(std::max(s.warp_max_h, 2));
-        const int crec_doubles = kChildChunk * static_cast<int>(sizeof(ChildRec) / sizeof(double));
-        d->tree_warp_stride = d->tree_cap_warp + d->tree_maxh_warp + even(d->tree_maxw) + crec_doubles;
-        const size_t blk = static_cast<size_t>(d->tree_cap_block) + d->tree_maxh_block + even(d->tree_maxw) + crec_doubles;
-        d->smem_tree = std::max(blk, static_cast<size_t>(kTreeWarps) * d->tree_warp_stride) * sizeof(double);
+        d->smem_tree = static_cast<size_t>(s.tree_slice[0]) * sizeof(double);
         if (d->smem_tree > 220 * 1024) { h->error = "block_panel too large for the shared memory of one block"; return MADIPM_BAD_ARGUMENT; }
         if (!prop.cooperativeLaunch) { h->error = "device does not support cooperative launches"; return MADIPM_CUDA_ERROR; }
         CUDA_OK(h, cudaFuncSetAttribute(k_tree<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_tree));
         CUDA_OK(h, cudaFuncSetAttribute(k_tree<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_tree));
         CUDA_OK(h, cudaFuncSetAttribute(k_tree<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_tree));
+        CUDA_OK(h, cudaFuncSetAttribute(k_tree_top<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_tree));
+        CUDA_OK(h, cudaFuncSetAttribute(k_tree_top<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_tree));
+        CUDA_OK(h, cudaFuncSetAttribute(k_tree_top<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_tree));
         CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->tree_occ[0], k_tree<0>, kTreeThreads, d->smem_tree));
         CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->tree_occ[1], k_tree<1>, kTreeThreads, d->smem_tree));
         CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->tree_occ[2], k_tree<2>, kTreeThreads, d->smem_tree));
+        int top_occ = 1;
+        {
+            int o = 0;
+            CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_tree_top<0>, kTopThreads, d->smem_tree)); top_occ = std::min(top_occ, o);
+            CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_tree_top<1>, kTopThreads, d->smem_tree)); top_occ = std::min(top_occ, o);
+            CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_tree_top<2>, kTopThreads, d->smem_tree)); top_occ = std::min(top_occ, o);
+        }
         for (int op = 0; op < 3; ++op)
             if (d->tree_occ[op] < 1) { h->error = "tree kernel does not fit on an SM"; return MADIPM_INTERNAL; }
         // launch plan: consecutive heights share one cooperative launch; a height with big supernodes ends it
-        // (MADIPM_TREE_SPLIT=1 gives every height its own launch: a per-height launch list for the profiler)
+        // (MADIPM_TREE_SPLIT=1 gives every height its own launch: a per-height launch list for the profiler;
+        //  MADIPM_TREE_NOTOP=1 keeps the heights near the root in k_tree)
         const char* split_env = std::getenv("MADIPM_TREE_SPLIT");
         const bool split = split_env && split_env[0] == '1';
+        const char* notop_env = std::getenv("MADIPM_TREE_NOTOP");
+        const bool use_top = top_occ >= 1 && !(notop_env && notop_env[0] == '1');
         int l0 = 0;
         for (int l = 0; l < s.n_levels; ++l) {
             const bool last = l + 1 == s.n_levels;
             if (s.big_ptr[l + 1] > s.big_ptr[l] || last || split) {
                 DeviceState::TreeSeg sg;
-                sg.ph0 = l0; sg.ph1 = l + 1;
-                int64_t need = 0;
-                for (int q = l0; q <= l; ++q) {
-                    const int64_t nblk = s.phase_nblock[q], nwrp = s.phase_ptr[q + 1] - s.phase_ptr[q] - nblk;
-                    need = std::max(need, nblk * B + (nwrp * B + kTreeWarps - 1) / kTreeWarps);
+                sg.ph0 = l0; sg.ph1 = l + 1; sg.split = sg.ph1;
+                auto ntasks = [&](int q) { return static_cast<int64_t>(s.phase_ptr[q + 1] - s.phase_ptr[q]) * B; };
+                if (use_top)
+                    while (sg.split > sg.ph0 && ntasks(sg.split - 1) <= d->num_sms) --sg.split;
+                int64_t need = 0, need_top = 0;
+                for (int q = sg.ph0; q < sg.split; ++q) {
+                    const int32_t* pc = s.phase_cls.data() + static_cast<size_t>(q) * 5;
+                    int64_t blocks = 0;
+                    for (int c = 0; c < 4; ++c) blocks += (static_cast<int64_t>(pc[c + 1] - pc[c]) * B + (1 << c) - 1) >> c;
+                    need = std::max(need, blocks);
                 }
+                for (int q = sg.split; q < sg.ph1; ++q) need_top = std::max(need_top, ntasks(q));
                 for (int op = 0; op < 3; ++op)
                     sg.grid[op] = static_cast<int>(std::min<int64_t>(need, static_cast<int64_t>(d->tree_occ[op]) * d->num_sms));
+                sg.grid_top = static_cast<int>(std::min<int64_t>(need_top, d->num_sms));
                 d->segs.push_back(sg);
                 l0 = l + 1;
             }

@@ -3,9 +3,13 @@
 // All supernodes of one height of the supernodal elimination tree are independent.  The three kernels below
 // are persistent: one cooperative launch walks a range of heights, with a grid-wide barrier between two
 // heights, so a factorisation or a triangular sweep of a tree whose panels all fit one block is ONE launch.
-// Inside a height every supernode is a task: a whole 256-thread block for the larger panels, one warp for
-// the small ones (eight independent warp tasks per block), each with the panel staged in shared memory by
-// cp.async (16-byte, L2 only).
+// Inside a height every supernode is a task for a GROUP of 256, 128, 64 or 32 threads (its class: the smallest
+// group whose proportional slice of the block's shared memory holds the panel), staged in shared memory by
+// cp.async (16-byte, L2 only).  Groups take tasks from a per-(height, class) ticket counter, largest class first,
+// so a block runs one 256-thread task, or two 128-thread tasks, ... or eight warp tasks at a time and nobody idles
+// while work of its class is left.  The last heights of a tree hold fewer tasks than the GPU has SMs; they run in
+// a second kernel with one 1024-thread block per task (k_tree_top): there the latency of a single task is all that
+// matters, and four times the threads put four times the loads in flight.
 //
 // The factorisation is multifrontal in its data flow, supernodal in its storage:
 //   * a task loads its h x w panel (original KKT entries, put there by k_assemble_panels, plus whatever big
@@ -70,10 +74,10 @@ struct TreeView {
     double* xw;                  // [batch][xw_stride] permuted right-hand side / solution
     int64_t xw_stride;
     unsigned* bar;               // grid barrier counter (monotone; the host passes the value it has before a launch)
+    int* tickets;                // [n_levels][4] task tickets of the launch (zeroed by the host before it)
+    const int* phase_cls;        // [n_levels][5] first task of class 256 / 128 / 64 / 32, end of the phase
     int B;
-    int cap_block, maxh_block;   // shared-memory panel capacity (doubles) and row capacity of a block task
-    int cap_warp, maxh_warp;     // the same for one warp task
-    int warp_stride;             // doubles between the warp slices
+    int slice[4], cap[4], maxh[4];   // per class: doubles of shared memory per group, of which panel, of which rows
     int maxw;
     int dbg_sn;                  // MADIPM_TREE_TIMING builds: supernode whose stage clocks are printed
 };
@@ -84,10 +88,13 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// barrier of one task group: a warp, the whole block (256 threads in k_tree, 1024 in k_tree_top), or a named
+// barrier for the 128- and 64-thread groups (ids 1-2 and 3-6; barrier 0 is __syncthreads)
 template <int G>
 __device__ __forceinline__ void gsync() {
     if (G == 32) __syncwarp();
-    else __syncthreads();
+    else if (G >= kTreeThreads) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"((G == 128 ? 1 : 3) + static_cast<int>(threadIdx.x) / G), "n"(G) : "memory");
 }
 
 // offset of column b inside a packed lower triangle of order nb, shifted so that [a] addresses row a >= b
@@ -138,11 +145,19 @@ template <int G>
 __device__ __forceinline__ void dense_ldl(double* Ps, int h, int w, int* fail, int t) {
     constexpr int NB = 4;
     for (int jb = 0; jb < w; jb += NB) {
+        LDL_PROBE(7);
+        if (jb + (t & ~31) >= h) {                        // this warp owns no row any more: only keep the barriers company
+            gsync<G>();
+            gsync<G>();
+            gsync<G>();
+            continue;
+        }
         const int bw = min(NB, w - jb);
         const int o1 = bw > 1 ? h : 0, o2 = bw > 2 ? 2 * h : 0, o3 = bw > 3 ? 3 * h : 0;   // missing columns alias column 0
         // 1. left-looking update of this block's entries of my rows (the first row stays in registers)
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         const double* U = Ps + jb * h;                     // U[k + c * h] = L[jb + c][k] * d_k for k < jb (upper triangle)
+#pragma unroll 1
         for (int i = jb + t; i < h; i += G) {
             const double* li = Ps + i;
             double* row = Ps + i + jb * h;
@@ -191,6 +206,7 @@ __device__ __forceinline__ void dense_ldl(double* Ps, int h, int w, int* fail, i
         //    (d3 = v3 of the fourth pivot row: its reciprocal is taken by the rows below from their own copy.)
         const double d3f = fma(-a32, l32, fma(-a31, l31, fma(-a30, l30, d3)));
         const double r3 = fast_rcp(d3f);
+#pragma unroll 1
         for (int i = jb + t; i < h; i += G) {
             double* row = Ps + i + jb * h;
             double* up = Ps + jb + i * h;
@@ -228,9 +244,9 @@ template <int G>
 __device__ __forceinline__ void tree_factor_task(const TreeView& T, int s, int inst, double* sm, int cap, int maxh) {
     const FactorView& F = T.F;
     constexpr int NW = G / 32;
-    const int t = (G == 32) ? (threadIdx.x & 31) : threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const int gw = (G == 32) ? 0 : (threadIdx.x >> 5);
+    const int t = threadIdx.x % G;
+    const int lane = t & 31;
+    const int gw = t >> 5;
     const SnMeta m = ldg32(T.meta + s);
     const int c0 = __ldg(T.child_ptr + s), c1 = __ldg(T.child_ptr + s + 1);
     const int w = m.w, h = m.h, nb = h - w;
@@ -300,7 +316,7 @@ __device__ __forceinline__ void tree_factor_task(const TreeView& T, int s, int i
         for (int a = b0 + lane; a < nb; a += 32) {
             const double* La = Ps + w + a;
             double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-#pragma unroll 2
+#pragma unroll 4
             for (int k = 0; k < w; ++k) {
                 const double av = La[k * h] * dk[k];
                 acc0 = fma(av, Lb[k * h], acc0);
@@ -372,9 +388,9 @@ __device__ __forceinline__ void tree_factor_task(const TreeView& T, int s, int i
 template <int G>
 __device__ __forceinline__ void tree_forward_task(const TreeView& T, int s, int inst, double* sm, int cap, int maxh) {
     const FactorView& F = T.F;
-    const int t = (G == 32) ? (threadIdx.x & 31) : threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const int gw = (G == 32) ? 0 : (threadIdx.x >> 5);
+    const int t = threadIdx.x % G;
+    const int lane = t & 31;
+    const int gw = t >> 5;
     const SnMeta m = ldg32(T.meta + s);
     const int c0 = __ldg(T.child_ptr + s), c1 = __ldg(T.child_ptr + s + 1);
     const int w = m.w, h = m.h, nb = h - w, fc = m.fc;
@@ -435,9 +451,9 @@ template <int G>
 __device__ __forceinline__ void tree_backward_task(const TreeView& T, int s, int inst, double* sm, int cap, int maxh) {
     const FactorView& F = T.F;
     constexpr int NW = G / 32;
-    const int t = (G == 32) ? (threadIdx.x & 31) : threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const int gw = (G == 32) ? 0 : (threadIdx.x >> 5);
+    const int t = threadIdx.x % G;
+    const int lane = t & 31;
+    const int gw = t >> 5;
     const SnMeta m = ldg32(T.meta + s);
     const int w = m.w, h = m.h, nb = h - w, fc = m.fc;
     const double* P = F.Lx + inst * F.lx_stride + m.xoff;
@@ -495,35 +511,59 @@ __device__ __forceinline__ void tree_task(const TreeView& T, int s, int inst, do
     else tree_backward_task<G>(T, s, inst, sm, cap, maxh);
 }
 
-// phases[k] = { first block task, first warp task, end of the warp tasks, unused } as indices into task_sn.
+// one group of G threads drains the tasks of its class in phase ph (ticket counter), then returns
+template <int OP, int G, int CLS>
+__device__ __forceinline__ void run_class(const TreeView& T, double* smem, int ph) {
+    const int first = __ldg(T.phase_cls + ph * 5 + CLS);
+    const int n = __ldg(T.phase_cls + ph * 5 + CLS + 1) - first;
+    if (n == 0) return;
+    const int64_t total = static_cast<int64_t>(n) * T.B;
+    double* sm = smem + (static_cast<int>(threadIdx.x) / G) * T.slice[CLS];
+    volatile int* slot = reinterpret_cast<volatile int*>(sm + T.slice[CLS] - 2);
+    const int t = threadIdx.x % G;
+    for (;;) {
+        gsync<G>();                                       // the previous ticket has been read by everyone
+        if (t == 0) *slot = atomicAdd(T.tickets + ph * 4 + CLS, 1);
+        gsync<G>();
+        const int64_t q = *slot;
+        if (q >= total) break;
+        const int inst = static_cast<int>(q / n);
+        tree_task<OP, G>(T, __ldg(T.task_sn + first + static_cast<int>(q - static_cast<int64_t>(inst) * n)), inst, sm, T.cap[CLS], T.maxh[CLS]);
+    }
+}
+
 // OP: 0 factor, 1 forward, 2 backward.  Heights ph_begin, ph_begin + step, ... (ph_end excluded).
 template <int OP>
 __global__ void __launch_bounds__(kTreeThreads, 4)
-k_tree(TreeView T, const int4* __restrict__ phases, int ph_begin, int ph_end, int step, unsigned bar_base) {
+k_tree(TreeView T, int ph_begin, int ph_end, int step, unsigned bar_base) {
     extern __shared__ double2 tree_smem2[];
     double* smem = reinterpret_cast<double*>(tree_smem2);
-    const int warp = threadIdx.x >> 5;
     unsigned target = bar_base;
     for (int ph = ph_begin; ph != ph_end; ph += step) {
-        const int4 p = phases[ph];
-        const int nblk = p.y - p.x, nwrp = p.z - p.y;
-        const int64_t nbt = static_cast<int64_t>(nblk) * T.B;
-        for (int64_t q = blockIdx.x; q < nbt; q += gridDim.x) {
-            const int inst = static_cast<int>(q / nblk);
-            tree_task<OP, kTreeThreads>(T, __ldg(T.task_sn + p.x + static_cast<int>(q - static_cast<int64_t>(inst) * nblk)), inst,
-                                        smem, T.cap_block, T.maxh_block);
-        }
-        if (nwrp > 0) {
-            __syncthreads();
-            // blocks that had no block task in their first round take the first warp tasks
-            const int rot = static_cast<int>((blockIdx.x + gridDim.x - static_cast<unsigned>(nbt % gridDim.x)) % gridDim.x);
-            const int64_t nwt = static_cast<int64_t>(nwrp) * T.B;
-            double* sm = smem + warp * T.warp_stride;
-            for (int64_t q = static_cast<int64_t>(rot) * kTreeWarps + warp; q < nwt; q += static_cast<int64_t>(gridDim.x) * kTreeWarps) {
-                const int inst = static_cast<int>(q / nwrp);
-                tree_task<OP, 32>(T, __ldg(T.task_sn + p.y + static_cast<int>(q - static_cast<int64_t>(inst) * nwrp)), inst, sm,
-                                  T.cap_warp, T.maxh_warp);
-            }
+        run_class<OP, 256, 0>(T, smem, ph);
+        run_class<OP, 128, 1>(T, smem, ph);
+        run_class<OP, 64, 2>(T, smem, ph);
+        run_class<OP, 32, 3>(T, smem, ph);
+        if (ph + step != ph_end) grid_barrier(T.bar, target);
+    }
+}
+
+// the heights near the root: at most one task per SM, one 1024-thread block per task
+constexpr int kTopThreads = 1024;
+template <int OP>
+__global__ void __launch_bounds__(kTopThreads, 1)
+k_tree_top(TreeView T, int ph_begin, int ph_end, int step, unsigned bar_base) {
+    extern __shared__ double2 tree_smem2[];
+    double* smem = reinterpret_cast<double*>(tree_smem2);
+    unsigned target = bar_base;
+    for (int ph = ph_begin; ph != ph_end; ph += step) {
+        const int first = __ldg(T.phase_cls + ph * 5);
+        const int n = __ldg(T.phase_cls + ph * 5 + 4) - first;
+        const int64_t total = static_cast<int64_t>(n) * T.B;
+        for (int64_t q = blockIdx.x; q < total; q += gridDim.x) {
+            const int inst = static_cast<int>(q / n);
+            tree_task<OP, kTopThreads>(T, __ldg(T.task_sn + first + static_cast<int>(q - static_cast<int64_t>(inst) * n)), inst, smem,
+                                       T.cap[0], T.maxh[0]);
         }
         if (ph + step != ph_end) grid_barrier(T.bar, target);
     }

@@ -372,7 +372,9 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
     std::vector<int32_t> perm0;
     if (opt.ordering == 1) { perm0.resize(n); std::iota(perm0.begin(), perm0.end(), 0); }
     else if (opt.ordering == 2) {
-        int32_t leaf = opt.nd_leaf > 0 ? opt.nd_leaf : std::min(4096, std::max(128, n / 1024));
+        // small leaves: the height of the supernodal tree (= number of phases of the factor / solve kernels, each a
+        // latency-bound critical path) matters more than the few percent of fill that AMD on larger leaves saves
+        int32_t leaf = opt.nd_leaf > 0 ? opt.nd_leaf : std::min(1024, std::max(128, n / 4096));
         nd_order(n, colptr, rowval, perm0, leaf, opt.nd_max_sep);
     } else amd_order(n, colptr, rowval, perm0, opt.dense_factor);
     std::vector<int32_t> ip0(n, -1);
@@ -715,8 +717,7 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
         }
     }
     S.sn_coff.assign(static_cast<size_t>(ns) + 1, 0);
-    S.small_max_panel = S.small_max_h = S.warp_max_panel = S.warp_max_h = 0;
-    std::vector<char> warp_task(ns, 0);
+    S.small_max_panel = S.small_max_h = 0;
     for (int32_t s = 0; s < ns; ++s) {
         int64_t hs = S.sn_rowptr[s + 1] - S.sn_rowptr[s], ws = S.sn_first[s + 1] - S.sn_first[s];
         int64_t nb = hs - ws, sz = 0;
@@ -724,20 +725,35 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
             sz = (nb * (nb + 1) / 2 + 1) & ~int64_t(1);
             S.small_max_panel = std::max<int32_t>(S.small_max_panel, static_cast<int32_t>(hs * ws));
             S.small_max_h = std::max<int32_t>(S.small_max_h, static_cast<int32_t>(hs));
-            if (hs * ws <= opt.warp_panel && hs <= opt.warp_rows) {
-                warp_task[s] = 1;
-                S.warp_max_panel = std::max<int32_t>(S.warp_max_panel, static_cast<int32_t>(hs * ws));
-                S.warp_max_h = std::max<int32_t>(S.warp_max_h, static_cast<int32_t>(hs));
-            }
         }
         S.sn_coff[s + 1] = S.sn_coff[s] + sz;
+    }
+    // shared-memory slices of the four task classes (doubles): [panel | h doubles | max_w doubles | 16 child records | ticket]
+    auto even = [](int64_t v) { return static_cast<int32_t>((v + 1) & ~int64_t(1)); };
+    auto panel_need = [&](int64_t np) { return even(np) + 2; };            // odd tail chunk + 4-column tile overrun
+    S.tree_fixed = even(std::max(S.max_w, 1)) + 16 * 4 + 2;
+    // a multiple of 16 doubles, so that the slices of the smaller classes nest exactly inside the larger ones
+    const int32_t slice256 = (panel_need(std::max(S.small_max_panel, 2)) + even(std::max(S.small_max_h, 2)) + S.tree_fixed + 15) & ~15;
+    for (int32_t c = 0; c < 4; ++c) {
+        const int32_t G = 256 >> c;
+        S.tree_slice[c] = slice256 >> c;
+        S.tree_maxh[c] = c == 0 ? even(std::max(S.small_max_h, 2)) : std::min(even(std::max(S.small_max_h, 2)), 4 * G);
+        S.tree_cap[c] = S.tree_slice[c] - S.tree_maxh[c] - S.tree_fixed;
+    }
+    std::vector<int8_t> cls(ns, 0);
+    for (int32_t s = 0; s < ns; ++s) {
+        if (S.sn_kind[s] == 2) continue;
+        int64_t hs = S.sn_rowptr[s + 1] - S.sn_rowptr[s], ws = S.sn_first[s + 1] - S.sn_first[s];
+        for (int32_t c = 3; c >= 1; --c)
+            if (hs <= S.tree_maxh[c] && panel_need(hs * ws) <= S.tree_cap[c]) { cls[s] = static_cast<int8_t>(c); break; }
     }
     S.phase_ptr.assign(static_cast<size_t>(S.n_levels) + 1, 0);
     S.big_ptr.assign(static_cast<size_t>(S.n_levels) + 1, 0);
     S.phase_nblock.assign(S.n_levels, 0);
+    S.phase_cls.assign(static_cast<size_t>(S.n_levels) * 5, 0);
     for (int32_t s = 0; s < ns; ++s) {
         if (S.sn_kind[s] == 2) ++S.big_ptr[S.sn_level[s] + 1];
-        else { ++S.phase_ptr[S.sn_level[s] + 1]; if (!warp_task[s]) ++S.phase_nblock[S.sn_level[s]]; }
+        else { ++S.phase_ptr[S.sn_level[s] + 1]; if (cls[s] != 3) ++S.phase_nblock[S.sn_level[s]]; }
     }
     for (int32_t l = 0; l < S.n_levels; ++l) { S.phase_ptr[l + 1] += S.phase_ptr[l]; S.big_ptr[l + 1] += S.big_ptr[l]; }
     S.task_sn.assign(S.phase_ptr[S.n_levels], 0);
@@ -752,11 +768,18 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
             double hs = static_cast<double>(S.sn_rowptr[s + 1] - S.sn_rowptr[s]), ws = static_cast<double>(S.sn_first[s + 1] - S.sn_first[s]);
             return ws * hs * hs;
         };
-        for (int32_t l = 0; l < S.n_levels; ++l)
+        for (int32_t l = 0; l < S.n_levels; ++l) {
             std::stable_sort(S.task_sn.begin() + S.phase_ptr[l], S.task_sn.begin() + S.phase_ptr[l + 1], [&](int32_t a, int32_t b) {
-                if (warp_task[a] != warp_task[b]) return warp_task[a] < warp_task[b];
+                if (cls[a] != cls[b]) return cls[a] < cls[b];
                 return cost(a) > cost(b);
             });
+            int32_t q = S.phase_ptr[l];
+            for (int32_t c = 0; c < 4; ++c) {
+                S.phase_cls[static_cast<size_t>(l) * 5 + c] = q;
+                while (q < S.phase_ptr[l + 1] && cls[S.task_sn[q]] == c) ++q;
+            }
+            S.phase_cls[static_cast<size_t>(l) * 5 + 4] = S.phase_ptr[l + 1];
+        }
     }
     S.n_big = static_cast<int32_t>(S.big_sn.size());
     S.n_block_tasks = 0;

@@ -38,8 +38,6 @@ struct SymbolicOptions {
     double relax_zeros[3] = {0.5, 0.2, 0.05};   // allowed zero fraction for merged width <= 16, <= 48, larger
     int64_t block_panel = 12288;   // panels up to this many doubles (and at most block_below rows under the diagonal
     int32_t block_below = 256;     //   block) are factorised by ONE thread block in shared memory; larger ones are "big"
-    int32_t warp_panel = 512;      // panels up to this many doubles and at most warp_rows rows are handled by one warp
-    int32_t warp_rows = 96;
     double dense_factor = 10.0;
 };
 
@@ -88,14 +86,20 @@ struct Symbolic {
     std::vector<int32_t> child_idx;      // children of every supernode, ascending
     std::vector<int32_t> par_pos;        // indexed like sn_rows: position of below-row i inside the PARENT's row list
     std::vector<int64_t> sn_coff;        // [nsuper+1] offsets of the contribution blocks (kind 0 / 1 only)
-    std::vector<int32_t> task_sn;        // small supernodes ordered by (height, block tasks first, heaviest first)
+    // A small supernode is a task of one of four classes: a group of 256, 128, 64 or 32 threads works on it with a
+    // proportional slice of the block's shared memory (class = the smallest group whose slice holds the panel).
+    std::vector<int32_t> task_sn;        // small supernodes ordered by (height, class 256 first, heaviest first)
     std::vector<int32_t> phase_ptr;      // [n_levels+1] into task_sn
-    std::vector<int32_t> phase_nblock;   // [n_levels] the first phase_nblock[k] tasks of a phase take a whole block
+    std::vector<int32_t> phase_cls;      // [n_levels][5] first task of class 256, 128, 64, 32 and the end of the phase
+    std::vector<int32_t> phase_nblock;   // [n_levels] tasks of a phase that are not warp (class 32) tasks
+    int32_t tree_slice[4] = {0, 0, 0, 0};   // doubles of shared memory of one group, per class
+    int32_t tree_cap[4] = {0, 0, 0, 0};     // ... of which panel
+    int32_t tree_maxh[4] = {0, 0, 0, 0};    // ... and rows (vector scratch)
+    int32_t tree_fixed = 0;                 // ... and the rest (max_w doubles, child records, ticket)
     std::vector<int32_t> big_ptr;        // [n_levels+1] into big_sn
     std::vector<int32_t> big_sn;         // big supernodes grouped by height
     int32_t n_block_tasks = 0, n_warp_tasks = 0, n_big = 0;
     int32_t small_max_panel = 0, small_max_h = 0;   // over kind 0 / 1 (shared-memory sizing of the tree kernels)
-    int32_t warp_max_panel = 0, warp_max_h = 0;     // over the warp tasks
 
     int64_t nnz_L = 0;        // exact nnz(L) = sum colcount
     int64_t nnz_stored = 0;   // panel storage incl. relaxation zeros and the unused upper triangles

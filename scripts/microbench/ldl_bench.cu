@@ -4,7 +4,10 @@
 #include <cmath>
 #include <cuda_runtime.h>
 __device__ long long g_probe[8];
-#define LDL_PROBE(k) do { if (t == 0 && jb == 0) g_probe[k] = clock64(); } while (0)
+#ifndef PROBE_JB
+#define PROBE_JB 0
+#endif
+#define LDL_PROBE(k) do { if (t == 0 && jb == PROBE_JB) g_probe[k] = clock64(); } while (0)
 #include "../../madqp.jl_b200/csrc/kernels_tree.cuh"
 using namespace madipm;
 template <int G>
@@ -43,7 +46,7 @@ int main() {
             cudaError_t e = cudaDeviceSynchronize();
             long long c; cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
             long long pr[8]; cudaMemcpyFromSymbol(pr, g_probe, 64);
-            printf("   first block step: update %lld | sync %lld | diag %lld | pivotcheck %lld | sync %lld | rows %lld | sync %lld\n", pr[0] - 0, pr[1] - pr[0], pr[2] - pr[1], pr[3] - pr[2], pr[4] - pr[3], pr[5] - pr[4], pr[6] - pr[5]);
+            printf("   probed block step: update %lld | sync %lld | diag %lld | pivotcheck %lld | sync %lld | rows %lld | sync %lld\n", pr[0] - pr[7], pr[1] - pr[0], pr[2] - pr[1], pr[3] - pr[2], pr[4] - pr[3], pr[5] - pr[4], pr[6] - pr[5]);
             std::vector<double> L(A.size()); cudaMemcpy(L.data(), dP, A.size() * 8, cudaMemcpyDeviceToHost);
             // check: A0 (lower) == L D L' on the h x w panel
             double err = 0;
