@@ -11,7 +11,7 @@
 namespace madipm {
 
 constexpr int kVecThreads = 256;
-constexpr int kMaxRedBlocks = 592;   // 148 SMs x 4 resident blocks
+constexpr int kMaxRedBlocks = 1184;  // 148 SMs x 8 resident blocks of 256 threads
 
 // ---------------------------------------------------------------------------------------------
 // block / grid reduction helpers

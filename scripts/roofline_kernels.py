@@ -1,8 +1,9 @@
 """Isolated roofline measurement of the streaming kernels (SpMV, assembly, vector phases) on config C3.
 
-Each kernel is timed alone with CUDA events on the solver's stream, cold (L2 flushed by writing a 512 MB
-buffer between repetitions) and warm (back to back), against the algorithmic bytes of SURVEY 8d and the
-measured HBM peak of MEASURED_PEAKS.json.  Output: one JSON line per kernel (kept under profiles/).
+Each kernel is timed with CUDA events on the solver's stream as a back-to-back series of 20 launches (no host
+gaps inside the timed region): warm = series / 20 (operands stay in the 126 MB L2), cold = a 512 MB memset
+between launches evicts L2 and the same series without the kernel is subtracted.  Bytes are the algorithmic
+bytes of SURVEY 8d, the peak is the measured HBM copy bandwidth of MEASURED_PEAKS.json.  Output: one JSON line per kernel (kept under profiles/).
 """
 import json, os, sys
 import numpy as np
@@ -43,17 +44,29 @@ KERNELS = {
     "update K14 (k_update_iterate)": (lambda: h.update_iterate(0.0, 0.0, 1e-3), 8 * (9 * n + 2 * m) + 8 * (nlb + nub)),
 }
 
+def run_series(fn, cold, reps):
+    """reps x [flush?; kernel] back to back on the solver's stream between two events (no host gaps)."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(reps):
+            if cold:
+                flush.zero_()
+            if fn is not None:
+                fn()
+        e1.record(stream)
+    h.synchronize()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3
+
+
 def timed(fn, cold, reps=20):
-    ts = []
-    for _ in range(reps):
-        if cold:
-            flush.zero_()
-            torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream); fn(); e1.record(stream)
-        h.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    return float(np.median(ts)) * 1e-3
+    """Device time of one launch: the series with the kernel minus the series without it (cold: a 512 MB
+    memset between launches evicts L2, and its own time is what the second series measures)."""
+    base = min(run_series(None, cold, reps) for _ in range(3)) if cold else 0.0
+    full = min(run_series(fn, cold, reps) for _ in range(3))
+    return max(full - base, 1e-9) / reps
+
 
 for kname, spec in KERNELS.items():
     if spec is None:
