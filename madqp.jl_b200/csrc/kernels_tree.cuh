@@ -241,13 +241,12 @@ __device__ __forceinline__ void dense_ldl(double* Ps, int h, int w, int* fail, i
 // ---- numeric factorisation of one small supernode ------------------------------------------------------
 // shared: [cap doubles panel][maxh doubles (unused by the blocked LDL')][maxw doubles D][kChildChunk child records]
 template <int G>
-__device__ __forceinline__ void tree_factor_task(const TreeView& T, int s, int inst, double* sm, int cap, int maxh) {
+__device__ __forceinline__ void tree_factor_task(const TreeView& T, int s, const SnMeta& m, int inst, double* sm, int cap, int maxh) {
     const FactorView& F = T.F;
     constexpr int NW = G / 32;
     const int t = threadIdx.x % G;
     const int lane = t & 31;
     const int gw = t >> 5;
-    const SnMeta m = ldg32(T.meta + s);
     const int c0 = __ldg(T.child_ptr + s), c1 = __ldg(T.child_ptr + s + 1);
     const int w = m.w, h = m.h, nb = h - w;
     double* Lx = F.Lx + inst * F.lx_stride;
@@ -278,22 +277,25 @@ __device__ __forceinline__ void tree_factor_task(const TreeView& T, int s, int i
             if (!r.pull) continue;                        // that child scattered its block itself
             const int* pos = T.par_pos + r.below;
             const double* Cc = Cx + r.coff;
-            // work items = (column b, 32-row chunk); four items in flight per warp so the loads overlap
-            const int nch = (r.nb + 31) >> 5, nitems = r.nbp * nch;
-            for (int q0 = gw; q0 < nitems; q0 += 4 * NW) {
-                int dsti[4];
-                double v[4];
+            // lanes own rows (32 per chunk), warps take columns four at a time so that the loads overlap
+            for (int a0 = 0; a0 < r.nb; a0 += 32) {
+                const int a = a0 + lane;
+                const int pa = a < r.nb ? __ldg(pos + a) : 0;
+                const int bend = min(r.nbp, a0 + 32);              // columns b <= a only
+                for (int b0 = gw; b0 < bend; b0 += 4 * NW) {
+                    int dsti[4];
+                    double v[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int q = q0 + u * NW;
-                    const int b = q / nch, a = ((q - b * nch) << 5) + lane;
-                    const bool ok = q < nitems && a >= b && a < r.nb;
-                    dsti[u] = ok ? __ldg(pos + a) + __ldg(pos + b) * h : -1;
-                    v[u] = ok ? __ldcg(Cc + packed_col(b, r.nb) + a) : 0.0;
+                    for (int u = 0; u < 4; ++u) {
+                        const int b = b0 + u * NW;
+                        const bool ok = b < bend && a >= b && a < r.nb;
+                        dsti[u] = ok ? pa + __ldg(pos + b) * h : -1;
+                        v[u] = ok ? __ldcg(Cc + packed_col(b, r.nb) + a) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (dsti[u] >= 0) Ps[dsti[u]] += v[u];
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (dsti[u] >= 0) Ps[dsti[u]] += v[u];
             }
             gsync<G>();
         }
@@ -341,24 +343,27 @@ __device__ __forceinline__ void tree_factor_task(const TreeView& T, int s, int i
             gsync<G>();                                   // C (or the previous child's additions) is in place
             const int* pos = T.par_pos + r.below;
             const double* Cc = Cx + r.coff;
-            const int nch = (r.nb + 31) >> 5, nitems = (r.nb - r.nbp) * nch;
-            for (int q0 = gw; q0 < nitems; q0 += 4 * NW) {
-                double* dst[4];
-                double v[4];
+            for (int a0 = (r.nbp >> 5) << 5; a0 < r.nb; a0 += 32) {
+                const int a = a0 + lane;
+                const int pa = a < r.nb ? __ldg(pos + a) - w : 0;
+                const int bend = min(r.nb, a0 + 32);
+                for (int b0 = r.nbp + gw; b0 < bend; b0 += 4 * NW) {
+                    double* dst[4];
+                    double v[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int q = q0 + u * NW;
-                    const int b = r.nbp + q / nch, a = ((q - (b - r.nbp) * nch) << 5) + lane;
-                    const bool ok = q < nitems && a >= b && a < r.nb;
-                    dst[u] = ok ? Cs + packed_col(__ldg(pos + b) - w, nb) + (__ldg(pos + a) - w) : nullptr;
-                    v[u] = ok ? __ldcg(Cc + packed_col(b, r.nb) + a) : 0.0;
+                    for (int u = 0; u < 4; ++u) {
+                        const int b = b0 + u * NW;
+                        const bool ok = b < bend && a >= b && a < r.nb;
+                        dst[u] = ok ? Cs + packed_col(__ldg(pos + b) - w, nb) + pa : nullptr;
+                        v[u] = ok ? __ldcg(Cc + packed_col(b, r.nb) + a) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (dst[u]) v[u] += __ldcg(dst[u]);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (dst[u]) *dst[u] = v[u];
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (dst[u]) v[u] += __ldcg(dst[u]);
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (dst[u]) *dst[u] = v[u];
             }
         }
     }
@@ -386,12 +391,11 @@ __device__ __forceinline__ void tree_factor_task(const TreeView& T, int s, int i
 // ---- forward sweep: y = L^-1 b, xw <- D^-1 y ---------------------------------------------------------------
 // shared: [cap doubles panel][maxh doubles pass-through][maxw doubles y][kChildChunk child records]
 template <int G>
-__device__ __forceinline__ void tree_forward_task(const TreeView& T, int s, int inst, double* sm, int cap, int maxh) {
+__device__ __forceinline__ void tree_forward_task(const TreeView& T, int s, const SnMeta& m, int inst, double* sm, int cap, int maxh) {
     const FactorView& F = T.F;
     const int t = threadIdx.x % G;
     const int lane = t & 31;
     const int gw = t >> 5;
-    const SnMeta m = ldg32(T.meta + s);
     const int c0 = __ldg(T.child_ptr + s), c1 = __ldg(T.child_ptr + s + 1);
     const int w = m.w, h = m.h, nb = h - w, fc = m.fc;
     const double* P = F.Lx + inst * F.lx_stride + m.xoff;
@@ -448,13 +452,12 @@ __device__ __forceinline__ void tree_forward_task(const TreeView& T, int s, int 
 // ---- backward sweep: x = L^-T xw -----------------------------------------------------------------------------
 // shared: [cap doubles panel][maxh doubles x at the below rows][maxw doubles block solution]
 template <int G>
-__device__ __forceinline__ void tree_backward_task(const TreeView& T, int s, int inst, double* sm, int cap, int maxh) {
+__device__ __forceinline__ void tree_backward_task(const TreeView& T, int s, const SnMeta& m, int inst, double* sm, int cap, int maxh) {
     const FactorView& F = T.F;
     constexpr int NW = G / 32;
     const int t = threadIdx.x % G;
     const int lane = t & 31;
     const int gw = t >> 5;
-    const SnMeta m = ldg32(T.meta + s);
     const int w = m.w, h = m.h, nb = h - w, fc = m.fc;
     const double* P = F.Lx + inst * F.lx_stride + m.xoff;
     double* xw = T.xw + inst * T.xw_stride;
@@ -505,10 +508,10 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
 }
 
 template <int OP, int G>
-__device__ __forceinline__ void tree_task(const TreeView& T, int s, int inst, double* sm, int cap, int maxh) {
-    if (OP == 0) tree_factor_task<G>(T, s, inst, sm, cap, maxh);
-    else if (OP == 1) tree_forward_task<G>(T, s, inst, sm, cap, maxh);
-    else tree_backward_task<G>(T, s, inst, sm, cap, maxh);
+__device__ __forceinline__ void tree_task(const TreeView& T, int s, const SnMeta& m, int inst, double* sm, int cap, int maxh) {
+    if (OP == 0) tree_factor_task<G>(T, s, m, inst, sm, cap, maxh);
+    else if (OP == 1) tree_forward_task<G>(T, s, m, inst, sm, cap, maxh);
+    else tree_backward_task<G>(T, s, m, inst, sm, cap, maxh);
 }
 
 // one group of G threads drains the tasks of its class in phase ph (ticket counter), then returns
@@ -528,7 +531,8 @@ __device__ __forceinline__ void run_class(const TreeView& T, double* smem, int p
         const int64_t q = *slot;
         if (q >= total) break;
         const int inst = static_cast<int>(q / n);
-        tree_task<OP, G>(T, __ldg(T.task_sn + first + static_cast<int>(q - static_cast<int64_t>(inst) * n)), inst, sm, T.cap[CLS], T.maxh[CLS]);
+        const int s = __ldg(T.task_sn + first + static_cast<int>(q - static_cast<int64_t>(inst) * n));
+        tree_task<OP, G>(T, s, ldg32(T.meta + s), inst, sm, T.cap[CLS], T.maxh[CLS]);
     }
 }
 
@@ -562,8 +566,8 @@ k_tree_top(TreeView T, int ph_begin, int ph_end, int step, unsigned bar_base) {
         const int64_t total = static_cast<int64_t>(n) * T.B;
         for (int64_t q = blockIdx.x; q < total; q += gridDim.x) {
             const int inst = static_cast<int>(q / n);
-            tree_task<OP, kTopThreads>(T, __ldg(T.task_sn + first + static_cast<int>(q - static_cast<int64_t>(inst) * n)), inst, smem,
-                                       T.cap[0], T.maxh[0]);
+            const int s = __ldg(T.task_sn + first + static_cast<int>(q - static_cast<int64_t>(inst) * n));
+            tree_task<OP, kTopThreads>(T, s, ldg32(T.meta + s), inst, smem, T.cap[0], T.maxh[0]);
         }
         if (ph + step != ph_end) grid_barrier(T.bar, target);
     }
