@@ -41,7 +41,7 @@ struct DeviceState {
     int* phase_cls = nullptr;
     int num_sms = 0;
     unsigned bar_base = 0;             // value of *bar before the next launch (barriers only ever add to it)
-    int *child_ptr = nullptr, *par_pos = nullptr, *task_sn = nullptr;
+    int* par_pos = nullptr;
     SnMeta* sn_meta = nullptr;
     ChildRec* child_rec = nullptr;
     double *Cx = nullptr, *cvec = nullptr;
@@ -165,8 +165,8 @@ FactorView make_factor_view(const DeviceState& d, int = 0) {
 TreeView make_tree_view(const DeviceState& d) {
     TreeView T;
     T.F = make_factor_view(d, 0);
-    T.meta = d.sn_meta; T.crec = d.child_rec; T.child_ptr = d.child_ptr; T.par_pos = d.par_pos;
-    T.task_sn = d.task_sn; T.Cx = d.Cx; T.cx_stride = d.cx_stride; T.cvec = d.cvec; T.cv_stride = d.cv_stride;
+    T.meta = d.sn_meta; T.crec = d.child_rec; T.par_pos = d.par_pos;
+    T.Cx = d.Cx; T.cx_stride = d.cx_stride; T.cvec = d.cvec; T.cv_stride = d.cv_stride;
     T.xw = d.xw; T.xw_stride = d.N; T.bar = d.bar; T.B = d.B; T.tickets = nullptr; T.phase_cls = d.phase_cls;
     for (int c = 0; c < 4; ++c) { T.slice[c] = d.sym->tree_slice[c]; T.cap[c] = d.sym->tree_cap[c]; T.maxh[c] = d.sym->tree_maxh[c]; }
     T.maxw = d.tree_maxw;
@@ -431,17 +431,22 @@ int32_t device_create(madipm_handle* h) {
     UP(int64_t, row_colbase, s.row_colbase); UP(int64_t, row_relbase, s.row_relbase); UP(int, rel, s.rel);
     UP(int, perm, s.perm); UP(int, iperm, s.iperm);
     UP(int, big_sn, s.big_sn);
-    UP(int, child_ptr, s.child_ptr); UP(int, par_pos, s.par_pos); UP(int, task_sn, s.task_sn);
+    UP(int, par_pos, s.par_pos);
     {
-        std::vector<SnMeta> meta(std::max(1, s.nsuper));
+        std::vector<SnMeta> meta(std::max<size_t>(1, s.task_sn.size()));      // in task order
         std::vector<ChildRec> crec(std::max<size_t>(1, s.child_idx.size()));
         std::memset(meta.data(), 0, meta.size() * sizeof(SnMeta));
         std::memset(crec.data(), 0, crec.size() * sizeof(ChildRec));
-        for (int sn = 0; sn < s.nsuper; ++sn) {
-            SnMeta& m = meta[sn];
+        for (size_t q = 0; q < s.task_sn.size(); ++q) {
+            const int sn = s.task_sn[q];
+            SnMeta& m = meta[q];
             m.xoff = s.sn_xoff[sn]; m.coff = s.sn_coff[sn]; m.rowptr = static_cast<int32_t>(s.sn_rowptr[sn]);
             m.fc = s.sn_first[sn]; m.h = static_cast<int32_t>(s.sn_rowptr[sn + 1] - s.sn_rowptr[sn]);
-            m.w = static_cast<uint16_t>(s.sn_first[sn + 1] - s.sn_first[sn]); m.kind = s.sn_kind[sn];
+            m.w = s.sn_first[sn + 1] - s.sn_first[sn]; m.kind = s.sn_kind[sn]; m.sn = sn;
+            m.c0 = s.child_ptr[sn]; m.c1 = s.child_ptr[sn + 1];
+        }
+        for (int sn = 0; sn < s.nsuper; ++sn) {
+            const int wp = s.sn_first[sn + 1] - s.sn_first[sn];
             for (int q = s.child_ptr[sn]; q < s.child_ptr[sn + 1]; ++q) {
                 const int c = s.child_idx[q];
                 const int wc = s.sn_first[c + 1] - s.sn_first[c];
@@ -451,7 +456,7 @@ int32_t device_create(madipm_handle* h) {
                 r.nb = static_cast<int32_t>(s.sn_rowptr[c + 1] - s.sn_rowptr[c]) - wc;
                 r.pull = s.sn_kind[c] == 0;
                 r.nbp = 0;
-                while (r.nbp < r.nb && s.par_pos[r.below + r.nbp] < m.w) ++r.nbp;
+                while (r.nbp < r.nb && s.par_pos[r.below + r.nbp] < wp) ++r.nbp;
             }
         }
         if (s.max_w > 65535) { h->error = "max_width too large"; return MADIPM_BAD_ARGUMENT; }

@@ -38,17 +38,18 @@ constexpr int kTreeWarps = kTreeThreads / 32;
 
 constexpr int kChildChunk = 16;  // child records staged per pass
 
-// Everything a task needs to know about its supernode, in one 32-byte record (one memory round trip
-// instead of a chain of dependent index loads: the tasks are latency-bound, not bandwidth-bound).
+// Everything a task needs to know about its supernode, in one 48-byte record stored in TASK order (one memory round
+// trip instead of a chain of dependent index loads: the tasks are latency-bound, not bandwidth-bound).
 struct __align__(16) SnMeta {
     int64_t xoff;      // panel offset in Lx
     int64_t coff;      // contribution-block offset in Cx
     int32_t rowptr;    // offset of the row list in sn_rows / par_pos / cvec
     int32_t fc;        // first column
     int32_t h;         // rows of the panel
-    uint16_t w;        // columns of the panel
-    uint8_t kind;      // 0 small (parent pulls), 1 small under a big parent, 2 big
-    uint8_t pad;
+    int32_t w;         // columns of the panel
+    int32_t c0, c1;    // its child records are crec[c0 .. c1)
+    int32_t sn;        // supernode number
+    int32_t kind;      // 0 small (parent pulls), 1 small under a big parent
 };
 // One (parent, child) edge, stored in child_ptr order.
 struct __align__(16) ChildRec {
@@ -62,11 +63,9 @@ struct __align__(16) ChildRec {
 
 struct TreeView {
     FactorView F;
-    const SnMeta* meta;          // [nsuper]
+    const SnMeta* meta;          // [number of tasks], in task order
     const ChildRec* crec;        // [nsuper - #roots], grouped by parent
-    const int* child_ptr;        // [nsuper+1] into crec
     const int* par_pos;          // indexed like sn_rows
-    const int* task_sn;
     double* Cx;                  // [batch][cx_stride] contribution blocks
     int64_t cx_stride;
     double* cvec;                // [batch][cv_stride] forward-sweep contribution vectors, indexed like sn_rows
@@ -101,11 +100,11 @@ __device__ __forceinline__ void gsync() {
 __device__ __forceinline__ int packed_col(int b, int nb) { return b * nb - ((b * (b + 1)) >> 1); }
 
 template <class T>
-__device__ __forceinline__ T ldg32(const T* p) {          // 32-byte record through the read-only path (two 16-byte loads)
-    static_assert(sizeof(T) == 32, "record size");
-    union { int4 v[2]; T t; } u;
-    u.v[0] = __ldg(reinterpret_cast<const int4*>(p));
-    u.v[1] = __ldg(reinterpret_cast<const int4*>(p) + 1);
+__device__ __forceinline__ T ldg_rec(const T* p) {        // 32- or 48-byte record through the read-only path (16-byte loads)
+    static_assert(sizeof(T) % 16 == 0 && sizeof(T) <= 48, "record size");
+    union { int4 v[sizeof(T) / 16]; T t; } u;
+#pragma unroll
+    for (int k = 0; k < static_cast<int>(sizeof(T) / 16); ++k) u.v[k] = __ldg(reinterpret_cast<const int4*>(p) + k);
     return u.t;
 }
 
@@ -114,7 +113,7 @@ template <int G>
 __device__ __forceinline__ int stage_children(const TreeView& T, ChildRec* cs, int c0, int c1, int base, int t) {
     const int n = min(kChildChunk, c1 - c0 - base);
     if (base > 0) gsync<G>();                              // everyone is done with the previous chunk
-    if (t < n) cs[t] = ldg32(T.crec + c0 + base + t);
+    if (t < n) cs[t] = ldg_rec(T.crec + c0 + base + t);
     gsync<G>();
     return n;
 }
@@ -241,13 +240,13 @@ __device__ __forceinline__ void dense_ldl(double* Ps, int h, int w, int* fail, i
 // ---- numeric factorisation of one small supernode ------------------------------------------------------
 // shared: [cap doubles panel][maxh doubles (unused by the blocked LDL')][maxw doubles D][kChildChunk child records]
 template <int G>
-__device__ __forceinline__ void tree_factor_task(const TreeView& T, int s, const SnMeta& m, int inst, double* sm, int cap, int maxh) {
+__device__ __forceinline__ void tree_factor_task(const TreeView& T, const SnMeta& m, int inst, double* sm, int cap, int maxh) {
     const FactorView& F = T.F;
     constexpr int NW = G / 32;
     const int t = threadIdx.x % G;
     const int lane = t & 31;
     const int gw = t >> 5;
-    const int c0 = __ldg(T.child_ptr + s), c1 = __ldg(T.child_ptr + s + 1);
+    const int c0 = m.c0, c1 = m.c1;
     const int w = m.w, h = m.h, nb = h - w;
     double* Lx = F.Lx + inst * F.lx_stride;
     double* P = Lx + m.xoff;
@@ -260,7 +259,7 @@ __device__ __forceinline__ void tree_factor_task(const TreeView& T, int s, const
     const int nchunk = (np + 1) >> 1;
 #ifdef MADIPM_TREE_TIMING
     long long tt[10];
-#define TT(k) do { if (s == T.dbg_sn && t == 0) tt[k] = clock64(); } while (0)
+#define TT(k) do { if (m.sn == T.dbg_sn && t == 0) tt[k] = clock64(); } while (0)
 #else
 #define TT(k)
 #endif
@@ -369,8 +368,8 @@ __device__ __forceinline__ void tree_factor_task(const TreeView& T, int s, const
     }
     TT(5);
 #ifdef MADIPM_TREE_TIMING
-    if (s == T.dbg_sn && t == 0)
-        printf("sn %d G %d w %d h %d children %d | stage+extend %lld ldl %lld store %lld schur %lld pass %lld cycles\n", s, G, w, h,
+    if (m.sn == T.dbg_sn && t == 0)
+        printf("sn %d G %d w %d h %d children %d | stage+extend %lld ldl %lld store %lld schur %lld pass %lld cycles\n", m.sn, G, w, h,
                c1 - c0, tt[1] - tt[0], tt[2] - tt[1], tt[3] - tt[2], tt[4] - tt[3], tt[5] - tt[4]);
 #endif
     // 5. under a big parent: scatter C into the ancestors' panels (the big kernels read panels only)
@@ -391,12 +390,12 @@ __device__ __forceinline__ void tree_factor_task(const TreeView& T, int s, const
 // ---- forward sweep: y = L^-1 b, xw <- D^-1 y ---------------------------------------------------------------
 // shared: [cap doubles panel][maxh doubles pass-through][maxw doubles y][kChildChunk child records]
 template <int G>
-__device__ __forceinline__ void tree_forward_task(const TreeView& T, int s, const SnMeta& m, int inst, double* sm, int cap, int maxh) {
+__device__ __forceinline__ void tree_forward_task(const TreeView& T, const SnMeta& m, int inst, double* sm, int cap, int maxh) {
     const FactorView& F = T.F;
     const int t = threadIdx.x % G;
     const int lane = t & 31;
     const int gw = t >> 5;
-    const int c0 = __ldg(T.child_ptr + s), c1 = __ldg(T.child_ptr + s + 1);
+    const int c0 = m.c0, c1 = m.c1;
     const int w = m.w, h = m.h, nb = h - w, fc = m.fc;
     const double* P = F.Lx + inst * F.lx_stride + m.xoff;
     double* xw = T.xw + inst * T.xw_stride;
@@ -452,7 +451,7 @@ __device__ __forceinline__ void tree_forward_task(const TreeView& T, int s, cons
 // ---- backward sweep: x = L^-T xw -----------------------------------------------------------------------------
 // shared: [cap doubles panel][maxh doubles x at the below rows][maxw doubles block solution]
 template <int G>
-__device__ __forceinline__ void tree_backward_task(const TreeView& T, int s, const SnMeta& m, int inst, double* sm, int cap, int maxh) {
+__device__ __forceinline__ void tree_backward_task(const TreeView& T, const SnMeta& m, int inst, double* sm, int cap, int maxh) {
     const FactorView& F = T.F;
     constexpr int NW = G / 32;
     const int t = threadIdx.x % G;
@@ -508,10 +507,10 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
 }
 
 template <int OP, int G>
-__device__ __forceinline__ void tree_task(const TreeView& T, int s, const SnMeta& m, int inst, double* sm, int cap, int maxh) {
-    if (OP == 0) tree_factor_task<G>(T, s, m, inst, sm, cap, maxh);
-    else if (OP == 1) tree_forward_task<G>(T, s, m, inst, sm, cap, maxh);
-    else tree_backward_task<G>(T, s, m, inst, sm, cap, maxh);
+__device__ __forceinline__ void tree_task(const TreeView& T, const SnMeta& m, int inst, double* sm, int cap, int maxh) {
+    if (OP == 0) tree_factor_task<G>(T, m, inst, sm, cap, maxh);
+    else if (OP == 1) tree_forward_task<G>(T, m, inst, sm, cap, maxh);
+    else tree_backward_task<G>(T, m, inst, sm, cap, maxh);
 }
 
 // one group of G threads drains the tasks of its class in phase ph (ticket counter), then returns
@@ -531,8 +530,7 @@ __device__ __forceinline__ void run_class(const TreeView& T, double* smem, int p
         const int64_t q = *slot;
         if (q >= total) break;
         const int inst = static_cast<int>(q / n);
-        const int s = __ldg(T.task_sn + first + static_cast<int>(q - static_cast<int64_t>(inst) * n));
-        tree_task<OP, G>(T, s, ldg32(T.meta + s), inst, sm, T.cap[CLS], T.maxh[CLS]);
+        tree_task<OP, G>(T, ldg_rec(T.meta + first + static_cast<int>(q - static_cast<int64_t>(inst) * n)), inst, sm, T.cap[CLS], T.maxh[CLS]);
     }
 }
 
@@ -566,8 +564,8 @@ k_tree_top(TreeView T, int ph_begin, int ph_end, int step, unsigned bar_base) {
         const int64_t total = static_cast<int64_t>(n) * T.B;
         for (int64_t q = blockIdx.x; q < total; q += gridDim.x) {
             const int inst = static_cast<int>(q / n);
-            const int s = __ldg(T.task_sn + first + static_cast<int>(q - static_cast<int64_t>(inst) * n));
-            tree_task<OP, kTopThreads>(T, s, ldg32(T.meta + s), inst, smem, T.cap[0], T.maxh[0]);
+            tree_task<OP, kTopThreads>(T, ldg_rec(T.meta + first + static_cast<int>(q - static_cast<int64_t>(inst) * n)), inst, smem,
+                                       T.cap[0], T.maxh[0]);
         }
         if (ph + step != ph_end) grid_barrier(T.bar, target);
     }
