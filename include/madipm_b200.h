@@ -129,7 +129,8 @@ enum {
     MADIPM_SYM_SUPER_COFF = 24,   /* nsuper + 1: offsets of the packed contribution blocks */
     MADIPM_SYM_TASK_SN = 25,      /* small supernodes in schedule order */
     MADIPM_SYM_PHASE_PTR = 26,    /* n_levels + 1 into TASK_SN */
-    MADIPM_SYM_PHASE_NBLOCK = 27  /* n_levels: leading tasks of a phase that take a whole thread block */
+    MADIPM_SYM_PHASE_NBLOCK = 27, /* n_levels: tasks of a phase that are not warp tasks */
+    MADIPM_SYM_PHASE_CLS = 28     /* n_levels x 5: first task of class 256 / 128 / 64 / 32 (threads per task), end of the phase */
 };
 int32_t madipm_get_symbolic(const madipm_handle* h, int32_t which, int64_t* out, int64_t cap, int64_t* len);
 

@@ -192,6 +192,7 @@ int32_t madipm_get_symbolic(const madipm_handle* h, int32_t which, int64_t* out,
         case MADIPM_SYM_TASK_SN: return copy_out(s.task_sn, out, cap, len);
         case MADIPM_SYM_PHASE_PTR: return copy_out(s.phase_ptr, out, cap, len);
         case MADIPM_SYM_PHASE_NBLOCK: return copy_out(s.phase_nblock, out, cap, len);
+        case MADIPM_SYM_PHASE_CLS: return copy_out(s.phase_cls, out, cap, len);
         default: return MADIPM_BAD_ARGUMENT;
     }
 }

@@ -256,8 +256,7 @@ class MPCSolver:
             lvar = qp.lvar - np.maximum(1.0, np.abs(qp.lvar)) * tol
             uvar = qp.uvar + np.maximum(1.0, np.abs(qp.uvar)) * tol
             x0 = _push_inside(np.asarray(qp.x0, dtype=float), lvar, uvar, opt.bound_push, opt.bound_fac)
-            cons0 = np.zeros(m)
-            np.add.at(cons0, qp.A_rows, qp.A_vals * x0[qp.A_cols])
+            cons0 = np.bincount(qp.A_rows, weights=qp.A_vals * x0[qp.A_cols], minlength=m)[:m] if m else np.zeros(0)
             ls = qp.lcon[ic.ind_ineq] - np.maximum(1.0, np.abs(qp.lcon[ic.ind_ineq])) * tol
             us = qp.ucon[ic.ind_ineq] + np.maximum(1.0, np.abs(qp.ucon[ic.ind_ineq])) * tol
             s0 = _push_inside(cons0[ic.ind_ineq], ls, us, opt.bound_push, opt.bound_fac)
@@ -267,12 +266,15 @@ class MPCSolver:
             # MadNLP.set_scaling!(..., 100.0)  (solver.jl:148-159)
             if opt.scaling:
                 rowmax = np.ones(m)
-                np.maximum.at(rowmax, qp.A_rows, np.abs(qp.A_vals))
+                if len(qp.A_rows):                       # max over each row (pattern-only sort, cached per instance)
+                    order, starts, present = self._row_groups(b, qp.A_rows)
+                    rowmax[present] = np.maximum(1.0, np.maximum.reduceat(np.abs(qp.A_vals)[order], starts))
                 self.con_scale[b] = np.minimum(1.0, 100.0 / rowmax)
                 g0 = qp.c.astype(float).copy()
-                np.add.at(g0, qp.H_rows, qp.H_vals * x0[qp.H_cols])
-                off = qp.H_rows != qp.H_cols
-                np.add.at(g0, qp.H_cols[off], qp.H_vals[off] * x0[qp.H_rows[off]])
+                if len(qp.H_rows):
+                    off = qp.H_rows != qp.H_cols
+                    g0 += np.bincount(qp.H_rows, weights=qp.H_vals * x0[qp.H_cols], minlength=nx)[:nx]
+                    g0 += np.bincount(qp.H_cols[off], weights=qp.H_vals[off] * x0[qp.H_rows[off]], minlength=nx)[:nx]
                 gmax = float(np.max(np.abs(g0))) if nx else 0.0
                 self.obj_scale[b] = min(1.0, 100.0 / gmax) if gmax > 0 else 1.0
                 cs = self.con_scale[b]
@@ -285,6 +287,16 @@ class MPCSolver:
         self._c0 = np.array([qp.c0 for qp in self.qps]) * self.obj_scale
         self._host = dict(X=X, XL=XL, XU=XU, Y=Y, RHS=RHS, COST=COST, HV=HV, JV=JV)
         self.norm_b = np.max(np.abs(RHS), axis=1) if m else np.zeros(B)     # solver.jl:173
+
+    def _row_groups(self, b, rows):
+        """Stable grouping of a COO row-index array (depends on the pattern only; kept across solves)."""
+        cache = self.__dict__.setdefault("_row_group_cache", {})
+        if b not in cache:
+            order = np.argsort(rows, kind="stable")
+            rs = rows[order]
+            starts = np.flatnonzero(np.diff(rs, prepend=-1))
+            cache[b] = (order, starts, rs[starts])
+        return cache[b]
 
     def upload(self):
         """Host -> device copy of one solve's inputs (iterate, bounds, rhs, cost, Jacobian/Hessian values)."""

@@ -139,3 +139,25 @@ def test_batch_matches_single_solves():
         assert abs(int(stb.iter[i]) - ref.k) <= 1
         assert abs(stb.objective[i] - ref.objective) <= 1e-8 * max(1.0, abs(ref.objective))
     sb.close()
+
+
+def test_small_front_factor_is_bit_reproducible():
+    """The height-scheduled factorisation has no atomics and a fixed summation order (kernels_tree.cuh): two
+    factorisations + solves of the same KKT values give bit-identical directions, run to run."""
+    qp = P.banded_qp(n=20000, m=10000)
+    s = MPCSolver(qp, regularization=FixedRegularization(1e-8, -1e-8))
+    assert (s.h.symbolic("SUPER_KIND") == 0).all()
+    used = np.diff(s.h.symbolic("PHASE_CLS").reshape(-1, 5), axis=1).sum(axis=0)
+    assert (used > 0).sum() >= 3, used                      # several task classes (thread-group sizes) are exercised
+    s.prepare_host(); s.upload(); s.start(); s._update_regularization()
+    h = s.h
+    h.set_aug_diagonal_reg(s.del_w, s.del_c); h.build_kkt()
+    outs = []
+    for _ in range(3):
+        assert h.factorize() == 0
+        h.set_predictive_rhs()
+        rc, norms = h.solve_system("D", "P")
+        assert rc == 0 and norms[0, 0] <= 1e-9 * max(1.0, norms[0, 1])
+        outs.append(h.vec_get("D").copy())
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    s.close()

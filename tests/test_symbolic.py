@@ -181,9 +181,16 @@ def test_schedule_covers_every_supernode_once():
             assert level[p] > level[s]                        # a parent is processed in a later phase
     # every small supernode is exactly one task, in the phase of its height
     assert sorted(task.tolist()) == np.flatnonzero(kind != 2).tolist()
+    cls = h.symbolic("PHASE_CLS").reshape(-1, 5)
+    first, rp = h.symbolic("SUPER_FIRST"), h.symbolic("SUPER_ROWPTR")
+    panel = np.diff(first) * np.diff(rp)
     for k in range(len(pptr) - 1):
         assert (level[task[pptr[k]:pptr[k + 1]]] == k).all()
         assert 0 <= nblk[k] <= pptr[k + 1] - pptr[k]
+        assert cls[k, 0] == pptr[k] and cls[k, 4] == pptr[k + 1] and (np.diff(cls[k]) >= 0).all()
+        assert cls[k, 3] - cls[k, 0] == nblk[k]
+    used = [int((cls[:, c + 1] - cls[:, c]).sum()) for c in range(4)]
+    assert sum(used) == len(task) and used[3] > 0 and sum(used[:3]) > 0      # warp tasks and multi-warp tasks both occur
 
 
 def _multifrontal_emulation(h, K):
