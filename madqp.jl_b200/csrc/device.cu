@@ -12,9 +12,9 @@
 #include <vector>
 
 #include "handle.hpp"
-#include "kernels_big.cuh"
 #include "kernels_factor.cuh"
 #include "kernels_tree.cuh"
+#include "kernels_big.cuh"
 #include "kernels_vec.cuh"
 
 namespace madipm {
@@ -48,7 +48,9 @@ struct DeviceState {
     int64_t cx_stride = 0, cv_stride = 0;
     unsigned* bar = nullptr;
     std::vector<int> big_ptr;          // big (multi-block) supernodes, per height
-    std::vector<int> big_rowblocks, big_rowblocks512, big_tiles;   // per height: grid sizes (max over its big supernodes)
+    std::vector<int> big_rowblocks, big_rowblocks512, big_tiles, big_panelblocks;   // per height: grid sizes (max over its big supernodes)
+    bool big_use_panel = false;
+    size_t smem_big_panel = 0;
     int* big_sn = nullptr;
     double *big_ybuf = nullptr, *big_tbuf = nullptr, *big_zbuf = nullptr;
     int big_zstride = 0;
@@ -387,7 +389,7 @@ int32_t device_create(madipm_handle* h) {
     // grid sizes of the multi-block kernels, per height (max over the big supernodes of that height)
     d->big_ptr.assign(s.big_ptr.begin(), s.big_ptr.end());
     for (int l = 0; l < s.n_levels; ++l) {
-        int rb = 0, rb512 = 0, tiles = 0;
+        int rb = 0, rb512 = 0, tiles = 0, pb = 0;
         for (int q = s.big_ptr[l]; q < s.big_ptr[l + 1]; ++q) {
             const int sn = s.big_sn[q];
             const int64_t hs = s.sn_rowptr[sn + 1] - s.sn_rowptr[sn], ws = s.sn_first[sn + 1] - s.sn_first[sn];
@@ -395,7 +397,9 @@ int32_t device_create(madipm_handle* h) {
             rb = std::max<int>(rb, static_cast<int>(nt));
             rb512 = std::max<int>(rb512, static_cast<int>((nb + 511) / 512));
             tiles = std::max<int>(tiles, static_cast<int>(nt * (nt + 1) / 2));
+            if (ws < kPanelThreads) pb = std::max<int>(pb, static_cast<int>((nb + (kPanelThreads - ws) - 1) / (kPanelThreads - ws)));
         }
+        d->big_panelblocks.push_back(pb);
         d->big_rowblocks.push_back(rb); d->big_rowblocks512.push_back(rb512); d->big_tiles.push_back(tiles);
         d->big_max_per_level = std::max(d->big_max_per_level, s.big_ptr[l + 1] - s.big_ptr[l]);
     }
@@ -557,12 +561,16 @@ int32_t device_create(madipm_handle* h) {
         const size_t mw = static_cast<size_t>(s.max_w);
         d->smem_big_diag = (2 * mw * mw + mw) * sizeof(double);
         d->smem_big_trsm = 2 * mw * kBigTileLd * sizeof(double);
-        d->smem_big_update = std::max<size_t>(2 * mw, kBigTile) * kBigTileLd * sizeof(double) + 2 * kBigTile * sizeof(int64_t);
+        d->smem_big_update = (2 * kBigStage + ((mw + 1) & ~size_t(1))) * sizeof(double) + 2 * kBigTile * sizeof(int64_t);
         if (!s.big_sn.empty()) {
             if (d->smem_big_trsm > 220 * 1024) { h->error = "max_width too large for the big-front kernels"; return MADIPM_BAD_ARGUMENT; }
             CUDA_OK(h, cudaFuncSetAttribute(k_big_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_big_diag));
             CUDA_OK(h, cudaFuncSetAttribute(k_big_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_big_trsm));
             CUDA_OK(h, cudaFuncSetAttribute(k_big_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_big_update));
+            d->big_use_panel = s.max_w <= 64;                 // one-launch panel factorisation (k_big_panel)
+            d->smem_big_panel = static_cast<size_t>(kPanelThreads) * mw * sizeof(double) + 64;
+            if (d->big_use_panel)
+                CUDA_OK(h, cudaFuncSetAttribute(k_big_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_big_panel));
             const size_t nbuf = static_cast<size_t>(B) * d->big_max_per_level * 256;
             if ((rc = dev_alloc(h, &d->big_ybuf, nbuf))) return rc;
             if ((rc = dev_alloc(h, &d->big_tbuf, nbuf))) return rc;
@@ -822,11 +830,17 @@ int32_t madipm_factorize(madipm_handle* h, int32_t* n_failed) {
                 const FactorView F = make_factor_view(*d, 0);
                 const int* list = d->big_sn + d->big_ptr[l];
                 const int exclusive = nbig == 1 ? 1 : 0;     // the only writer of its targets during these launches
-                LAUNCH(h, k_big_diag, dim3(nbig, B), 256, d->smem_big_diag, F, list, d->big_zbuf, d->big_zstride);
-                if (d->big_rowblocks[l] > 0) {
-                    LAUNCH(h, k_big_trsm, dim3(d->big_rowblocks[l], nbig, B), 128, d->smem_big_trsm, F, list, d->big_zbuf, d->big_zstride);
-                    LAUNCH(h, k_big_update, dim3(d->big_tiles[l], nbig, B), 128, d->smem_big_update, F, list, exclusive);
+                if (d->big_use_panel) {
+                    LAUNCH(h, k_big_panel, dim3(std::max(1, d->big_panelblocks[l]), nbig, B), kPanelThreads, d->smem_big_panel, F, list,
+                           d->big_zbuf, d->big_zstride);
+                    LAUNCH(h, k_big_store_diag, dim3(nbig, B), 256, 0, F, list, d->big_zbuf, d->big_zstride);
+                } else {
+                    LAUNCH(h, k_big_diag, dim3(nbig, B), 256, d->smem_big_diag, F, list, d->big_zbuf, d->big_zstride);
+                    if (d->big_rowblocks[l] > 0)
+                        LAUNCH(h, k_big_trsm, dim3(d->big_rowblocks[l], nbig, B), 128, d->smem_big_trsm, F, list, d->big_zbuf, d->big_zstride);
                 }
+                if (d->big_rowblocks[l] > 0)
+                    LAUNCH(h, k_big_update, dim3(d->big_tiles[l], nbig, B), 128, d->smem_big_update, F, list, exclusive);
             }
         }
         if (light) cudaEventRecord(d->ev1, d->stream);

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include "kernels_factor.cuh"
+#include "kernels_tree.cuh"
 
 namespace madipm {
 
@@ -150,11 +151,80 @@ k_big_trsm(FactorView F, const int* __restrict__ big_sn, const double* __restric
     }
 }
 
+// ---- panel factorisation of a big supernode, one launch (w <= 64) ------------------------------------------
+// grid.x = block of R = 128 - w rows below the diagonal block, grid.y = big supernode, grid.z = instance; 128 threads.
+// Every block stages the w x w diagonal block AND its own R rows as one (w + R) x w panel in shared memory and runs the
+// same left-looking dense LDL' as the small path (dense_ldl, kernels_tree.cuh): the diagonal block is factorised
+// redundantly by every block (parallel, so it costs no time) and each thread solves its own row against it -- no
+// explicit inverse, no second launch.  The rows below are written back in place; the factored diagonal block goes to
+// zbuf (other blocks may still be reading the unfactored one) and k_big_store_diag copies it into the panel afterwards.
+constexpr int kPanelThreads = 128;
+__global__ void __launch_bounds__(kPanelThreads)
+k_big_panel(FactorView F, const int* __restrict__ big_sn, double* __restrict__ zbuf, int zstride) {
+    extern __shared__ double2 big_smem2[];
+    double* Ps = reinterpret_cast<double*>(big_smem2);
+    const int inst = blockIdx.z;
+    const int s = big_sn[blockIdx.y];
+    double* Lx = F.Lx + inst * F.lx_stride;
+    const int t = threadIdx.x;
+    const int w = F.sn_first[s + 1] - F.sn_first[s];
+    const int h = static_cast<int>(F.sn_rowptr[s + 1] - F.sn_rowptr[s]);
+    const int R = kPanelThreads - w;
+    const int r0 = w + blockIdx.x * R;
+    if (r0 >= h && blockIdx.x > 0) return;
+    const int nr = max(0, min(R, h - r0));
+    const int hp = w + nr;                                 // rows of the staged panel
+    double* P = Lx + F.sn_xoff[s];
+    const int64_t ld = h;
+    for (int idx = t; idx < hp * w; idx += kPanelThreads) {
+        const int i = idx % hp, j = idx / hp;
+        Ps[idx] = ldcg(&P[(i < w ? i : r0 + i - w) + j * ld]);
+    }
+    __syncthreads();
+    dense_ldl<kPanelThreads>(Ps, hp, w, F.fail + inst, t);
+    __syncthreads();
+    for (int idx = t; idx < nr * w; idx += kPanelThreads) {
+        const int i = idx % nr, j = idx / nr;
+        P[r0 + i + j * ld] = Ps[w + i + j * hp];
+    }
+    if (blockIdx.x == 0) {
+        double* Z = zbuf + (static_cast<int64_t>(inst) * gridDim.y + blockIdx.y) * zstride;
+        for (int idx = t; idx < w * w; idx += kPanelThreads) {
+            const int i = idx % w, j = idx / w;
+            Z[idx] = Ps[i + j * hp];
+        }
+    }
+}
+
+__global__ void k_big_store_diag(FactorView F, const int* __restrict__ big_sn, const double* __restrict__ zbuf, int zstride) {
+    const int inst = blockIdx.y;
+    const int s = big_sn[blockIdx.x];
+    const int w = F.sn_first[s + 1] - F.sn_first[s];
+    const int64_t ld = F.sn_rowptr[s + 1] - F.sn_rowptr[s];
+    double* P = F.Lx + inst * F.lx_stride + F.sn_xoff[s];
+    const double* Z = zbuf + (static_cast<int64_t>(inst) * gridDim.x + blockIdx.x) * zstride;
+    for (int idx = threadIdx.x; idx < w * w; idx += blockDim.x) {
+        const int i = idx % w, j = idx / w;
+        if (i >= j) P[i + j * ld] = Z[idx];
+    }
+}
+
 // ---- Schur complement on the FP64 tensor cores ----------------------------------------------------
 // grid.x = linear index of a lower-triangular 64 x 64 tile (ti >= tj) of the (h-w) x (h-w) update,
 // grid.y = big supernode of the level, grid.z = instance.  128 threads = 4 warps, each 32 x 32.
-// shared: [w * 68 doubles A (rows of tile ti)][w * 68 doubles B = D L21' (rows of tile tj)]
-//         [64 int64 colbase][64 int64 relbase]
+// The operands stream through shared memory in chunks of 16 columns of the panel (k), double-buffered with
+// cp.async, so a block needs 35 KB instead of the whole K extent (5 blocks per SM instead of 3) and its loads
+// overlap its DMMAs.  B = D L21' is formed on the fly (D in shared memory).
+// shared: 2 stages x [16 x 68 doubles A][16 x 68 doubles B] (reused by the 64 x 68 epilogue tile)
+//         [w doubles D][64 int64 colbase][64 int64 relbase]
+constexpr int kBigKc = 16;
+constexpr int kBigStage = 2 * kBigKc * kBigTileLd;        // doubles per stage (A + B)
+
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+
 __global__ void __launch_bounds__(128)
 k_big_update(FactorView F, const int* __restrict__ big_sn, int exclusive) {
     const int inst = blockIdx.z;
@@ -175,23 +245,34 @@ k_big_update(FactorView F, const int* __restrict__ big_sn, int exclusive) {
     const int64_t ld = h;
     const double* P = Lx + F.sn_xoff[s];
     const int* rows = F.sn_rows + F.sn_rowptr[s];
-    double* As = madipm_smem;
-    double* Bs = As + w * kBigTileLd;
-    int64_t* colb = reinterpret_cast<int64_t*>(As + max(2 * w, kBigTile) * kBigTileLd);   // past the operands AND the epilogue tile
+    double* stage = madipm_smem;
+    double* Ds = stage + 2 * kBigStage;
+    int64_t* colb = reinterpret_cast<int64_t*>(Ds + ((w + 1) & ~1));
     int64_t* relb = colb + kBigTile;
     const int i0 = w + ti * kBigTile, j0 = w + tj * kBigTile;
     const int ni = min(kBigTile, h - i0), nj = min(kBigTile, h - j0);
-    for (int idx = tid; idx < w * kBigTile; idx += 128) {
-        const int r = idx % kBigTile, k = idx / kBigTile;
-        As[k * kBigTileLd + r] = (r < ni) ? ldcg(&P[i0 + r + k * ld]) : 0.0;
-        Bs[k * kBigTileLd + r] = (r < nj) ? ldcg(&P[j0 + r + k * ld]) * P[k + k * ld] : 0.0;
-    }
+    auto issue = [&](int c) {                              // chunk c -> stage c & 1
+        double* As = stage + (c & 1) * kBigStage;
+        double* Bs = As + kBigKc * kBigTileLd;
+        const int k0 = c * kBigKc;
+        for (int idx = tid; idx < kBigKc * kBigTile; idx += 128) {
+            const int r = idx % kBigTile, k = idx / kBigTile;
+            const bool kin = k0 + k < w;
+            if (kin && r < ni) cp_async8(&As[k * kBigTileLd + r], &P[i0 + r + (k0 + k) * ld]);
+            else As[k * kBigTileLd + r] = 0.0;
+            if (kin && r < nj) cp_async8(&Bs[k * kBigTileLd + r], &P[j0 + r + (k0 + k) * ld]);
+            else Bs[k * kBigTileLd + r] = 0.0;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int nchunk = (w + kBigKc - 1) / kBigKc;
+    issue(0);
     if (tid < kBigTile) {
         const int jj = j0 + tid;
         colb[tid] = (tid < nj) ? F.row_colbase[F.sn_rowptr[s] + jj] : 0;
         relb[tid] = (tid < nj) ? F.row_relbase[F.sn_rowptr[s] + jj] : 0;
     }
-    __syncthreads();
+    for (int k = tid; k < w; k += 128) Ds[k] = ldcg(&P[k + k * ld]);
     const int lane = tid & 31, warp = tid >> 5;
     const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;     // warp's 32 x 32 corner inside the tile
     const int fr = lane >> 2, fk = lane & 3;                   // fragment row / k (A), n / k (B)
@@ -200,18 +281,31 @@ k_big_update(FactorView F, const int* __restrict__ big_sn, int exclusive) {
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-    for (int k0 = 0; k0 < w; k0 += 4) {
-        double af[4], bf[4];
-        const int kk = k0 + fk;
-        const bool kin = kk < w;
+    for (int c = 0; c < nchunk; ++c) {
+        if (c + 1 < nchunk) {
+            issue(c + 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const double* As = stage + (c & 1) * kBigStage;
+        const double* Bs = As + kBigKc * kBigTileLd;
 #pragma unroll
-        for (int a = 0; a < 4; ++a) af[a] = kin ? As[kk * kBigTileLd + wm + a * 8 + fr] : 0.0;
+        for (int k0 = 0; k0 < kBigKc; k0 += 4) {
+            double af[4], bf[4];
+            const int kk = k0 + fk;
+            const double dk = Ds[min(c * kBigKc + kk, w - 1)];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) bf[b] = kin ? Bs[kk * kBigTileLd + wn + b * 8 + fr] : 0.0;
+            for (int a = 0; a < 4; ++a) af[a] = As[kk * kBigTileLd + wm + a * 8 + fr];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+            for (int b = 0; b < 4; ++b) bf[b] = Bs[kk * kBigTileLd + wn + b * 8 + fr] * dk;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        }
+        __syncthreads();                                       // this stage is free for chunk c + 2
     }
     // epilogue: transpose the tile through shared memory (reusing the operand space) so that consecutive
     // lanes own consecutive rows of one target column: coalesced RMW / RED instead of 8-row fragments.
