@@ -52,7 +52,8 @@ struct DeviceState {
     bool big_use_panel = false;
     size_t smem_big_panel = 0;
     int* big_sn = nullptr;
-    double *big_ybuf = nullptr, *big_tbuf = nullptr, *big_zbuf = nullptr;
+    double *big_tbuf = nullptr, *big_zbuf = nullptr;
+    int* big_done = nullptr;           // per (instance, big supernode of a height): blocks finished (self-resetting)
     int big_zstride = 0;
     int big_max_per_level = 0;
     size_t smem_big_diag = 0, smem_big_trsm = 0, smem_big_update = 0;
@@ -327,9 +328,8 @@ int32_t tri_solve(madipm_handle* h) {
         const int nbig = d->big_ptr[l + 1] - d->big_ptr[l];
         if (nbig > 0) {
             const int* list = d->big_sn + d->big_ptr[l];
-            LAUNCH(h, k_big_fwd_diag, dim3(nbig, d->B), 256, d->smem_tri, F, list, d->big_ybuf, 256, d->xw, N, d->tri_cap);
-            if (d->big_rowblocks[l] > 0)
-                LAUNCH(h, k_big_fwd_below, dim3((d->big_rowblocks[l] + 1) / 2, nbig, d->B), 128, 0, F, list, d->big_ybuf, 256, d->xw, N);
+            LAUNCH(h, k_big_forward, dim3(std::max(1, d->big_rowblocks[l] / 2 + d->big_rowblocks[l] % 2), nbig, d->B), 128, d->smem_tri, F, list,
+                   d->xw, N, d->tri_cap, d->big_done);
         }
     }
     for (auto it = d->segs.rbegin(); it != d->segs.rend(); ++it) {
@@ -337,9 +337,8 @@ int32_t tri_solve(madipm_handle* h) {
         const int nbig = d->big_ptr[l + 1] - d->big_ptr[l];
         if (nbig > 0) {
             const int* list = d->big_sn + d->big_ptr[l];
-            if (d->big_rowblocks512[l] > 0)
-                LAUNCH(h, k_big_bwd_below, dim3(d->big_rowblocks512[l], nbig, d->B), 256, 0, F, list, d->big_tbuf, 256, d->xw, N);
-            LAUNCH(h, k_big_bwd_diag, dim3(nbig, d->B), 256, d->smem_tri, F, list, d->big_tbuf, 256, d->xw, N, d->tri_cap);
+            LAUNCH(h, k_big_backward, dim3(std::max(1, d->big_rowblocks512[l]), nbig, d->B), 256, d->smem_tri, F, list, d->big_tbuf, 256,
+                   d->xw, N, d->tri_cap, d->big_done);
         }
         if ((rc = launch_tree<2>(h, *it))) return rc;
     }
@@ -572,7 +571,8 @@ int32_t device_create(madipm_handle* h) {
             if (d->big_use_panel)
                 CUDA_OK(h, cudaFuncSetAttribute(k_big_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_big_panel));
             const size_t nbuf = static_cast<size_t>(B) * d->big_max_per_level * 256;
-            if ((rc = dev_alloc(h, &d->big_ybuf, nbuf))) return rc;
+            if ((rc = dev_alloc(h, &d->big_done, static_cast<size_t>(B) * d->big_max_per_level))) return rc;
+            CUDA_OK(h, cudaMemsetAsync(d->big_done, 0, static_cast<size_t>(B) * d->big_max_per_level * sizeof(int), d->stream));
             if ((rc = dev_alloc(h, &d->big_tbuf, nbuf))) return rc;
             if ((rc = dev_alloc(h, &d->big_zbuf, static_cast<size_t>(B) * d->big_max_per_level * mw * mw))) return rc;
             d->big_zstride = static_cast<int>(mw * mw);

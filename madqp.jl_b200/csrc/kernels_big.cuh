@@ -347,123 +347,126 @@ k_big_update(FactorView F, const int* __restrict__ big_sn, int exclusive) {
     }
 }
 
-// ---- multi-block triangular-solve helpers for tall panels ------------------------------------------
-// forward, below rows:  xw[rows[i]] -= sum_j L[i,j] y[j]   (y = xw[fc .. fc+w) already holds the solved block, UNSCALED by D)
-__global__ void k_big_fwd_below(FactorView F, const int* __restrict__ big_sn, const double* __restrict__ ybuf, int ystride,
-                                double* xw, int64_t xw_stride) {
+// ---- triangular solves with a big supernode: one launch per height and sweep ---------------------------------
+// Forward: grid.x = block of 128 rows below the diagonal block (at least one block), grid.y = big supernode,
+// grid.z = instance.  Every block solves the w x w unit-lower triangle redundantly (one warp, a few microseconds: it
+// is the only serial part and doing it in every block saves a launch and a round trip through global memory), then
+// pushes its rows' products into xw with FP64 atomics.  The last block to finish (counter) stores D^-1 y into the
+// supernode's own entries of xw -- not earlier: the other blocks read the right-hand side from there.
+// shared: [tri_cap doubles triangle][256 doubles y]
+__global__ void __launch_bounds__(128)
+k_big_forward(FactorView F, const int* __restrict__ big_sn, double* xw, int64_t xw_stride, int tri_cap, int* __restrict__ done) {
+    double* tri = madipm_smem;
+    double* sy = tri + tri_cap;
+    __shared__ int s_last;
     const int inst = blockIdx.z;
     const int b = blockIdx.y;
     const int s = big_sn[b];
     const double* Lx = F.Lx + inst * F.lx_stride;
     xw += inst * xw_stride;
-    const int w = F.sn_first[s + 1] - F.sn_first[s];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int fc = F.sn_first[s];
+    const int w = F.sn_first[s + 1] - fc;
     const int h = static_cast<int>(F.sn_rowptr[s + 1] - F.sn_rowptr[s]);
     const int64_t ld = h;
     const double* P = Lx + F.sn_xoff[s];
     const int* rows = F.sn_rows + F.sn_rowptr[s];
-    __shared__ double sy[256];
-    const double* y = ybuf + (static_cast<int64_t>(inst) * gridDim.y + b) * ystride;
-    for (int j = threadIdx.x; j < w; j += blockDim.x) sy[j] = y[j];
+    const bool staged = w * w <= tri_cap;
+    for (int j = tid; j < w; j += 128) sy[j] = ldcg(&xw[fc + j]);
+    if (staged)
+        for (int idx = tid; idx < w * w; idx += 128) {
+            const int i = idx % w, j = idx / w;
+            if (i > j) tri[idx] = P[i + j * ld];
+        }
     __syncthreads();
-    const int i = w + blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < 32) {
+        for (int j = 0; j + 1 < w; ++j) {
+            const double yj = sy[j];
+            if (staged) { for (int i = j + 1 + lane; i < w; i += 32) sy[i] -= tri[i + j * w] * yj; }
+            else { for (int i = j + 1 + lane; i < w; i += 32) sy[i] -= P[i + j * ld] * yj; }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    const int i = w + blockIdx.x * 128 + tid;
     if (i < h) {
         double acc = 0.0;
+#pragma unroll 4
         for (int j = 0; j < w; ++j) acc = fma(P[i + j * ld], sy[j], acc);
         atomicAdd(&xw[rows[i]], -acc);
     }
-}
-
-// forward, diagonal block of big supernodes: y = L11^-1 b, ybuf <- y, xw[fc+j] <- y_j / d_j
-__global__ void k_big_fwd_diag(FactorView F, const int* __restrict__ big_sn, double* __restrict__ ybuf, int ystride,
-                               double* xw, int64_t xw_stride, int tri_cap) {
-    double* tri = madipm_smem;
-    double* sy = tri + tri_cap;
-    const int inst = blockIdx.y;
-    const int b = blockIdx.x;
-    const int s = big_sn[b];
-    const double* Lx = F.Lx + inst * F.lx_stride;
-    xw += inst * xw_stride;
-    const int tid = threadIdx.x, T = blockDim.x;
-    const int fc = F.sn_first[s];
-    const int w = F.sn_first[s + 1] - fc;
-    const int64_t ld = F.sn_rowptr[s + 1] - F.sn_rowptr[s];
-    const double* P = Lx + F.sn_xoff[s];
-    for (int j = tid; j < w; j += T) sy[j] = ldcg(&xw[fc + j]);
-    for (int idx = tid; idx < w * w; idx += T) {
-        const int i = idx % w, j = idx / w;
-        if (i > j) tri[idx] = P[i + j * ld];
-    }
-    for (int j = 0; j + 1 < w; ++j) {
-        __syncthreads();
-        const double yj = sy[j];
-        for (int i = j + 1 + tid; i < w; i += T) sy[i] -= tri[i + j * w] * yj;
-    }
+    __threadfence();
     __syncthreads();
-    double* y = ybuf + (static_cast<int64_t>(inst) * gridDim.x + b) * ystride;
-    for (int j = tid; j < w; j += T) {
-        y[j] = sy[j];
-        xw[fc + j] = sy[j] / P[j + j * ld];
+    int* cnt = done + inst * gridDim.y + b;
+    if (tid == 0) s_last = atomicAdd(cnt, 1) == static_cast<int>(gridDim.x) - 1;
+    __syncthreads();
+    if (s_last) {
+        for (int j = tid; j < w; j += 128) xw[fc + j] = sy[j] / P[j + j * ld];
+        if (tid == 0) *cnt = 0;
     }
 }
 
-// backward, below rows: tbuf[j] += sum_{i in row block} L[i,j] x[rows[i]]  (one warp per column chunk)
-__global__ void k_big_bwd_below(FactorView F, const int* __restrict__ big_sn, double* __restrict__ tbuf, int tstride,
-                                const double* xw, int64_t xw_stride) {
+// Backward: grid.x = block of 512 rows below the diagonal block (at least one block).  Every block adds its part of
+// L21' x into tbuf (FP64 atomics); the last block to finish solves the unit-upper triangle and clears tbuf.
+__global__ void __launch_bounds__(256)
+k_big_backward(FactorView F, const int* __restrict__ big_sn, double* __restrict__ tbuf, int tstride, double* xw, int64_t xw_stride,
+               int tri_cap, int* __restrict__ done) {
+    double* tri = madipm_smem;
+    double* st = tri + tri_cap;
+    __shared__ double sx[512];
+    __shared__ int s_last;
     const int inst = blockIdx.z;
     const int b = blockIdx.y;
     const int s = big_sn[b];
     const double* Lx = F.Lx + inst * F.lx_stride;
     xw += inst * xw_stride;
-    const int w = F.sn_first[s + 1] - F.sn_first[s];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fc = F.sn_first[s];
+    const int w = F.sn_first[s + 1] - fc;
     const int h = static_cast<int>(F.sn_rowptr[s + 1] - F.sn_rowptr[s]);
     const int64_t ld = h;
     const double* P = Lx + F.sn_xoff[s];
     const int* rows = F.sn_rows + F.sn_rowptr[s];
-    const int i0 = w + blockIdx.x * 512;
-    if (i0 >= h) return;
-    const int i1 = min(h, i0 + 512);
-    __shared__ double sx[512];
-    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) sx[i - i0] = ldcg(&xw[rows[i]]);
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     double* tb = tbuf + (static_cast<int64_t>(inst) * gridDim.y + b) * tstride;
-    for (int j = warp; j < w; j += nwarp) {
-        double acc = 0.0;
-        for (int i = i0 + lane; i < i1; i += 32) acc = fma(P[i + j * ld], sx[i - i0], acc);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-        if (lane == 0) atomicAdd(&tb[j], acc);
-    }
-}
-
-// backward, diagonal block: x = L11^-T (z - tbuf); clears tbuf for the next solve
-__global__ void k_big_bwd_diag(FactorView F, const int* __restrict__ big_sn, double* __restrict__ tbuf, int tstride,
-                               double* xw, int64_t xw_stride, int tri_cap) {
-    double* tri = madipm_smem;
-    double* st = tri + tri_cap;
-    const int inst = blockIdx.y;
-    const int b = blockIdx.x;
-    const int s = big_sn[b];
-    const double* Lx = F.Lx + inst * F.lx_stride;
-    xw += inst * xw_stride;
-    const int tid = threadIdx.x, T = blockDim.x;
-    const int fc = F.sn_first[s];
-    const int w = F.sn_first[s + 1] - fc;
-    const int64_t ld = F.sn_rowptr[s + 1] - F.sn_rowptr[s];
-    const double* P = Lx + F.sn_xoff[s];
-    double* tb = tbuf + (static_cast<int64_t>(inst) * gridDim.x + b) * tstride;
-    for (int j = tid; j < w; j += T) { st[j] = ldcg(&xw[fc + j]) - ldcg(&tb[j]); tb[j] = 0.0; }
-    for (int idx = tid; idx < w * w; idx += T) {
-        const int i = idx % w, j = idx / w;
-        if (i > j) tri[idx] = P[i + j * ld];
-    }
-    for (int j = w - 1; j > 0; --j) {
+    const int i0 = w + blockIdx.x * 512;
+    if (i0 < h) {
+        const int i1 = min(h, i0 + 512);
+        for (int i = i0 + tid; i < i1; i += 256) sx[i - i0] = ldcg(&xw[rows[i]]);
         __syncthreads();
-        const double xj = st[j];
-        for (int k = tid; k < j; k += T) st[k] -= tri[j + k * w] * xj;
+        for (int j = warp; j < w; j += 8) {
+            double acc = 0.0;
+            for (int i = i0 + lane; i < i1; i += 32) acc = fma(P[i + j * ld], sx[i - i0], acc);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+            if (lane == 0) atomicAdd(&tb[j], acc);
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    int* cnt = done + inst * gridDim.y + b;
+    if (tid == 0) s_last = atomicAdd(cnt, 1) == static_cast<int>(gridDim.x) - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const bool staged = w * w <= tri_cap;
+    for (int j = tid; j < w; j += 256) { st[j] = ldcg(&xw[fc + j]) - ldcg(&tb[j]); tb[j] = 0.0; }
+    if (staged)
+        for (int idx = tid; idx < w * w; idx += 256) {
+            const int i = idx % w, j = idx / w;
+            if (i > j) tri[idx] = P[i + j * ld];
+        }
+    __syncthreads();
+    if (tid < 32) {
+        for (int j = w - 1; j > 0; --j) {
+            const double xj = st[j];
+            if (staged) { for (int k = lane; k < j; k += 32) st[k] -= tri[j + k * w] * xj; }
+            else { for (int k = lane; k < j; k += 32) st[k] -= P[j + k * ld] * xj; }
+            __syncwarp();
+        }
     }
     __syncthreads();
-    for (int j = tid; j < w; j += T) xw[fc + j] = st[j];
+    for (int j = tid; j < w; j += 256) xw[fc + j] = st[j];
+    if (tid == 0) *cnt = 0;
 }
 
 }  // namespace madipm
