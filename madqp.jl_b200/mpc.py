@@ -88,6 +88,8 @@ class IPMOptions:
     ordering: int = _lib.ORDER_ND
     max_width: int = 64
     block_panel: int = 0            # 0 = library default (csrc/symbolic.hpp)
+    relax_small: int = 0            # relaxed amalgamation (0 / None = library defaults)
+    relax_zeros: tuple = None
     nd_leaf: int = 0
     device: int = 0
 
@@ -202,7 +204,9 @@ class MPCSolver:
             raise ValueError("The KKT system NormalKKTSystem supports only linear programs.")   # normalkkt.jl:43-46
         kind = _lib.KKT_K2 if opt.kkt_system == "K2" else _lib.KKT_NORMAL
         self.h = Handle(kkt_kind=kind, batch=self.B, device=opt.device, ordering=opt.ordering,
-                        max_width=opt.max_width, block_panel=opt.block_panel, nd_leaf=opt.nd_leaf)
+                        max_width=opt.max_width, block_panel=opt.block_panel, nd_leaf=opt.nd_leaf,
+                        **({'relax_small': opt.relax_small} if opt.relax_small else {}),
+                        **({'relax_zeros': opt.relax_zeros} if opt.relax_zeros else {}))
         if kind == _lib.KKT_K2:
             self.h.set_pattern_k2(self.nx, self.m, q0.H_rows + 1, q0.H_cols + 1, q0.A_rows + 1, q0.A_cols + 1,
                                   ic.ind_ineq + 1)

@@ -10,7 +10,7 @@ scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 kw = {}
 for a in sys.argv[3:]:
     k, v = a.split("=")
-    kw[k] = int(float(v))
+    kw[k] = tuple(float(x) for x in v.split(",")) if "," in v else int(float(v))
 qps, kkt, name = bench.make_workload(wl, scale)
 t = time.time()
 s = MPCSolver(qps[0], kkt_system=kkt, regularization=FixedRegularization(1e-8, -1e-8), **kw)

@@ -12,7 +12,7 @@ scale = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
 extra = {}
 for a in sys.argv[4:]:
     k, v = a.split("=")
-    extra[k] = int(float(v))
+    extra[k] = tuple(float(x) for x in v.split(",")) if "," in v else int(float(v))
 qps, kkt, name = bench.make_workload(wl, scale)
 for b in budgets:
     s = MPCSolver(qps if len(qps) > 1 else qps[0], kkt_system=kkt, regularization=FixedRegularization(1e-8, -1e-8), block_panel=b, **extra)
