@@ -212,7 +212,7 @@ int32_t spmv_launch(madipm_handle* h, int rows, int64_t nnz, const int* rp, cons
     const double avg = static_cast<double>(nnz) / rows;
     dim3 grid(1, d->B);
     auto blocks = [&](int lanes) {
-        int64_t rpb = kVecThreads / lanes;
+        int64_t rpb = static_cast<int64_t>(kVecThreads / lanes) * kSpmvRows;
         return static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((rows + rpb - 1) / rpb, 148 * 16)));
     };
     if (avg <= 2.5) { grid.x = blocks(2); LAUNCH(h, k_spmv<2>, grid, kVecThreads, 0, rows, rp, ci, val, val_stride, x, xs, y, ys, alpha, beta); }

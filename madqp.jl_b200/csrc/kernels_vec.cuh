@@ -130,6 +130,10 @@ __device__ __forceinline__ double csr_row_dot(const int* __restrict__ rp, const 
     return acc;
 }
 
+// LANES threads per row, kSpmvRows rows per group in flight: the row pointers of all of them are loaded first, then
+// all (column, value) pairs, then all x entries, so a thread has several independent loads outstanding instead of
+// one chain rowptr -> (col, val) -> x per row.
+constexpr int kSpmvRows = 4;
 template <int LANES>
 __global__ void __launch_bounds__(kVecThreads)
 k_spmv(int rows, const int* __restrict__ rp, const int* __restrict__ ci, const double* __restrict__ val,
@@ -140,10 +144,36 @@ k_spmv(int rows, const int* __restrict__ rp, const int* __restrict__ ci, const d
     x += inst * x_stride;
     y += inst * y_stride;
     const int sub = threadIdx.x % LANES;
-    const int rows_per_block = kVecThreads / LANES;
-    for (int row = blockIdx.x * rows_per_block + threadIdx.x / LANES; row < rows; row += gridDim.x * rows_per_block) {
-        double acc = csr_row_dot<LANES>(rp, ci, val, x, row, sub);
-        if (sub == 0) y[row] = (beta == 0.0) ? alpha * acc : alpha * acc + beta * y[row];
+    constexpr int rows_per_block = kVecThreads / LANES;
+    // a block owns kSpmvRows consecutive slabs of rows_per_block rows; adjacent threads keep adjacent rows in each slab
+    for (int base = blockIdx.x * (kSpmvRows * rows_per_block); base < rows; base += gridDim.x * (kSpmvRows * rows_per_block)) {
+        const int r0 = base + threadIdx.x / LANES;
+        int p[kSpmvRows], e[kSpmvRows], c[kSpmvRows];
+        double v[kSpmvRows], acc[kSpmvRows];
+#pragma unroll
+        for (int j = 0; j < kSpmvRows; ++j) {
+            const int r = r0 + j * rows_per_block;
+            p[j] = r < rows ? __ldg(rp + r) + sub : 0;
+            e[j] = r < rows ? __ldg(rp + r + 1) : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < kSpmvRows; ++j) {
+            const bool ok = p[j] < e[j];
+            c[j] = ok ? __ldg(ci + p[j]) : 0;
+            v[j] = ok ? __ldg(val + p[j]) : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < kSpmvRows; ++j) acc[j] = p[j] < e[j] ? v[j] * __ldg(x + c[j]) : 0.0;
+#pragma unroll
+        for (int j = 0; j < kSpmvRows; ++j)
+            for (int q = p[j] + LANES; q < e[j]; q += LANES) acc[j] = fma(__ldg(val + q), __ldg(x + __ldg(ci + q)), acc[j]);
+#pragma unroll
+        for (int j = 0; j < kSpmvRows; ++j) {
+#pragma unroll
+            for (int o = LANES / 2; o > 0; o >>= 1) acc[j] += __shfl_down_sync(0xffffffffu, acc[j], o, LANES);
+            const int r = r0 + j * rows_per_block;
+            if (sub == 0 && r < rows) y[r] = (beta == 0.0) ? alpha * acc[j] : alpha * acc[j] + beta * y[r];
+        }
     }
 }
 
