@@ -115,18 +115,13 @@ def get_index_constraints(lvar, uvar, lcon, ucon):
 
 def _push_inside(x, l, u, bound_push, bound_fac):
     """MadNLP.initialize_variables! (Ipopt's projection of x0 into the interior of [l, u])."""
-    out = x.copy()
     fl, fu = np.isfinite(l), np.isfinite(u)
     with np.errstate(invalid="ignore"):
-        pl = np.minimum(bound_push * np.maximum(1.0, np.abs(l)), bound_fac * (u - l))
-        pu = np.minimum(bound_push * np.maximum(1.0, np.abs(u)), bound_fac * (u - l))
-        both = fl & fu
-        out[both] = np.minimum(u - pu, np.maximum(l + pl, x))[both]
-        lo = fl & ~fu
-        out[lo] = np.maximum(l + bound_push * np.maximum(1.0, np.abs(l)), x)[lo]
-        up = ~fl & fu
-        out[up] = np.minimum(u - bound_push * np.maximum(1.0, np.abs(u)), x)[up]
-    return out
+        pl = bound_push * np.maximum(1.0, np.abs(l))
+        pu = bound_push * np.maximum(1.0, np.abs(u))
+        width = bound_fac * (u - l)
+        inside = np.minimum(u - np.minimum(pu, width), np.maximum(l + np.minimum(pl, width), x))
+        return np.where(fl & fu, inside, np.where(fl, np.maximum(l + pl, x), np.where(fu, np.minimum(u - pu, x), x)))
 
 
 @dataclass
