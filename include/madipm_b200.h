@@ -139,6 +139,25 @@ int32_t madipm_get_symbolic(const madipm_handle* h, int32_t which, int64_t* out,
  *      /root/reference/src/KKT/normalkkt.jl:149-160).  Arrays are batch-major. ----------- */
 int32_t madipm_set_values(madipm_handle* h, const double* hess_V, const double* jac_V);
 
+/* One call for everything solve! does with the problem data before the first iteration
+ * (/root/reference/src/solver.jl:131-170): MadNLP.initialize!(cb, x, xl, xu, y, rhs, ind_ineq; tol, bound_push,
+ * bound_fac) -- bounds relaxed by tol, x0 pushed into their interior, slacks started at the pushed constraint values --,
+ * MadNLP.set_scaling! (con_scale = min(1, max_gradient / row max of |J|), obj_scale = min(1, max_gradient / max |grad f(x0)|)),
+ * and the evaluation + compression of the scaled Jacobian / Hessian values (what madipm_set_values does).
+ * Inputs are HOST arrays of the unscaled model, batch-major: x0, lvar, uvar, c [nvar]; y0, lcon, ucon [ncon];
+ * hess_V [nnzh], jac_V [nnzj].  All of it runs on the device.  Outputs (host, one per instance): obj_scale and
+ * norm_b = ||rhs||_inf (solver.jl:173); con_scale stays on the device as MADIPM_VEC_CON_SCALE. */
+typedef struct {
+    double tol;            /* bound_relax_factor */
+    double bound_push, bound_fac;
+    double max_gradient;   /* 100 in the reference (solver.jl:148-159) */
+    int32_t scaling;       /* 0: con_scale = obj_scale = 1 */
+    int32_t reserved;
+} madipm_load_options;
+int32_t madipm_load_problem(madipm_handle* h, const double* x0, const double* lvar, const double* uvar, const double* y0,
+                            const double* lcon, const double* ucon, const double* c, const double* hess_V, const double* jac_V,
+                            const madipm_load_options* opt, double* obj_scale, double* norm_b);
+
 /* ---- device vectors owned by the handle (MPCSolver fields, /root/reference/src/structure.jl:1-75,
  *      and the KKT diagonals, /root/reference/src/KKT/normalkkt.jl:10-18) ------------------ */
 enum {
@@ -152,6 +171,7 @@ enum {
     MADIPM_VEC_L_DIAG, MADIPM_VEC_L_LOWER,                                          /* nlb */
     MADIPM_VEC_U_DIAG, MADIPM_VEC_U_LOWER,                                          /* nub */
     MADIPM_VEC_KKT_NZVAL,                                                           /* kkt_nnz (aug_com.nzval) */
+    MADIPM_VEC_CON_SCALE,                                                           /* ncon (set_scaling!, see madipm_load_problem) */
     MADIPM_VEC_COUNT
 };
 int32_t madipm_vec_len(const madipm_handle* h, int32_t vec, int64_t* len);     /* per instance */

@@ -22,7 +22,7 @@ OP_A, OP_AT, OP_Q = 0, 1, 2
 
 VEC_NAMES = [
     "X", "XL", "XU", "ZL", "ZU", "F", "JACL", "COST", "Y", "C", "RHS", "D", "P", "W1", "W2",
-    "CORR_LB", "CORR_UB", "REG", "PR_DIAG", "DU_DIAG", "L_DIAG", "L_LOWER", "U_DIAG", "U_LOWER", "KKT_NZVAL",
+    "CORR_LB", "CORR_UB", "REG", "PR_DIAG", "DU_DIAG", "L_DIAG", "L_LOWER", "U_DIAG", "U_LOWER", "KKT_NZVAL", "CON_SCALE",
 ]
 VEC = {name: i for i, name in enumerate(VEC_NAMES)}
 
@@ -44,6 +44,11 @@ class Config(C.Structure):
     _fields_ = [("kkt_kind", C.c_int32), ("ordering", C.c_int32), ("max_width", C.c_int32), ("relax_small", C.c_int32),
                 ("relax_zeros", C.c_double * 3), ("block_panel", C.c_int64), ("device", C.c_int32), ("batch", C.c_int32),
                 ("nd_leaf", C.c_int32), ("reserved", C.c_int32)]
+
+
+class LoadOptions(C.Structure):
+    _fields_ = [("tol", C.c_double), ("bound_push", C.c_double), ("bound_fac", C.c_double), ("max_gradient", C.c_double),
+                ("scaling", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Info(C.Structure):
@@ -74,6 +79,7 @@ _SIGNATURES = {
     "madipm_get_info": ([C.POINTER(Info)], C.c_int32),
     "madipm_get_symbolic": ([C.c_int32, _P64, C.c_int64, _P64], C.c_int32),
     "madipm_set_values": ([_PD, _PD], C.c_int32),
+    "madipm_load_problem": ([_PD, _PD, _PD, _PD, _PD, _PD, _PD, _PD, _PD, C.POINTER(LoadOptions), _PD, _PD], C.c_int32),
     "madipm_vec_len": ([C.c_int32, _P64], C.c_int32),
     "madipm_vec_set": ([C.c_int32, _PD], C.c_int32),
     "madipm_vec_get": ([C.c_int32, _PD], C.c_int32),
@@ -238,6 +244,15 @@ class Handle:
     def set_values(self, hess_V, jac_V):
         hv, jv = _f64(hess_V), _f64(jac_V)
         self._check(self.lib.madipm_set_values(self._h, _pd(hv), _pd(jv)))
+
+    def load_problem(self, x0, lvar, uvar, y0, lcon, ucon, c, hess_V, jac_V, tol, bound_push, bound_fac, scaling,
+                     max_gradient=100.0):
+        """initialize! + set_scaling! + value compression on the device; returns (obj_scale, norm_b) per instance."""
+        arrs = [_f64(a) for a in (x0, lvar, uvar, y0, lcon, ucon, c, hess_V, jac_V)]
+        opt = LoadOptions(tol, bound_push, bound_fac, max_gradient, 1 if scaling else 0, 0)
+        os_, nb = np.zeros(self.batch), np.zeros(self.batch)
+        self._check(self.lib.madipm_load_problem(self._h, *[_pd(a) for a in arrs], C.byref(opt), _pd(os_), _pd(nb)))
+        return os_, nb, sum(a.nbytes for a in arrs)
 
     def vec_len(self, vec):
         n = C.c_int64()

@@ -64,7 +64,9 @@ struct DeviceState {
     int *A_rp = nullptr, *A_ci = nullptr, *AT_rp = nullptr, *AT_ci = nullptr, *Q_rp = nullptr, *Q_ci = nullptr;
     int *A_order = nullptr, *AT_src = nullptr, *Q_src = nullptr;
     double *A_val = nullptr, *AT_val = nullptr, *Q_val = nullptr, *hessV = nullptr, *jacV = nullptr;
-    int *aug_map = nullptr, *diag_slot = nullptr;
+    int *aug_map = nullptr, *diag_slot = nullptr, *jac_row = nullptr;
+    double* d_objscale = nullptr;
+    int nx = 0, n_slack = 0;
     double* const_diag = nullptr;
     int64_t* prod_ptr = nullptr;
     int *prod_a = nullptr, *prod_b = nullptr, *prod_k = nullptr;
@@ -382,6 +384,7 @@ int32_t device_create(madipm_handle* h) {
     d->L = static_cast<int64_t>(p.n_tot) + p.m + h->nlb + h->nub;
     d->nnzA = p.A_rowptr.back(); d->nnzQ = p.Q_rowptr.empty() ? 0 : p.Q_rowptr.back();
     d->nnzh = p.nnzh; d->nnzj = p.nnzj; d->nnzJfull = p.nnzj + p.n_slack;
+    d->nx = p.nx; d->n_slack = p.n_slack;
     d->kkt_nnz = p.kkt_colptr.back();
     d->lx_stride = s.nnz_stored;
     d->nsuper = s.nsuper; d->n_levels = s.n_levels;
@@ -411,7 +414,7 @@ int32_t device_create(madipm_handle* h) {
     for (int k = 0; k < h->nub; ++k) ub_of[h->ind_ub[k]] = k;
     UP(int, ind_lb, h->ind_lb); UP(int, ind_ub, h->ind_ub); UP(int, lb_of, lb_of); UP(int, ub_of, ub_of);
     // operators
-    UP(int, A_rp, p.A_rowptr); UP(int, A_ci, p.A_colind); UP(int, A_order, p.A_csr_order);
+    UP(int, A_rp, p.A_rowptr); UP(int, A_ci, p.A_colind); UP(int, A_order, p.A_csr_order); UP(int, jac_row, p.jac_I);
     UP(int, AT_rp, p.AT_rowptr); UP(int, AT_ci, p.AT_colind); UP(int, AT_src, p.AT_src);
     std::vector<int64_t> qrp = p.Q_rowptr;
     if (qrp.empty()) qrp.assign(static_cast<size_t>(d->n) + 1, 0);
@@ -585,7 +588,7 @@ int32_t device_create(madipm_handle* h) {
     int64_t* vl = d->veclen;
     for (int v : {MADIPM_VEC_X, MADIPM_VEC_XL, MADIPM_VEC_XU, MADIPM_VEC_ZL, MADIPM_VEC_ZU, MADIPM_VEC_F, MADIPM_VEC_JACL,
                   MADIPM_VEC_COST, MADIPM_VEC_REG, MADIPM_VEC_PR_DIAG}) vl[v] = n;
-    for (int v : {MADIPM_VEC_Y, MADIPM_VEC_C, MADIPM_VEC_RHS, MADIPM_VEC_DU_DIAG}) vl[v] = m;
+    for (int v : {MADIPM_VEC_Y, MADIPM_VEC_C, MADIPM_VEC_RHS, MADIPM_VEC_DU_DIAG, MADIPM_VEC_CON_SCALE}) vl[v] = m;
     for (int v : {MADIPM_VEC_D, MADIPM_VEC_P, MADIPM_VEC_W1, MADIPM_VEC_W2}) vl[v] = d->L;
     vl[MADIPM_VEC_CORR_LB] = vl[MADIPM_VEC_L_DIAG] = vl[MADIPM_VEC_L_LOWER] = d->nlb;
     vl[MADIPM_VEC_CORR_UB] = vl[MADIPM_VEC_U_DIAG] = vl[MADIPM_VEC_U_LOWER] = d->nub;
@@ -605,6 +608,7 @@ int32_t device_create(madipm_handle* h) {
     if ((rc = dev_alloc(h, &d->d_steps, static_cast<size_t>(B) * 2))) return rc;
     if ((rc = dev_alloc(h, &d->d_mu, B))) return rc;
     if ((rc = dev_alloc(h, &d->d_tau, B))) return rc;
+    if ((rc = dev_alloc(h, &d->d_objscale, B))) return rc;
     if ((rc = dev_alloc(h, &d->d_ones, B))) return rc;
     if ((rc = dev_alloc(h, &d->d_active, B))) return rc;
     if ((rc = dev_alloc(h, &d->d_inertia, static_cast<size_t>(B) * 3))) return rc;
@@ -637,19 +641,24 @@ using namespace madipm;
 extern "C" {
 
 // ---- values -----------------------------------------------------------------------------------
-int32_t madipm_set_values(madipm_handle* h, const double* hess_V, const double* jac_V) {
-    int32_t rc = check(h);
-    if (rc) return rc;
+// host -> device copy of the coordinate values (slack columns of the Jacobian: -1, normalkkt.jl:151)
+static int32_t upload_values(madipm_handle* h, const double* hess_V, const double* jac_V) {
     DeviceState* d = h->dev;
     const int B = d->B;
     if ((d->nnzh > 0 && !hess_V) || (d->nnzj > 0 && !jac_V)) return MADIPM_BAD_ARGUMENT;
-    Timer t(h, MADIPM_T_ASSEMBLY);
     if (d->nnzh) CUDA_OK(h, cudaMemcpyAsync(d->hessV, hess_V, sizeof(double) * B * d->nnzh, cudaMemcpyHostToDevice, d->stream));
     if (d->nnzJfull > d->nnzj)
-        LAUNCH(h, k_fill, dim3(vec_blocks(d->nnzJfull), B), kVecThreads, 0, d->nnzJfull, d->jacV, d->nnzJfull, -1.0);   // slack columns: -1 (normalkkt.jl:151)
+        LAUNCH(h, k_fill, dim3(vec_blocks(d->nnzJfull), B), kVecThreads, 0, d->nnzJfull, d->jacV, d->nnzJfull, -1.0);
     if (d->nnzj)
         CUDA_OK(h, cudaMemcpy2DAsync(d->jacV, sizeof(double) * d->nnzJfull, jac_V, sizeof(double) * d->nnzj,
                                      sizeof(double) * d->nnzj, B, cudaMemcpyHostToDevice, d->stream));
+    return MADIPM_OK;
+}
+
+// compress_jacobian! / compress_hessian! from the device copies of the coordinate values
+static int32_t compress_values(madipm_handle* h) {
+    DeviceState* d = h->dev;
+    const int B = d->B;
     // compress_jacobian! (normalkkt.jl:149-158): AT.nzval[i] = A.V[A_csr_map[i]]
     if (d->nnzA) {
         LAUNCH(h, k_gather, dim3(vec_blocks(d->nnzA), B), kVecThreads, 0, d->nnzA, d->A_order, d->jacV, d->nnzJfull, d->A_val, d->nnzA);
@@ -671,13 +680,88 @@ int32_t madipm_set_values(madipm_handle* h, const double* hess_V, const double* 
     return MADIPM_OK;
 }
 
+int32_t madipm_set_values(madipm_handle* h, const double* hess_V, const double* jac_V) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    Timer t(h, MADIPM_T_ASSEMBLY);
+    if ((rc = upload_values(h, hess_V, jac_V))) return rc;
+    return compress_values(h);
+}
+
+int32_t madipm_load_problem(madipm_handle* h, const double* x0, const double* lvar, const double* uvar, const double* y0,
+                            const double* lcon, const double* ucon, const double* c, const double* hess_V, const double* jac_V,
+                            const madipm_load_options* opt, double* obj_scale, double* norm_b) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    const int B = d->B, nx = d->nx, n = d->n, m = d->m;
+    if (!opt || !obj_scale || !norm_b || (nx > 0 && (!x0 || !lvar || !uvar || !c)) || (m > 0 && (!y0 || !lcon || !ucon)))
+        return MADIPM_BAD_ARGUMENT;
+    Timer t(h, MADIPM_T_ASSEMBLY);
+    auto up_n = [&](int vec, const double* src) {           // [B][nx] host -> the first nx entries of an n_tot vector
+        return nx == 0 ? cudaSuccess
+                       : cudaMemcpy2DAsync(d->vec[vec], sizeof(double) * n, src, sizeof(double) * nx, sizeof(double) * nx, B,
+                                           cudaMemcpyHostToDevice, d->stream);
+    };
+    auto up_m = [&](int vec, const double* src) {
+        return m == 0 ? cudaSuccess : cudaMemcpyAsync(d->vec[vec], src, sizeof(double) * B * m, cudaMemcpyHostToDevice, d->stream);
+    };
+    CUDA_OK(h, up_n(MADIPM_VEC_X, x0)); CUDA_OK(h, up_n(MADIPM_VEC_XL, lvar)); CUDA_OK(h, up_n(MADIPM_VEC_XU, uvar));
+    CUDA_OK(h, up_n(MADIPM_VEC_COST, c));
+    CUDA_OK(h, up_m(MADIPM_VEC_Y, y0)); CUDA_OK(h, up_m(MADIPM_VEC_RHS, lcon)); CUDA_OK(h, up_m(MADIPM_VEC_C, ucon));
+    if ((rc = upload_values(h, hess_V, jac_V))) return rc;
+    VecView V = make_view(*d);
+    const dim3 gn(vec_blocks(n), B), gm(vec_blocks(m), B);
+    // initialize!: relaxed bounds, start pushed inside, slacks at the constraint values of the pushed start
+    LAUNCH(h, k_load_variables, gn, kVecThreads, 0, V, nx, opt->tol, opt->bound_push, opt->bound_fac);
+    if (d->nnzA)
+        LAUNCH(h, k_gather, dim3(vec_blocks(d->nnzA), B), kVecThreads, 0, d->nnzA, d->A_order, d->jacV, d->nnzJfull, d->A_val, d->nnzA);
+    if (d->n_slack > 0) {
+        spmv_launch(h, m, d->nnzA, d->A_rp, d->A_ci, d->A_val, d->nnzA, d->vec[MADIPM_VEC_X], n, d->buffer_m, m, 1.0, 0.0);
+        LAUNCH(h, k_load_slacks, dim3(vec_blocks(d->n_slack), B), kVecThreads, 0, V, nx, d->n_slack, d->jac_row + d->nnzj, d->buffer_m,
+               (int64_t)m, opt->tol, opt->bound_push, opt->bound_fac);
+    }
+    // set_scaling!
+    double* cs = d->vec[MADIPM_VEC_CON_SCALE];
+    std::vector<double> os(B, 1.0);
+    if (opt->scaling) {
+        if (m > 0) LAUNCH(h, k_con_scale, gm, kVecThreads, 0, m, d->A_rp, d->A_val, d->nnzA, opt->max_gradient, cs, (int64_t)m);
+        if (nx > 0) {
+            if (d->nnzQ)
+                LAUNCH(h, k_gather, dim3(vec_blocks(d->nnzQ), B), kVecThreads, 0, d->nnzQ, d->Q_src, d->hessV, d->nnzh, d->Q_val, d->nnzQ);
+            LAUNCH(h, k_grad0_max, dim3(vec_blocks(nx), B), kVecThreads, 0, V, nx, d->Q_rp, d->Q_ci, d->Q_val, d->nnzQ, d->nnzQ > 0 ? 1 : 0,
+                   d->red_scratch, d->red_counter, d->d_out);
+            if ((rc = fetch(h, d->d_out, os.data(), B))) return rc;
+            for (int b = 0; b < B; ++b) os[b] = os[b] > 0.0 ? std::min(1.0, opt->max_gradient / os[b]) : 1.0;
+        }
+    } else if (m > 0) {
+        LAUNCH(h, k_fill, gm, kVecThreads, 0, (int64_t)m, cs, (int64_t)m, 1.0);
+    }
+    CUDA_OK(h, cudaMemcpyAsync(d->d_objscale, os.data(), sizeof(double) * B, cudaMemcpyHostToDevice, d->stream));
+    LAUNCH(h, k_load_scale, dim3(vec_blocks(std::max(n, m)), B), kVecThreads, 0, V, nx, d->n_slack, d->jac_row + d->nnzj, cs, (int64_t)m,
+           d->d_objscale);
+    if (opt->scaling && (d->nnzh > 0 || d->nnzj > 0))
+        LAUNCH(h, k_scale_values, dim3(vec_blocks(std::max(d->nnzh, d->nnzj)), B), kVecThreads, 0, d->nnzh, d->hessV, d->nnzh, d->nnzj,
+               d->jacV, d->nnzJfull, d->jac_row, cs, (int64_t)m, d->d_objscale);
+    if ((rc = compress_values(h))) return rc;
+    for (int b = 0; b < B; ++b) norm_b[b] = 0.0;
+    if (m > 0) {
+        LAUNCH(h, k_norm_inf, gm, kVecThreads, 0, (int64_t)m, d->vec[MADIPM_VEC_RHS], (int64_t)m, d->red_scratch, d->red_counter, d->d_out);
+        if ((rc = fetch(h, d->d_out, norm_b, B))) return rc;
+    } else {
+        CUDA_OK(h, cudaStreamSynchronize(d->stream));       // `os` is read by the copy above
+    }
+    for (int b = 0; b < B; ++b) obj_scale[b] = os[b];
+    return MADIPM_OK;
+}
+
 // ---- vectors ----------------------------------------------------------------------------------
 int32_t madipm_vec_len(const madipm_handle* h, int32_t vec, int64_t* len) {
     if (!h || !len || vec < 0 || vec >= MADIPM_VEC_COUNT) return MADIPM_BAD_ARGUMENT;
     const KktPattern& p = h->pat;
     int64_t n = p.n_tot, m = p.m, L = n + m + h->nlb + h->nub;
     switch (vec) {
-        case MADIPM_VEC_Y: case MADIPM_VEC_C: case MADIPM_VEC_RHS: case MADIPM_VEC_DU_DIAG: *len = m; break;
+        case MADIPM_VEC_Y: case MADIPM_VEC_C: case MADIPM_VEC_RHS: case MADIPM_VEC_DU_DIAG: case MADIPM_VEC_CON_SCALE: *len = m; break;
         case MADIPM_VEC_D: case MADIPM_VEC_P: case MADIPM_VEC_W1: case MADIPM_VEC_W2: *len = L; break;
         case MADIPM_VEC_CORR_LB: case MADIPM_VEC_L_DIAG: case MADIPM_VEC_L_LOWER: *len = h->nlb; break;
         case MADIPM_VEC_CORR_UB: case MADIPM_VEC_U_DIAG: case MADIPM_VEC_U_LOWER: *len = h->nub; break;

@@ -593,6 +593,120 @@ __global__ void k_update_iterate(VecView V, const double* __restrict__ d, const 
     }
 }
 
+// ---- problem loading on the device: MadNLP.initialize!(cb, x, xl, xu, y, rhs, ind_ineq; ...) and set_scaling!
+// (called at /root/reference/src/solver.jl:131-159; un-vendored MadNLP code, restated in mpc.py prepare_host, which
+// is the host reference these kernels are tested against).  Raw inputs are uploaded into the vectors they end up in.
+__device__ __forceinline__ double push_inside(double x, double l, double u, double bound_push, double bound_fac) {
+    // Ipopt's projection of x0 into the interior of [l, u] (MadNLP.initialize_variables!)
+    const bool fl = isfinite(l), fu = isfinite(u);
+    const double pl = bound_push * fmax(1.0, fabs(l)), pu = bound_push * fmax(1.0, fabs(u));
+    if (fl && fu) {
+        const double width = bound_fac * (u - l);
+        return fmin(u - fmin(pu, width), fmax(l + fmin(pl, width), x));
+    }
+    if (fl) return fmax(l + pl, x);
+    if (fu) return fmin(u - pu, x);
+    return x;
+}
+
+// x[:nx] holds x0, xl[:nx] lvar, xu[:nx] uvar on entry; relaxed bounds and the pushed start on exit; slack part zeroed
+__global__ void k_load_variables(VecView V, int nx, double tol, double bound_push, double bound_fac) {
+    V = shift(V, blockIdx.y);
+    MADIPM_GRID_STRIDE(i, V.n) {
+        if (i < nx) {
+            const double l0 = V.xl[i], u0 = V.xu[i];
+            const double l = l0 - fmax(1.0, fabs(l0)) * tol, u = u0 + fmax(1.0, fabs(u0)) * tol;
+            V.xl[i] = l; V.xu[i] = u;
+            V.x[i] = push_inside(V.x[i], l, u, bound_push, bound_fac);
+        } else {
+            V.x[i] = 0.0;
+        }
+    }
+}
+
+// slack k of inequality row r = slack_row[k]: bounds = relaxed (lcon, ucon)[r], start = cons0[r] pushed inside.
+// rhs holds lcon and c holds ucon on entry (they are rewritten by k_load_scale afterwards).
+__global__ void k_load_slacks(VecView V, int nx, int n_slack, const int* __restrict__ slack_row, const double* __restrict__ cons0,
+                              int64_t cons_stride, double tol, double bound_push, double bound_fac) {
+    cons0 += blockIdx.y * cons_stride;
+    V = shift(V, blockIdx.y);
+    MADIPM_GRID_STRIDE(k, n_slack) {
+        const int r = slack_row[k];
+        const double l0 = V.rhs[r], u0 = V.c[r];
+        const double l = l0 - fmax(1.0, fabs(l0)) * tol, u = u0 + fmax(1.0, fabs(u0)) * tol;
+        V.xl[nx + k] = l; V.xu[nx + k] = u;
+        V.x[nx + k] = push_inside(cons0[r], l, u, bound_push, bound_fac);
+    }
+}
+
+// con_scale[r] = min(1, max_gradient / max(1, max_k |A[r,k]|))   (set_scaling!, rows of the Jacobian)
+__global__ void k_con_scale(int m, const int* __restrict__ rp, const double* __restrict__ val, int64_t val_stride,
+                            double max_gradient, double* __restrict__ con_scale, int64_t cs_stride) {
+    val += blockIdx.y * val_stride;
+    con_scale += blockIdx.y * cs_stride;
+    MADIPM_GRID_STRIDE(r, m) {
+        double mx = 1.0;
+        for (int p = rp[r]; p < rp[r + 1]; ++p) mx = fmax(mx, fabs(val[p]));
+        con_scale[r] = fmin(1.0, max_gradient / mx);
+    }
+}
+
+// g = Q x + cost over the structural variables, out = max |g|  (gradient of the objective at the start, for obj_scale)
+__global__ void __launch_bounds__(kVecThreads)
+k_grad0_max(VecView V, int nx, const int* __restrict__ Qrp, const int* __restrict__ Qci, const double* __restrict__ Qv,
+            int64_t q_stride, int has_q, double* scratch, unsigned int* counter, double* out) {
+    V = shift(V, blockIdx.y);
+    Qv += blockIdx.y * q_stride;
+    RedVals<1> r;
+    r.v[0] = 0.0;
+    MADIPM_GRID_STRIDE(i, nx) {
+        double g = V.cost[i];
+        if (has_q)
+            for (int p = Qrp[i]; p < Qrp[i + 1]; ++p) g = fma(Qv[p], V.x[Qci[p]], g);
+        r.v[0] = nanmax(r.v[0], fabs(g));
+    }
+    grid_reduce<1, RED_MAX>(r, scratch, counter, out);
+}
+
+// apply the scalings: y = y0 / cs, rhs = (lcon == ucon ? lcon : 0) * cs, slack x / xl / xu *= cs[row], cost *= obj_scale
+// (rhs holds lcon and c holds ucon on entry)
+__global__ void k_load_scale(VecView V, int nx, int n_slack, const int* __restrict__ slack_row, const double* __restrict__ con_scale,
+                             int64_t cs_stride, const double* __restrict__ obj_scale) {
+    con_scale += blockIdx.y * cs_stride;
+    const double os = obj_scale[blockIdx.y];
+    V = shift(V, blockIdx.y);
+    const int top = max(V.n, V.m);
+    MADIPM_GRID_STRIDE(i, top) {
+        if (i < V.m) {
+            const double cs = con_scale[i];
+            const double l = V.rhs[i], u = V.c[i];
+            V.y[i] = V.y[i] / cs;
+            V.rhs[i] = (l == u ? l : 0.0) * cs;
+        }
+        if (i < nx) V.cost[i] *= os;
+        else if (i < V.n) {
+            V.cost[i] = 0.0;
+            const double cs = con_scale[slack_row[i - nx]];
+            V.x[i] *= cs; V.xl[i] *= cs; V.xu[i] *= cs;
+        }
+    }
+}
+
+// coordinate values: hess *= obj_scale, jac[k] *= con_scale[row of k] (structural entries only)
+__global__ void k_scale_values(int64_t nnzh, double* __restrict__ hessV, int64_t h_stride, int64_t nnzj, double* __restrict__ jacV,
+                               int64_t j_stride, const int* __restrict__ jac_row, const double* __restrict__ con_scale, int64_t cs_stride,
+                               const double* __restrict__ obj_scale) {
+    hessV += blockIdx.y * h_stride;
+    jacV += blockIdx.y * j_stride;
+    con_scale += blockIdx.y * cs_stride;
+    const double os = obj_scale[blockIdx.y];
+    const int64_t top = nnzh > nnzj ? nnzh : nnzj;
+    for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < top; k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        if (k < nnzh) hessV[k] *= os;
+        if (k < nnzj) jacV[k] *= con_scale[jac_row[k]];
+    }
+}
+
 // ---- K8 model evaluation (/root/reference/src/solver.jl:338-340, scripts/qp_gpu.jl:29-40):
 // f = Qx + cost (slack part: cost only), c = A x - rhs (slack columns are in A with -1),
 // out[2] = { cost'x, x'Qx }.  One thread per row.

@@ -88,6 +88,7 @@ class IPMOptions:
     ordering: int = _lib.ORDER_ND
     max_width: int = 64
     block_panel: int = 0            # 0 = library default (csrc/symbolic.hpp)
+    device_prepare: bool = True     # initialize! / set_scaling! on the device (madipm_load_problem) instead of numpy
     relax_small: int = 0            # relaxed amalgamation (0 / None = library defaults)
     relax_zeros: tuple = None
     nd_leaf: int = 0
@@ -285,6 +286,7 @@ class MPCSolver:
             JV[b] = qp.A_vals * self.con_scale[b][qp.A_rows]   # eval_jac_wrapper! (solver.jl:167)
         self._c0 = np.array([qp.c0 for qp in self.qps]) * self.obj_scale
         self._host = dict(X=X, XL=XL, XU=XU, Y=Y, RHS=RHS, COST=COST, HV=HV, JV=JV)
+        self._con_scale_on_device = False
         self.norm_b = np.max(np.abs(RHS), axis=1) if m else np.zeros(B)     # solver.jl:173
 
     def _row_groups(self, b, rows):
@@ -296,6 +298,24 @@ class MPCSolver:
             starts = np.flatnonzero(np.diff(rs, prepend=-1))
             cache[b] = (order, starts, rs[starts])
         return cache[b]
+
+    def load_device(self):
+        """prepare_host + upload in one device-side call (madipm_load_problem): the raw model arrays go to the GPU and
+        MadNLP.initialize! / set_scaling! / the value compression run there.  prepare_host stays as the host reference."""
+        opt, h = self.opt, self.h
+        cat = (lambda f: np.ascontiguousarray(f(self.qps[0]), dtype=np.float64)) if self.B == 1 else \
+            (lambda f: np.stack([np.asarray(f(qp), dtype=np.float64) for qp in self.qps]))
+        os_, nb, nbytes = h.load_problem(cat(lambda q: q.x0), cat(lambda q: q.lvar), cat(lambda q: q.uvar), cat(lambda q: q.y0),
+                                         cat(lambda q: q.lcon), cat(lambda q: q.ucon), cat(lambda q: q.c),
+                                         cat(lambda q: q.H_vals), cat(lambda q: q.A_vals),
+                                         opt.bound_relax_factor, opt.bound_push, opt.bound_fac, opt.scaling)
+        self.obj_scale[:] = os_
+        self.norm_b = nb
+        self._c0 = np.array([qp.c0 for qp in self.qps]) * self.obj_scale
+        self._con_scale_on_device = True
+        self.h2d_bytes = nbytes
+        if self.keep_snapshot:
+            h.snapshot_inputs()
 
     def upload(self):
         """Host -> device copy of one solve's inputs (iterate, bounds, rhs, cost, Jacobian/Hessian values)."""
@@ -497,6 +517,8 @@ class MPCSolver:
         try:
             if resident:
                 self.upload_resident()
+            elif self.opt.device_prepare:
+                self.load_device()
             else:
                 self.prepare_host()
                 self.upload()
@@ -514,6 +536,9 @@ class MPCSolver:
         x = self.h.vec_get("X").reshape(self.B, -1)
         y = self.h.vec_get("Y").reshape(self.B, -1)
         self.d2h_bytes = x.nbytes + y.nbytes
+        if getattr(self, "_con_scale_on_device", False):
+            self.con_scale = self.h.vec_get("CON_SCALE").reshape(self.B, -1)
+            self.d2h_bytes += self.con_scale.nbytes
         self.total_time = time.perf_counter() - t0
         return ExecutionStats(
             status=list(self.status), iter=self.iters.copy(), objective=self.obj_val / self.obj_scale,

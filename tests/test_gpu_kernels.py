@@ -371,3 +371,35 @@ def test_full_size_c3_factor_solve_properties():
     x3 = h.vec_get("W2")[:N]
     np.testing.assert_allclose(x3, 2.0 * x1 - 3.0 * x2, rtol=0, atol=1e-6 * np.max(np.abs(x3)))
     s.close()
+
+
+@pytest.mark.parametrize("maker,kw,kkt", [
+    (P.inequality_qp, dict(seed=1, n=60, m=40, n_ineq=15), "K2"),
+    (P.maros_meszaros_like, dict(seed=3, n=300, m=150, nnz=1500), "K2"),
+    (P.sparse_lp, dict(n=3000, m=1500), "NORMAL"),
+])
+@pytest.mark.parametrize("scaling", [True, False])
+def test_load_problem_matches_host_preparation(maker, kw, kkt, scaling):
+    """madipm_load_problem (initialize! + set_scaling! + value compression on the device) against the numpy
+    restatement MPCSolver.prepare_host + upload: same iterate, bounds, rhs, cost, scalings and KKT values."""
+    from madqp_jl_b200.mpc import MPCSolver, FixedRegularization
+    qp = maker(**kw)
+    a = MPCSolver(qp, kkt_system=kkt, regularization=FixedRegularization(1e-8, -1e-8), scaling=scaling, device_prepare=False)
+    b = MPCSolver(qp, kkt_system=kkt, regularization=FixedRegularization(1e-8, -1e-8), scaling=scaling, device_prepare=True)
+    a.prepare_host(); a.upload()
+    b.load_device()
+    assert np.allclose(b.obj_scale, a.obj_scale, rtol=1e-14, atol=0)
+    assert np.allclose(b.norm_b, a.norm_b, rtol=1e-14, atol=0)
+    assert np.allclose(b.h.vec_get("CON_SCALE"), a.con_scale.ravel(), rtol=1e-15, atol=0)
+    for v in ("X", "XL", "XU", "Y", "RHS", "COST"):
+        x, y = a.h.vec_get(v), b.h.vec_get(v)
+        assert np.array_equal(np.isinf(x), np.isinf(y)), v
+        f = np.isfinite(x)
+        assert np.allclose(y[f], x[f], rtol=1e-14, atol=1e-300), v
+    if kkt == "K2":
+        assert np.allclose(b.h.vec_get("KKT_NZVAL"), a.h.vec_get("KKT_NZVAL"), rtol=1e-14, atol=1e-300)
+    sa, sb = a.solve(), b.solve()
+    assert sa.status == sb.status and abs(int(sa.iter[0]) - int(sb.iter[0])) <= 1
+    assert abs(sa.objective[0] - sb.objective[0]) <= 1e-8 * max(1.0, abs(sa.objective[0]))
+    assert np.allclose(sa.multipliers, sb.multipliers, rtol=1e-5, atol=1e-7)
+    a.close(); b.close()
