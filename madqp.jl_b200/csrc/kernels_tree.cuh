@@ -411,18 +411,30 @@ __device__ __forceinline__ void tree_forward_task(const TreeView& T, const SnMet
     for (int i = t; i < nb; i += G) su[i] = 0.0;
     for (int base = 0; base < c1 - c0; base += kChildChunk) {
         const int n = stage_children<G>(T, cs, c0, c1, base, t);   // its barrier also publishes sy / su
-        for (int ci = 0; ci < n; ++ci) {
-            const ChildRec r = cs[ci];
-            if (!r.pull) continue;
-            const int* pos = T.par_pos + r.below;
-            const double* cc = cv + r.below;
-            for (int a = t; a < r.nb; a += G) {
-                const int pa = __ldg(pos + a);
-                const double v = __ldcg(cc + a);
-                if (pa < w) sy[pa] -= v;
-                else su[pa - w] += v;
+        // The contribution vectors of all staged children are fetched in ONE pass (entry e of the concatenated
+        // vectors goes to thread e), so their memory round trips overlap; they are then applied child by child,
+        // which keeps the summation order fixed.
+        int total = 0;
+        for (int ci = 0; ci < n; ++ci) total += cs[ci].pull ? cs[ci].nb : 0;
+        for (int e0 = 0; e0 < total; e0 += G) {
+            int e = e0 + t, mine = -1, pa = 0;
+            double v = 0.0;
+            if (e < total) {
+                for (int ci = 0; ci < n; ++ci) {
+                    const int len = cs[ci].pull ? cs[ci].nb : 0;
+                    if (e < len) { mine = ci; break; }
+                    e -= len;
+                }
+                pa = __ldg(T.par_pos + cs[mine].below + e);
+                v = __ldcg(cv + cs[mine].below + e);
             }
-            gsync<G>();
+            for (int ci = 0; ci < n; ++ci) {
+                if (mine == ci) {
+                    if (pa < w) sy[pa] -= v;
+                    else su[pa - w] += v;
+                }
+                gsync<G>();
+            }
         }
     }
     cp_async_wait_all();
