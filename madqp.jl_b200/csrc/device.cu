@@ -76,6 +76,12 @@ struct DeviceState {
     int64_t *row_colbase = nullptr, *row_relbase = nullptr;
     int* rel = nullptr;
     double *Lx = nullptr, *xw = nullptr;
+    // K2 without big supernodes: the assembled panels are kept as an image P0 (constant part written once per
+    // set_values, the N diagonal slots rewritten by build_kkt); the factor tasks read P0 and write Lx, so a
+    // factorisation needs neither the memset of Lx nor k_assemble_panels.
+    double* P0 = nullptr;
+    int64_t* diag_lx = nullptr;
+    bool image_valid = false;
     int *perm = nullptr, *iperm = nullptr;
     int* fail = nullptr;
     std::vector<int> h_fail;
@@ -172,6 +178,7 @@ TreeView make_tree_view(const DeviceState& d) {
     T.F = make_factor_view(d, 0);
     T.meta = d.sn_meta; T.crec = d.child_rec; T.par_pos = d.par_pos;
     T.Cx = d.Cx; T.cx_stride = d.cx_stride; T.cvec = d.cvec; T.cv_stride = d.cv_stride;
+    T.image = nullptr;
     T.xw = d.xw; T.xw_stride = d.N; T.bar = d.bar; T.B = d.B; T.tickets = nullptr; T.phase_cls = d.phase_cls;
     for (int c = 0; c < 4; ++c) { T.slice[c] = d.sym->tree_slice[c]; T.cap[c] = d.sym->tree_cap[c]; T.maxh[c] = d.sym->tree_maxh[c]; }
     T.maxw = d.tree_maxw;
@@ -238,15 +245,18 @@ __global__ void k_scatter_add(int64_t n, const int* __restrict__ map, const doub
 // (transfer! semantics, /root/reference/scripts/cuda_wrapper.jl:17-28, restricted to the entries that moved)
 __global__ void k_build_kkt_k2(int n, int m, const int* __restrict__ diag_slot, const double* __restrict__ const_diag,
                                const double* __restrict__ pr_diag, const double* __restrict__ du_diag,
-                               double* __restrict__ nzval, int64_t nz_stride) {
+                               double* __restrict__ nzval, int64_t nz_stride, const int64_t* __restrict__ diag_lx,
+                               double* __restrict__ image, int64_t image_stride) {
     const int inst = blockIdx.y;
     const_diag += static_cast<int64_t>(inst) * (n + m);
     pr_diag += static_cast<int64_t>(inst) * n;
     du_diag += static_cast<int64_t>(inst) * m;
     nzval += inst * nz_stride;
+    if (image) image += inst * image_stride;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n + m; i += gridDim.x * blockDim.x) {
-        const double v = (i < n) ? pr_diag[i] : du_diag[i - n];
-        nzval[diag_slot[i]] = v + const_diag[i];
+        const double v = ((i < n) ? pr_diag[i] : du_diag[i - n]) + const_diag[i];
+        nzval[diag_slot[i]] = v;
+        if (image) image[diag_lx[i]] = v;                 // the same entry in the panel image (see DeviceState::P0)
     }
 }
 
@@ -289,6 +299,7 @@ int32_t launch_tree(madipm_handle* h, const DeviceState::TreeSeg& sg) {
     DeviceState* d = h->dev;
     TreeView T = make_tree_view(*d);
     T.tickets = d->tickets[OP];
+    if (OP == 0 && d->image_valid) T.image = d->P0;
     const bool reverse = OP == 2;
     auto bottom = [&]() -> int32_t {
         if (sg.split <= sg.ph0 || sg.grid[OP] <= 0) return MADIPM_OK;
@@ -487,6 +498,12 @@ int32_t device_create(madipm_handle* h) {
             diag_pos[j] = s.sn_xoff[sn] + static_cast<int64_t>(j - s.sn_first[sn]) * (hs + 1);
     }
     UP(int64_t, diag_pos, diag_pos);
+    if (p.kind == 0 && s.n_big == 0) {
+        std::vector<int64_t> diag_lx(d->N);
+        for (int i = 0; i < d->N; ++i) diag_lx[i] = s.asm_map[p.diag_slot[i]];
+        UP(int64_t, diag_lx, diag_lx);
+        if ((rc = dev_alloc(h, &d->P0, static_cast<size_t>(h->cfg.batch) * s.nnz_stored))) return rc;
+    }
 #undef UP
     if ((rc = dev_alloc(h, &d->Lx, static_cast<size_t>(B) * d->lx_stride))) return rc;
     if ((rc = dev_alloc(h, &d->xw, static_cast<size_t>(B) * d->N))) return rc;
@@ -675,6 +692,12 @@ static int32_t compress_values(madipm_handle* h) {
         if (d->nnzJfull)
             LAUNCH(h, k_scatter_add, dim3(vec_blocks(d->nnzJfull), B), kVecThreads, 0, d->nnzJfull, d->aug_map + d->n + d->nnzh, d->jacV, d->nnzJfull, nz, d->kkt_nnz);
         LAUNCH(h, k_extract_diag, dim3(vec_blocks(d->N), B), kVecThreads, 0, d->N, d->diag_slot, nz, d->kkt_nnz, d->const_diag);
+        if (d->P0) {                                       // panel image of the constant part
+            CUDA_OK(h, cudaMemsetAsync(d->P0, 0, sizeof(double) * B * d->lx_stride, d->stream));
+            LAUNCH(h, k_assemble_panels, dim3(vec_blocks(d->kkt_nnz) * 4, B), kVecThreads, 0, d->kkt_nnz, d->asm_map, nz, d->kkt_nnz, d->P0,
+                   d->lx_stride);
+            d->image_valid = true;
+        }
     }
     d->values_set = true;
     return MADIPM_OK;
@@ -776,6 +799,7 @@ int32_t madipm_vec_set(madipm_handle* h, int32_t vec, const double* host) {
     if (rc) return rc;
     if (vec < 0 || vec >= MADIPM_VEC_COUNT || !host) return MADIPM_BAD_ARGUMENT;
     DeviceState* d = h->dev;
+    if (vec == MADIPM_VEC_KKT_NZVAL) d->image_valid = false;   // the caller owns the KKT values now: assemble from nzval
     CUDA_OK(h, cudaMemcpyAsync(d->vec[vec], host, sizeof(double) * d->B * d->veclen[vec], cudaMemcpyHostToDevice, d->stream));
     return MADIPM_OK;
 }
@@ -795,6 +819,7 @@ int32_t madipm_vec_fill(madipm_handle* h, int32_t vec, double value) {
     if (rc) return rc;
     if (vec < 0 || vec >= MADIPM_VEC_COUNT) return MADIPM_BAD_ARGUMENT;
     DeviceState* d = h->dev;
+    if (vec == MADIPM_VEC_KKT_NZVAL) d->image_valid = false;
     LAUNCH(h, k_fill, dim3(vec_blocks(d->veclen[vec]), d->B), kVecThreads, 0, d->veclen[vec], d->vec[vec], d->veclen[vec], value);
     return MADIPM_OK;
 }
@@ -803,6 +828,7 @@ int32_t madipm_vec_device_ptr(madipm_handle* h, int32_t vec, void** dev) {
     int32_t rc = check(h);
     if (rc) return rc;
     if (vec < 0 || vec >= MADIPM_VEC_COUNT || !dev) return MADIPM_BAD_ARGUMENT;
+    if (vec == MADIPM_VEC_KKT_NZVAL) h->dev->image_valid = false;   // may be written through the pointer
     *dev = h->dev->vec[vec];
     return MADIPM_OK;
 }
@@ -821,6 +847,7 @@ int32_t madipm_vec_copy(madipm_handle* h, int32_t dst, int32_t src) {
     if (rc) return rc;
     DeviceState* d = h->dev;
     if (dst < 0 || src < 0 || dst >= MADIPM_VEC_COUNT || src >= MADIPM_VEC_COUNT || d->veclen[dst] != d->veclen[src]) return MADIPM_BAD_ARGUMENT;
+    if (dst == MADIPM_VEC_KKT_NZVAL) d->image_valid = false;
     CUDA_OK(h, cudaMemcpyAsync(d->vec[dst], d->vec[src], sizeof(double) * d->B * d->veclen[dst], cudaMemcpyDeviceToDevice, d->stream));
     return MADIPM_OK;
 }
@@ -882,7 +909,8 @@ int32_t madipm_build_kkt(madipm_handle* h) {
     double* nz = d->vec[MADIPM_VEC_KKT_NZVAL];
     if (d->kind == 0) {
         LAUNCH(h, k_build_kkt_k2, dim3(vec_blocks(d->N), d->B), kVecThreads, 0, d->n, d->m, d->diag_slot, d->const_diag,
-               d->vec[MADIPM_VEC_PR_DIAG], d->vec[MADIPM_VEC_DU_DIAG], nz, d->kkt_nnz);
+               d->vec[MADIPM_VEC_PR_DIAG], d->vec[MADIPM_VEC_DU_DIAG], nz, d->kkt_nnz, d->diag_lx,
+               d->image_valid ? d->P0 : nullptr, d->lx_stride);
     } else {
         LAUNCH(h, k_assemble_normal, dim3(vec_blocks(d->kkt_nnz), d->B), kVecThreads, 0, d->kkt_nnz, d->prod_ptr, d->prod_a,
                d->prod_b, d->prod_k, d->A_val, d->nnzA, d->vec[MADIPM_VEC_PR_DIAG], (int64_t)d->n, nz, d->kkt_nnz);
@@ -900,10 +928,12 @@ int32_t madipm_factorize(madipm_handle* h, int32_t* n_failed) {
     {
         Timer t(h, MADIPM_T_FACTOR);
         if (light) cudaEventRecord(d->ev0, d->stream);
-        CUDA_OK(h, cudaMemsetAsync(d->Lx, 0, sizeof(double) * B * d->lx_stride, d->stream));
         CUDA_OK(h, cudaMemsetAsync(d->fail, 0, sizeof(int) * B, d->stream));
-        LAUNCH(h, k_assemble_panels, dim3(vec_blocks(d->kkt_nnz) * 4, B), kVecThreads, 0, d->kkt_nnz, d->asm_map,
-               d->vec[MADIPM_VEC_KKT_NZVAL], d->kkt_nnz, d->Lx, d->lx_stride);
+        if (!d->image_valid) {                             // (with a valid panel image the tasks read P0 instead)
+            CUDA_OK(h, cudaMemsetAsync(d->Lx, 0, sizeof(double) * B * d->lx_stride, d->stream));
+            LAUNCH(h, k_assemble_panels, dim3(vec_blocks(d->kkt_nnz) * 4, B), kVecThreads, 0, d->kkt_nnz, d->asm_map,
+                   d->vec[MADIPM_VEC_KKT_NZVAL], d->kkt_nnz, d->Lx, d->lx_stride);
+        }
         for (const DeviceState::TreeSeg& sg : d->segs) {
             if (light && first_tree) cudaEventRecord(d->ev2, d->stream);
             if ((rc = launch_tree<0>(h, sg))) return rc;

@@ -66,6 +66,7 @@ struct TreeView {
     const SnMeta* meta;          // [number of tasks], in task order
     const ChildRec* crec;        // [nsuper - #roots], grouped by parent
     const int* par_pos;          // indexed like sn_rows
+    const double* image;         // factor: assembled panels to read instead of Lx (same layout), or null
     double* Cx;                  // [batch][cx_stride] contribution blocks
     int64_t cx_stride;
     double* cvec;                // [batch][cv_stride] forward-sweep contribution vectors, indexed like sn_rows
@@ -265,7 +266,8 @@ __device__ __forceinline__ void tree_factor_task(const TreeView& T, const SnMeta
 #endif
     TT(0);
     gsync<G>();                                           // the previous task of this group is done with the scratch
-    for (int c = t; c < nchunk; c += G) cp_async16(Ps + 2 * c, P + 2 * c);
+    const double* Psrc = T.image ? T.image + inst * F.lx_stride + m.xoff : P;
+    for (int c = t; c < nchunk; c += G) cp_async16(Ps + 2 * c, Psrc + 2 * c);
     // 1. extend-add: the parts of the children's contribution blocks that land in this panel
     bool waited = false;
     for (int base = 0; base < c1 - c0; base += kChildChunk) {
