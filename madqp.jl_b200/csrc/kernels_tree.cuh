@@ -312,25 +312,32 @@ __device__ __forceinline__ void tree_factor_task(const TreeView& T, const SnMeta
     for (int k = t; k < w; k += G) dk[k] = Ps[k * (h + 1)];
     gsync<G>();
     TT(3);
-    // 3. contribution block C = -L21 D L21' (packed lower triangle, 4 columns per warp pass, lanes over rows)
+    // 3. contribution block C = -L21 D L21' (packed lower triangle) on the FP64 tensor cores: the lower-triangular
+    //    8 x 8 blocks of C are dealt to the warps; a block is w / 4 DMMA.8x8x4 with both operands read straight from
+    //    the k-major panel in shared memory (A = rows of L21, B = rows of L21 scaled by D on the fly)
     double* Cs = Cx + m.coff;
-    for (int b0 = 4 * gw; b0 < nb; b0 += 4 * NW) {
-        const double* Lb = Ps + w + b0;
-        for (int a = b0 + lane; a < nb; a += 32) {
-            const double* La = Ps + w + a;
-            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-#pragma unroll 4
-            for (int k = 0; k < w; ++k) {
-                const double av = La[k * h] * dk[k];
-                acc0 = fma(av, Lb[k * h], acc0);
-                acc1 = fma(av, Lb[k * h + 1], acc1);          // columns past nb read scratch; never stored
-                acc2 = fma(av, Lb[k * h + 2], acc2);
-                acc3 = fma(av, Lb[k * h + 3], acc3);
+    {
+        const int fr = lane >> 2, fk = lane & 3;
+        const int nb8 = (nb + 7) >> 3;
+        int bi = 0, bj = 0;                               // block q of the row-major enumeration of the lower triangle
+        for (int q = 0, mine = gw; mine < nb8 * (nb8 + 1) / 2; mine += NW) {
+            while (q < mine) { if (++bj > bi) { ++bi; bj = 0; } ++q; }
+            const int ra = w + bi * 8 + fr, rb = w + bj * 8 + fr;
+            const bool ain = ra < h, bin = rb < h;
+            double c0 = 0.0, c1 = 0.0;
+            for (int k0 = 0; k0 < w; k0 += 4) {
+                const int kk = k0 + fk;
+                const bool kin = kk < w;
+                const double a = (kin && ain) ? Ps[ra + kk * h] : 0.0;
+                const double b = (kin && bin) ? Ps[rb + kk * h] * dk[kk] : 0.0;
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
             }
-            Cs[packed_col(b0, nb) + a] = -acc0;
-            if (b0 + 1 < nb && a >= b0 + 1) Cs[packed_col(b0 + 1, nb) + a] = -acc1;
-            if (b0 + 2 < nb && a >= b0 + 2) Cs[packed_col(b0 + 2, nb) + a] = -acc2;
-            if (b0 + 3 < nb && a >= b0 + 3) Cs[packed_col(b0 + 3, nb) + a] = -acc3;
+            const int arow = bi * 8 + fr, col0 = bj * 8 + 2 * fk;
+            if (arow < nb) {
+                if (arow >= col0) Cs[packed_col(col0, nb) + arow] = -c0;
+                if (arow >= col0 + 1) Cs[packed_col(col0 + 1, nb) + arow] = -c1;
+            }
         }
     }
     TT(4);
