@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmadipm_b200.so")
+# MADIPM_LIB: another build of the same library (instrumented development builds), never a different backend
+LIB_PATH = os.environ.get("MADIPM_LIB") or os.path.join(_HERE, "libmadipm_b200.so")
 
 OK, FACTOR_BREAKDOWN, NONFINITE, CUDA_ERROR, BAD_ARGUMENT, INTERNAL = range(6)
 KKT_K2, KKT_NORMAL = 0, 1

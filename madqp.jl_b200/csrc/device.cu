@@ -182,7 +182,15 @@ TreeView make_tree_view(const DeviceState& d) {
     T.xw = d.xw; T.xw_stride = d.N; T.bar = d.bar; T.B = d.B; T.tickets = nullptr; T.phase_cls = d.phase_cls;
     for (int c = 0; c < 4; ++c) { T.slice[c] = d.sym->tree_slice[c]; T.cap[c] = d.sym->tree_cap[c]; T.maxh[c] = d.sym->tree_maxh[c]; }
     T.maxw = d.tree_maxw;
-    { const char* e = std::getenv("MADIPM_DBG_SN"); T.dbg_sn = e ? std::atoi(e) : -1; }
+    {   // MADIPM_DBG_SN=a,b,...: supernodes whose stage clocks a MADIPM_TREE_TIMING build prints
+        for (int k = 0; k < 8; ++k) T.dbg_sn[k] = -1;
+        const char* e = std::getenv("MADIPM_DBG_SN");
+        for (int k = 0; e && *e && k < 8; ++k) {
+            T.dbg_sn[k] = std::atoi(e);
+            while (*e && *e != ',') ++e;
+            if (*e == ',') ++e;
+        }
+    }
     return T;
 }
 

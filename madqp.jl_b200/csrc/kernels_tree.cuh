@@ -79,8 +79,14 @@ struct TreeView {
     int B;
     int slice[4], cap[4], maxh[4];   // per class: doubles of shared memory per group, of which panel, of which rows
     int maxw;
-    int dbg_sn;                  // MADIPM_TREE_TIMING builds: supernode whose stage clocks are printed
+    int dbg_sn[8];               // MADIPM_TREE_TIMING builds: supernodes whose stage clocks are printed
 };
+__device__ __forceinline__ bool dbg_hit(const TreeView& T, int sn) {
+    bool hit = false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) hit |= T.dbg_sn[k] == sn;
+    return hit;
+}
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
@@ -97,8 +103,31 @@ __device__ __forceinline__ void gsync() {
     else asm volatile("bar.sync %0, %1;" ::"r"((G == 128 ? 1 : 3) + static_cast<int>(threadIdx.x) / G), "n"(G) : "memory");
 }
 
+// barrier among the first `nact` threads (a multiple of 32) of a task group: the warps of a group that still own rows of
+// the panel in dense_ldl.  The whole group -> its own barrier; one warp -> __syncwarp; in between -> an auxiliary named
+// barrier (7-8 for the two 128-thread groups of a block, 9 for a 256- or 1024-thread group; 64-thread groups never need one).
+template <int G>
+__device__ __forceinline__ void gsync_active(int nact) {
+    if (G == 32 || nact <= 32) __syncwarp();
+    else if (nact >= G) gsync<G>();
+    else asm volatile("bar.sync %0, %1;" ::"r"(G == 128 ? 7 + static_cast<int>(threadIdx.x) / G : 9), "r"(nact) : "memory");
+}
+
 // offset of column b inside a packed lower triangle of order nb, shifted so that [a] addresses row a >= b
 __device__ __forceinline__ int packed_col(int b, int nb) { return b * nb - ((b * (b + 1)) >> 1); }
+
+// packed lower triangle of order nb as one flat array: first entry of column b, and the column of entry e
+// (float square root, exact after one correction step: the discriminant is an integer below 2^24)
+__device__ __forceinline__ int tri_colstart(int b, int nb) { return b * nb - ((b * (b - 1)) >> 1); }
+__device__ __forceinline__ int tri_col(int e, int nb) {
+    const int two = 2 * nb + 1;
+    int b = static_cast<int>((static_cast<float>(two) - sqrtf(static_cast<float>(two * two - 8 * e))) * 0.5f);
+    b = max(0, min(b, nb - 1));
+    if (tri_colstart(b + 1, nb) <= e) ++b;
+    else if (tri_colstart(b, nb) > e) --b;
+    return b;
+}
+constexpr int kFlat = 4;         // contribution-block entries a thread keeps in flight
 
 template <class T>
 __device__ __forceinline__ T ldg_rec(const T* p) {        // 32- or 48-byte record through the read-only path (16-byte loads)
@@ -146,12 +175,8 @@ __device__ __forceinline__ void dense_ldl(double* Ps, int h, int w, int* fail, i
     constexpr int NB = 4;
     for (int jb = 0; jb < w; jb += NB) {
         LDL_PROBE(7);
-        if (jb + (t & ~31) >= h) {                        // this warp owns no row any more: only keep the barriers company
-            gsync<G>();
-            gsync<G>();
-            gsync<G>();
-            continue;
-        }
+        if (jb + (t & ~31) >= h) break;                   // this warp owns no row any more (nor will it later): it waits at the end
+        const int nact = min(G, (h - jb + 31) & ~31);     // threads of the warps that still own rows
         const int bw = min(NB, w - jb);
         const int o1 = bw > 1 ? h : 0, o2 = bw > 2 ? 2 * h : 0, o3 = bw > 3 ? 3 * h : 0;   // missing columns alias column 0
         // 1. left-looking update of this block's entries of my rows (the first row stays in registers)
@@ -179,7 +204,7 @@ __device__ __forceinline__ void dense_ldl(double* Ps, int h, int w, int* fail, i
             }
         }
         LDL_PROBE(0);
-        gsync<G>();
+        gsync_active<G>(nact);
         LDL_PROBE(1);
         // 2. diagonal block (identity-padded when fewer than 4 columns are left), redundantly in every thread
         const double* Db = Ps + jb * (h + 1);
@@ -198,7 +223,7 @@ __device__ __forceinline__ void dense_ldl(double* Ps, int h, int w, int* fail, i
         const double l32 = a32 * r2;
         LDL_PROBE(2);
         LDL_PROBE(3);
-        gsync<G>();                                       // everyone has read the block before the pivot rows are rewritten
+        gsync_active<G>(nact);                            // everyone has read the block before the pivot rows are rewritten
         LDL_PROBE(4);
         // 3. my rows against the block, one branch-free path for pivot rows and rows below: forward substitution
         //    gives v = l D; column c gets v_c / d_c left of the row's diagonal and v_c (= d) on it.  Rows that
@@ -229,9 +254,10 @@ __device__ __forceinline__ void dense_ldl(double* Ps, int h, int w, int* fail, i
             }
         }
         LDL_PROBE(5);
-        gsync<G>();
+        gsync_active<G>(nact);
         LDL_PROBE(6);
     }
+    gsync<G>();                                           // the warps that ran out of rows rejoin here
     // pivots: a zero / non-finite one poisons everything after it, so one pass over D at the end is enough
     bool bad = false;
     for (int k = t; k < w; k += G) bad |= bad_pivot(Ps[k * (h + 1)]);
@@ -260,7 +286,7 @@ __device__ __forceinline__ void tree_factor_task(const TreeView& T, const SnMeta
     const int nchunk = (np + 1) >> 1;
 #ifdef MADIPM_TREE_TIMING
     long long tt[10];
-#define TT(k) do { if (m.sn == T.dbg_sn && t == 0) tt[k] = clock64(); } while (0)
+#define TT(k) do { if (t == 0 && dbg_hit(T, m.sn)) tt[k] = clock64(); } while (0)
 #else
 #define TT(k)
 #endif
@@ -276,27 +302,28 @@ __device__ __forceinline__ void tree_factor_task(const TreeView& T, const SnMeta
         for (int ci = 0; ci < n; ++ci) {
             const ChildRec r = cs[ci];
             if (!r.pull) continue;                        // that child scattered its block itself
+            // The block is one flat array (columns b < nbp, the ones that land in this panel, come first): thread t
+            // takes entries t, t + G, ... with kFlat loads in flight, whatever the shape of the triangle.
             const int* pos = T.par_pos + r.below;
             const double* Cc = Cx + r.coff;
-            // lanes own rows (32 per chunk), warps take columns four at a time so that the loads overlap
-            for (int a0 = 0; a0 < r.nb; a0 += 32) {
-                const int a = a0 + lane;
-                const int pa = a < r.nb ? __ldg(pos + a) : 0;
-                const int bend = min(r.nbp, a0 + 32);              // columns b <= a only
-                for (int b0 = gw; b0 < bend; b0 += 4 * NW) {
-                    int dsti[4];
-                    double v[4];
+            const int e1 = tri_colstart(r.nbp, r.nb);
+            for (int e0 = t; e0 < e1; e0 += kFlat * G) {
+                int dsti[kFlat];
+                double v[kFlat];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int b = b0 + u * NW;
-                        const bool ok = b < bend && a >= b && a < r.nb;
-                        dsti[u] = ok ? pa + __ldg(pos + b) * h : -1;
-                        v[u] = ok ? __ldcg(Cc + packed_col(b, r.nb) + a) : 0.0;
+                for (int u = 0; u < kFlat; ++u) {
+                    const int e = e0 + u * G;
+                    dsti[u] = -1;
+                    v[u] = 0.0;
+                    if (e < e1) {
+                        v[u] = __ldcg(Cc + e);
+                        const int b = tri_col(e, r.nb);
+                        dsti[u] = __ldg(pos + b + e - tri_colstart(b, r.nb)) + __ldg(pos + b) * h;
                     }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (dsti[u] >= 0) Ps[dsti[u]] += v[u];
                 }
+#pragma unroll
+                for (int u = 0; u < kFlat; ++u)
+                    if (dsti[u] >= 0) Ps[dsti[u]] += v[u];
             }
             gsync<G>();
         }
@@ -304,9 +331,8 @@ __device__ __forceinline__ void tree_factor_task(const TreeView& T, const SnMeta
     if (!waited) { cp_async_wait_all(); gsync<G>(); }
     TT(1);
     // 2. dense LDL' of the panel: D on the diagonal of the top w x w block, unit-lower L elsewhere
-    dense_ldl<G>(Ps, h, w, F.fail + inst, t);
+    dense_ldl<G>(Ps, h, w, F.fail + inst, t);            // ends with a barrier of the whole group
     TT(2);
-    gsync<G>();
     for (int c = t; c < nchunk; c += G) reinterpret_cast<double2*>(P)[c] = reinterpret_cast<const double2*>(Ps)[c];
     if (nb == 0) return;
     for (int k = t; k < w; k += G) dk[k] = Ps[k * (h + 1)];
@@ -351,34 +377,34 @@ __device__ __forceinline__ void tree_factor_task(const TreeView& T, const SnMeta
             gsync<G>();                                   // C (or the previous child's additions) is in place
             const int* pos = T.par_pos + r.below;
             const double* Cc = Cx + r.coff;
-            for (int a0 = (r.nbp >> 5) << 5; a0 < r.nb; a0 += 32) {
-                const int a = a0 + lane;
-                const int pa = a < r.nb ? __ldg(pos + a) - w : 0;
-                const int bend = min(r.nb, a0 + 32);
-                for (int b0 = r.nbp + gw; b0 < bend; b0 += 4 * NW) {
-                    double* dst[4];
-                    double v[4];
+            const int e1 = tri_colstart(r.nb, r.nb);
+            for (int e0 = tri_colstart(r.nbp, r.nb) + t; e0 < e1; e0 += kFlat * G) {
+                int off[kFlat];
+                double v[kFlat];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int b = b0 + u * NW;
-                        const bool ok = b < bend && a >= b && a < r.nb;
-                        dst[u] = ok ? Cs + packed_col(__ldg(pos + b) - w, nb) + pa : nullptr;
-                        v[u] = ok ? __ldcg(Cc + packed_col(b, r.nb) + a) : 0.0;
+                for (int u = 0; u < kFlat; ++u) {
+                    const int e = e0 + u * G;
+                    off[u] = -1;
+                    v[u] = 0.0;
+                    if (e < e1) {
+                        v[u] = __ldcg(Cc + e);
+                        const int b = tri_col(e, r.nb);
+                        off[u] = packed_col(__ldg(pos + b) - w, nb) + __ldg(pos + b + e - tri_colstart(b, r.nb)) - w;
                     }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (dst[u]) v[u] += __ldcg(dst[u]);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (dst[u]) *dst[u] = v[u];
                 }
+#pragma unroll
+                for (int u = 0; u < kFlat; ++u)
+                    if (off[u] >= 0) v[u] += __ldcg(Cs + off[u]);
+#pragma unroll
+                for (int u = 0; u < kFlat; ++u)
+                    if (off[u] >= 0) Cs[off[u]] = v[u];
             }
         }
     }
     TT(5);
 #ifdef MADIPM_TREE_TIMING
-    if (m.sn == T.dbg_sn && t == 0)
-        printf("sn %d G %d w %d h %d children %d | stage+extend %lld ldl %lld store %lld schur %lld pass %lld cycles\n", m.sn, G, w, h,
+    if (t == 0 && dbg_hit(T, m.sn))
+        printf("factor sn %d G %d w %d h %d children %d | stage+extend %lld ldl %lld store %lld schur %lld pass %lld cycles\n", m.sn, G, w, h,
                c1 - c0, tt[1] - tt[0], tt[2] - tt[1], tt[3] - tt[2], tt[4] - tt[3], tt[5] - tt[4]);
 #endif
     // 5. under a big parent: scatter C into the ancestors' panels (the big kernels read panels only)
@@ -414,6 +440,10 @@ __device__ __forceinline__ void tree_forward_task(const TreeView& T, const SnMet
     double* sy = su + maxh;
     ChildRec* cs = reinterpret_cast<ChildRec*>(sy + ((T.maxw + 1) & ~1));
     const int nchunk = (h * w + 1) >> 1;
+#ifdef MADIPM_TREE_TIMING
+    long long tt[6];
+#endif
+    TT(0);
     gsync<G>();
     for (int c = t; c < nchunk; c += G) cp_async16(Ps + 2 * c, P + 2 * c);
     for (int j = t; j < w; j += G) sy[j] = __ldcg(xw + fc + j);
@@ -446,16 +476,43 @@ __device__ __forceinline__ void tree_forward_task(const TreeView& T, const SnMet
             }
         }
     }
+    TT(1);
     cp_async_wait_all();
     gsync<G>();
+    TT(2);
     if (gw == 0) {                                        // unit-lower triangular solve, one warp
-        for (int j = 0; j + 1 < w; ++j) {
-            const double yj = sy[j];
-            for (int i = j + 1 + lane; i < w; i += 32) sy[i] -= Ps[i + j * h] * yj;
-            __syncwarp();
+        if (w <= 64) {
+            // y in registers (lane l holds y[l] and y[l + 32]); per column one shuffle and one FMA on the dependent
+            // chain, the entries of L come from shared memory ahead of it
+            double y0 = lane < w ? sy[lane] : 0.0, y1 = lane + 32 < w ? sy[lane + 32] : 0.0;
+            const double* Pl = Ps + lane;
+            const int w0 = min(w, 32);
+#pragma unroll 4
+            for (int j = 0; j < w0; ++j) {
+                const double l0 = (lane > j && lane < w) ? Pl[j * h] : 0.0;
+                const double l1 = lane + 32 < w ? Pl[32 + j * h] : 0.0;
+                const double yj = __shfl_sync(0xffffffffu, y0, j);
+                y0 = fma(-l0, yj, y0);
+                y1 = fma(-l1, yj, y1);
+            }
+#pragma unroll 4
+            for (int j = 32; j < w; ++j) {
+                const double l1 = (lane + 32 > j && lane + 32 < w) ? Pl[32 + j * h] : 0.0;
+                const double yj = __shfl_sync(0xffffffffu, y1, j - 32);
+                y1 = fma(-l1, yj, y1);
+            }
+            if (lane < w) sy[lane] = y0;
+            if (lane + 32 < w) sy[lane + 32] = y1;
+        } else {
+            for (int j = 0; j + 1 < w; ++j) {
+                const double yj = sy[j];
+                for (int i = j + 1 + lane; i < w; i += 32) sy[i] -= Ps[i + j * h] * yj;
+                __syncwarp();
+            }
         }
     }
     gsync<G>();
+    TT(3);
     const bool pull = m.kind == 0;
     const int* rows = F.sn_rows + m.rowptr + w;
     for (int i = t; i < nb; i += G) {
@@ -467,6 +524,12 @@ __device__ __forceinline__ void tree_forward_task(const TreeView& T, const SnMet
         else atomicAdd(xw + __ldg(rows + i), -acc);
     }
     for (int j = t; j < w; j += G) xw[fc + j] = sy[j] / Ps[j * (h + 1)];
+    TT(4);
+#ifdef MADIPM_TREE_TIMING
+    if (t == 0 && dbg_hit(T, m.sn))
+        printf("forward sn %d G %d w %d h %d children %d | children %lld panel-wait %lld tri %lld matvec+store %lld cycles\n", m.sn, G, w, h,
+               c1 - c0, tt[1] - tt[0], tt[2] - tt[1], tt[3] - tt[2], tt[4] - tt[3]);
+#endif
 }
 
 // ---- backward sweep: x = L^-T xw -----------------------------------------------------------------------------
@@ -485,6 +548,10 @@ __device__ __forceinline__ void tree_backward_task(const TreeView& T, const SnMe
     double* sx = Ps + cap;
     double* st = sx + maxh;
     const int nchunk = (h * w + 1) >> 1;
+#ifdef MADIPM_TREE_TIMING
+    long long tt[6];
+#endif
+    TT(0);
     gsync<G>();
     for (int c = t; c < nchunk; c += G) cp_async16(Ps + 2 * c, P + 2 * c);
     const int* rows = F.sn_rows + m.rowptr + w;
@@ -492,6 +559,7 @@ __device__ __forceinline__ void tree_backward_task(const TreeView& T, const SnMe
     for (int i = t; i < nb; i += G) sx[i] = __ldcg(xw + __ldg(rows + i));
     cp_async_wait_all();
     gsync<G>();
+    TT(1);
     for (int j = gw; j < w; j += NW) {
         const double* Lj = Ps + w + j * h;
         double acc = 0.0;
@@ -501,15 +569,44 @@ __device__ __forceinline__ void tree_backward_task(const TreeView& T, const SnMe
         if (lane == 0) st[j] -= acc;
     }
     gsync<G>();
-    if (gw == 0) {
-        for (int j = w - 1; j > 0; --j) {
-            const double xj = st[j];
-            for (int k = lane; k < j; k += 32) st[k] -= Ps[j + k * h] * xj;
-            __syncwarp();
+    TT(2);
+    if (gw == 0) {                                        // unit-upper triangular solve with L11', one warp
+        if (w <= 64) {
+            // x in registers (lane l holds x[l] and x[l + 32]); L11'[k][j] = L[j][k] = Ps[j + k * h]
+            double x0 = lane < w ? st[lane] : 0.0, x1 = lane + 32 < w ? st[lane + 32] : 0.0;
+            const double* Pk0 = Ps + lane * h;
+            const double* Pk1 = Ps + (lane + 32) * h;
+#pragma unroll 4
+            for (int j = w - 1; j >= 32; --j) {
+                const double l0 = Pk0[j];                                      // lane < 32 <= j < w
+                const double l1 = lane + 32 < j ? Pk1[j] : 0.0;
+                const double xj = __shfl_sync(0xffffffffu, x1, j - 32);
+                x0 = fma(-l0, xj, x0);
+                x1 = fma(-l1, xj, x1);
+            }
+#pragma unroll 4
+            for (int j = min(w, 32) - 1; j > 0; --j) {
+                const double l0 = lane < j ? Pk0[j] : 0.0;
+                const double xj = __shfl_sync(0xffffffffu, x0, j);
+                x0 = fma(-l0, xj, x0);
+            }
+            if (lane < w) st[lane] = x0;
+            if (lane + 32 < w) st[lane + 32] = x1;
+        } else {
+            for (int j = w - 1; j > 0; --j) {
+                const double xj = st[j];
+                for (int k = lane; k < j; k += 32) st[k] -= Ps[j + k * h] * xj;
+                __syncwarp();
+            }
         }
     }
     gsync<G>();
+    TT(3);
     for (int j = t; j < w; j += G) xw[fc + j] = st[j];
+#ifdef MADIPM_TREE_TIMING
+    if (t == 0 && dbg_hit(T, m.sn))
+        printf("backward sn %d G %d w %d h %d | load %lld matvec %lld tri %lld cycles\n", m.sn, G, w, h, tt[1] - tt[0], tt[2] - tt[1], tt[3] - tt[2]);
+#endif
 }
 
 // ---- grid barrier (cooperative launch: every block is resident) -------------------------------------------

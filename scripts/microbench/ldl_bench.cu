@@ -15,7 +15,7 @@ __global__ void kb(double* P, int h, int w, int* fail, long long* cyc, int reps)
     extern __shared__ double2 sm2[];
     double* Ps = reinterpret_cast<double*>(sm2);
     const int t = threadIdx.x % G;
-    if (G == 32 && threadIdx.x >= 32) return;
+    if (G < 256 && threadIdx.x >= G) return;
     long long best = 1LL << 60;
     for (int r = 0; r < reps; ++r) {
         for (int i = t; i < h * w; i += G) Ps[i] = P[i];
@@ -30,7 +30,7 @@ __global__ void kb(double* P, int h, int w, int* fail, long long* cyc, int reps)
     for (int i = t; i < h * w; i += G) P[i] = Ps[i];
 }
 int main() {
-    int shapes[][2] = {{37, 16}, {70, 64}, {109, 47}, {16, 4}, {24, 8}};
+    int shapes[][2] = {{37, 16}, {72, 64}, {109, 47}, {73, 47}, {65, 25}, {16, 4}, {24, 8}};
     for (auto& sh : shapes) {
         int h = sh[0], w = sh[1];
         std::vector<double> A(h * w), A0;
@@ -38,10 +38,12 @@ int main() {
         A0 = A;
         double* dP; int* fail; long long* cyc;
         cudaMalloc(&dP, A.size() * 8); cudaMalloc(&fail, 4); cudaMalloc(&cyc, 8); cudaMemset(fail, 0, 4);
-        for (int G : {256, 32}) {
+        for (int G : {1024, 256, 128, 32}) {
             cudaMemcpy(dP, A0.data(), A.size() * 8, cudaMemcpyHostToDevice);
             size_t smem = (h * w + 64) * 8;
-            if (G == 256) { cudaFuncSetAttribute(kb<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); kb<256><<<1, 256, smem>>>(dP, h, w, fail, cyc, 5); }
+            if (G == 1024) { cudaFuncSetAttribute(kb<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); kb<1024><<<1, 1024, smem>>>(dP, h, w, fail, cyc, 5); }
+            else if (G == 128) { cudaFuncSetAttribute(kb<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); kb<128><<<1, 256, smem>>>(dP, h, w, fail, cyc, 5); }
+            else if (G == 256) { cudaFuncSetAttribute(kb<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); kb<256><<<1, 256, smem>>>(dP, h, w, fail, cyc, 5); }
             else { cudaFuncSetAttribute(kb<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); kb<32><<<1, 32, smem>>>(dP, h, w, fail, cyc, 5); }
             cudaError_t e = cudaDeviceSynchronize();
             long long c; cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
