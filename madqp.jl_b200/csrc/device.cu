@@ -82,6 +82,11 @@ struct DeviceState {
     double* P0 = nullptr;
     int64_t* diag_lx = nullptr;
     bool image_valid = false;
+    // With a valid image, build_kkt writes only `dperm` = the per-iteration diagonals (pr_diag | du_diag) in PIVOT order
+    // (one coalesced pass); the factor task of a supernode adds its w entries to the diagonal of the staged panel.
+    // The diagonal slots of KKT_NZVAL are then brought up to date only when somebody looks at that vector.
+    double* dperm = nullptr;
+    bool nzval_diag_stale = false;
     int *perm = nullptr, *iperm = nullptr;
     int* fail = nullptr;
     std::vector<int> h_fail;
@@ -178,7 +183,7 @@ TreeView make_tree_view(const DeviceState& d) {
     T.F = make_factor_view(d, 0);
     T.meta = d.sn_meta; T.crec = d.child_rec; T.par_pos = d.par_pos;
     T.Cx = d.Cx; T.cx_stride = d.cx_stride; T.cvec = d.cvec; T.cv_stride = d.cv_stride;
-    T.image = nullptr;
+    T.image = nullptr; T.dperm = nullptr;
     T.xw = d.xw; T.xw_stride = d.N; T.bar = d.bar; T.B = d.B; T.tickets = nullptr; T.phase_cls = d.phase_cls;
     for (int c = 0; c < 4; ++c) { T.slice[c] = d.sym->tree_slice[c]; T.cap[c] = d.sym->tree_cap[c]; T.maxh[c] = d.sym->tree_maxh[c]; }
     T.maxw = d.tree_maxw;
@@ -253,18 +258,27 @@ __global__ void k_scatter_add(int64_t n, const int* __restrict__ map, const doub
 // (transfer! semantics, /root/reference/scripts/cuda_wrapper.jl:17-28, restricted to the entries that moved)
 __global__ void k_build_kkt_k2(int n, int m, const int* __restrict__ diag_slot, const double* __restrict__ const_diag,
                                const double* __restrict__ pr_diag, const double* __restrict__ du_diag,
-                               double* __restrict__ nzval, int64_t nz_stride, const int64_t* __restrict__ diag_lx,
-                               double* __restrict__ image, int64_t image_stride) {
+                               double* __restrict__ nzval, int64_t nz_stride) {
     const int inst = blockIdx.y;
     const_diag += static_cast<int64_t>(inst) * (n + m);
     pr_diag += static_cast<int64_t>(inst) * n;
     du_diag += static_cast<int64_t>(inst) * m;
     nzval += inst * nz_stride;
-    if (image) image += inst * image_stride;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n + m; i += gridDim.x * blockDim.x) {
-        const double v = ((i < n) ? pr_diag[i] : du_diag[i - n]) + const_diag[i];
-        nzval[diag_slot[i]] = v;
-        if (image) image[diag_lx[i]] = v;                 // the same entry in the panel image (see DeviceState::P0)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n + m; i += gridDim.x * blockDim.x)
+        nzval[diag_slot[i]] = ((i < n) ? pr_diag[i] : du_diag[i - n]) + const_diag[i];
+}
+
+// K2a with a panel image: dperm[k] = (pr_diag | du_diag)[perm[k]], k in pivot order (coalesced writes, gathers from
+// two vectors that stay in L2)
+__global__ void k_build_kkt_k2_perm(int n, int m, const int* __restrict__ perm, const double* __restrict__ pr_diag,
+                                    const double* __restrict__ du_diag, double* __restrict__ dperm) {
+    const int inst = blockIdx.y;
+    pr_diag += static_cast<int64_t>(inst) * n;
+    du_diag += static_cast<int64_t>(inst) * m;
+    dperm += static_cast<int64_t>(inst) * (n + m);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n + m; k += gridDim.x * blockDim.x) {
+        const int i = __ldg(perm + k);
+        dperm[k] = (i < n) ? pr_diag[i] : du_diag[i - n];
     }
 }
 
@@ -307,7 +321,7 @@ int32_t launch_tree(madipm_handle* h, const DeviceState::TreeSeg& sg) {
     DeviceState* d = h->dev;
     TreeView T = make_tree_view(*d);
     T.tickets = d->tickets[OP];
-    if (OP == 0 && d->image_valid) T.image = d->P0;
+    if (OP == 0 && d->image_valid) { T.image = d->P0; T.dperm = d->dperm; }
     const bool reverse = OP == 2;
     auto bottom = [&]() -> int32_t {
         if (sg.split <= sg.ph0 || sg.grid[OP] <= 0) return MADIPM_OK;
@@ -511,6 +525,7 @@ int32_t device_create(madipm_handle* h) {
         for (int i = 0; i < d->N; ++i) diag_lx[i] = s.asm_map[p.diag_slot[i]];
         UP(int64_t, diag_lx, diag_lx);
         if ((rc = dev_alloc(h, &d->P0, static_cast<size_t>(h->cfg.batch) * s.nnz_stored))) return rc;
+        if ((rc = dev_alloc(h, &d->dperm, static_cast<size_t>(h->cfg.batch) * d->N))) return rc;
     }
 #undef UP
     if ((rc = dev_alloc(h, &d->Lx, static_cast<size_t>(B) * d->lx_stride))) return rc;
@@ -802,12 +817,22 @@ int32_t madipm_vec_len(const madipm_handle* h, int32_t vec, int64_t* len) {
     return MADIPM_OK;
 }
 
+// KKT_NZVAL is about to be read (or handed out): write the diagonal slots build_kkt skipped while the panel image was in use
+static int32_t refresh_nzval_diag(madipm_handle* h) {
+    DeviceState* d = h->dev;
+    if (!d->nzval_diag_stale) return MADIPM_OK;
+    LAUNCH(h, k_build_kkt_k2, dim3(vec_blocks(d->N), d->B), kVecThreads, 0, d->n, d->m, d->diag_slot, d->const_diag,
+           d->vec[MADIPM_VEC_PR_DIAG], d->vec[MADIPM_VEC_DU_DIAG], d->vec[MADIPM_VEC_KKT_NZVAL], d->kkt_nnz);
+    d->nzval_diag_stale = false;
+    return MADIPM_OK;
+}
+
 int32_t madipm_vec_set(madipm_handle* h, int32_t vec, const double* host) {
     int32_t rc = check(h);
     if (rc) return rc;
     if (vec < 0 || vec >= MADIPM_VEC_COUNT || !host) return MADIPM_BAD_ARGUMENT;
     DeviceState* d = h->dev;
-    if (vec == MADIPM_VEC_KKT_NZVAL) d->image_valid = false;   // the caller owns the KKT values now: assemble from nzval
+    if (vec == MADIPM_VEC_KKT_NZVAL) { d->image_valid = false; d->nzval_diag_stale = false; }   // the caller owns the KKT values now: assemble from nzval
     CUDA_OK(h, cudaMemcpyAsync(d->vec[vec], host, sizeof(double) * d->B * d->veclen[vec], cudaMemcpyHostToDevice, d->stream));
     return MADIPM_OK;
 }
@@ -817,6 +842,7 @@ int32_t madipm_vec_get(madipm_handle* h, int32_t vec, double* host) {
     if (rc) return rc;
     if (vec < 0 || vec >= MADIPM_VEC_COUNT || !host) return MADIPM_BAD_ARGUMENT;
     DeviceState* d = h->dev;
+    if (vec == MADIPM_VEC_KKT_NZVAL && (rc = refresh_nzval_diag(h))) return rc;
     CUDA_OK(h, cudaMemcpyAsync(host, d->vec[vec], sizeof(double) * d->B * d->veclen[vec], cudaMemcpyDeviceToHost, d->stream));
     CUDA_OK(h, cudaStreamSynchronize(d->stream));
     return MADIPM_OK;
@@ -827,7 +853,7 @@ int32_t madipm_vec_fill(madipm_handle* h, int32_t vec, double value) {
     if (rc) return rc;
     if (vec < 0 || vec >= MADIPM_VEC_COUNT) return MADIPM_BAD_ARGUMENT;
     DeviceState* d = h->dev;
-    if (vec == MADIPM_VEC_KKT_NZVAL) d->image_valid = false;
+    if (vec == MADIPM_VEC_KKT_NZVAL) { d->image_valid = false; d->nzval_diag_stale = false; }
     LAUNCH(h, k_fill, dim3(vec_blocks(d->veclen[vec]), d->B), kVecThreads, 0, d->veclen[vec], d->vec[vec], d->veclen[vec], value);
     return MADIPM_OK;
 }
@@ -836,7 +862,10 @@ int32_t madipm_vec_device_ptr(madipm_handle* h, int32_t vec, void** dev) {
     int32_t rc = check(h);
     if (rc) return rc;
     if (vec < 0 || vec >= MADIPM_VEC_COUNT || !dev) return MADIPM_BAD_ARGUMENT;
-    if (vec == MADIPM_VEC_KKT_NZVAL) h->dev->image_valid = false;   // may be written through the pointer
+    if (vec == MADIPM_VEC_KKT_NZVAL) {                          // may be read or written through the pointer
+        if ((rc = refresh_nzval_diag(h))) return rc;
+        h->dev->image_valid = false;
+    }
     *dev = h->dev->vec[vec];
     return MADIPM_OK;
 }
@@ -855,7 +884,8 @@ int32_t madipm_vec_copy(madipm_handle* h, int32_t dst, int32_t src) {
     if (rc) return rc;
     DeviceState* d = h->dev;
     if (dst < 0 || src < 0 || dst >= MADIPM_VEC_COUNT || src >= MADIPM_VEC_COUNT || d->veclen[dst] != d->veclen[src]) return MADIPM_BAD_ARGUMENT;
-    if (dst == MADIPM_VEC_KKT_NZVAL) d->image_valid = false;
+    if (src == MADIPM_VEC_KKT_NZVAL && (rc = refresh_nzval_diag(h))) return rc;
+    if (dst == MADIPM_VEC_KKT_NZVAL) { d->image_valid = false; d->nzval_diag_stale = false; }
     CUDA_OK(h, cudaMemcpyAsync(d->vec[dst], d->vec[src], sizeof(double) * d->B * d->veclen[dst], cudaMemcpyDeviceToDevice, d->stream));
     return MADIPM_OK;
 }
@@ -915,10 +945,14 @@ int32_t madipm_build_kkt(madipm_handle* h) {
     DeviceState* d = h->dev;
     Timer t(h, MADIPM_T_ASSEMBLY);
     double* nz = d->vec[MADIPM_VEC_KKT_NZVAL];
-    if (d->kind == 0) {
+    if (d->kind == 0 && d->image_valid) {
+        LAUNCH(h, k_build_kkt_k2_perm, dim3(vec_blocks(d->N), d->B), kVecThreads, 0, d->n, d->m, d->perm,
+               d->vec[MADIPM_VEC_PR_DIAG], d->vec[MADIPM_VEC_DU_DIAG], d->dperm);
+        d->nzval_diag_stale = true;
+    } else if (d->kind == 0) {
         LAUNCH(h, k_build_kkt_k2, dim3(vec_blocks(d->N), d->B), kVecThreads, 0, d->n, d->m, d->diag_slot, d->const_diag,
-               d->vec[MADIPM_VEC_PR_DIAG], d->vec[MADIPM_VEC_DU_DIAG], nz, d->kkt_nnz, d->diag_lx,
-               d->image_valid ? d->P0 : nullptr, d->lx_stride);
+               d->vec[MADIPM_VEC_PR_DIAG], d->vec[MADIPM_VEC_DU_DIAG], nz, d->kkt_nnz);
+        d->nzval_diag_stale = false;
     } else {
         LAUNCH(h, k_assemble_normal, dim3(vec_blocks(d->kkt_nnz), d->B), kVecThreads, 0, d->kkt_nnz, d->prod_ptr, d->prod_a,
                d->prod_b, d->prod_k, d->A_val, d->nnzA, d->vec[MADIPM_VEC_PR_DIAG], (int64_t)d->n, nz, d->kkt_nnz);

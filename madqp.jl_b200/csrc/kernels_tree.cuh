@@ -67,6 +67,7 @@ struct TreeView {
     const ChildRec* crec;        // [nsuper - #roots], grouped by parent
     const int* par_pos;          // indexed like sn_rows
     const double* image;         // factor: assembled panels to read instead of Lx (same layout), or null
+    const double* dperm;         // ... and the per-iteration diagonal in pivot order to add to them ([batch][xw_stride]), or null
     double* Cx;                  // [batch][cx_stride] contribution blocks
     int64_t cx_stride;
     double* cvec;                // [batch][cv_stride] forward-sweep contribution vectors, indexed like sn_rows
@@ -294,6 +295,10 @@ __device__ __forceinline__ void tree_factor_task(const TreeView& T, const SnMeta
     gsync<G>();                                           // the previous task of this group is done with the scratch
     const double* Psrc = T.image ? T.image + inst * F.lx_stride + m.xoff : P;
     for (int c = t; c < nchunk; c += G) cp_async16(Ps + 2 * c, Psrc + 2 * c);
+    // this iteration's diagonal of my columns (the image holds the constant part), added before the LDL'
+    const double* dpm = T.dperm ? T.dperm + inst * T.xw_stride + m.fc : nullptr;
+    const double dg0 = (dpm && t < w) ? __ldcg(dpm + t) : 0.0;
+    const double dg1 = (dpm && t + G < w) ? __ldcg(dpm + t + G) : 0.0;
     // 1. extend-add: the parts of the children's contribution blocks that land in this panel
     bool waited = false;
     for (int base = 0; base < c1 - c0; base += kChildChunk) {
@@ -329,6 +334,11 @@ __device__ __forceinline__ void tree_factor_task(const TreeView& T, const SnMeta
         }
     }
     if (!waited) { cp_async_wait_all(); gsync<G>(); }
+    if (dpm) {                                            // entry (k, k) is next touched by thread k (block 0) or after a barrier
+        if (t < w) Ps[t * (h + 1)] += dg0;
+        if (t + G < w) Ps[(t + G) * (h + 1)] += dg1;
+        for (int k = t + 2 * G; k < w; k += G) Ps[k * (h + 1)] += __ldcg(dpm + k);
+    }
     TT(1);
     // 2. dense LDL' of the panel: D on the diagonal of the top w x w block, unit-lower L elsewhere
     dense_ldl<G>(Ps, h, w, F.fail + inst, t);            // ends with a barrier of the whole group

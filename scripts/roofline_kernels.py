@@ -14,7 +14,8 @@ from madqp_jl_b200 import _lib
 from madqp_jl_b200.mpc import MPCSolver, FixedRegularization
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "C3"
-qps, kkt, name = bench.make_workload(wl)
+scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0      # > 1: the same generator at a multiple of the size (launch overhead amortised)
+qps, kkt, name = bench.make_workload(wl, scale)
 qp = qps[0]
 s = MPCSolver(qp, kkt_system=kkt, regularization=FixedRegularization(1e-8, -1e-8))
 s.prepare_host(); s.upload(); s.start(); s._update_regularization()
@@ -37,7 +38,7 @@ KERNELS = {
     "spmv_AT  (k_spmv, y = A'x)": (lambda: h.spmv(_lib.OP_AT, "JACL", "Y"), spmv_bytes(nnzA, n, m)),
     "spmv_Q   (k_spmv, y = Q x)": (lambda: h.spmv(_lib.OP_Q, "F", "X"), spmv_bytes(nnzQ, n, n)) if nnzQ else None,
     "assembly K1 (k_set_aug_diagonal_reg)": (lambda: h.set_aug_diagonal_reg(1e-8, -1e-8), 8 * (5 * (nlb + nub) + 2 * n + m) + 8 * (nlb + nub) + 8 * n),
-    "assembly K2a (k_build_kkt_k2)": (lambda: h.build_kkt(), 28 * (n + m)) if kkt == "K2" else (lambda: h.build_kkt(), 12 * nnzA + 8 * n + 12 * info["kkt_nnz"] + 12 * info["n_products"]),
+    "assembly K2a (k_build_kkt_k2_perm)": (lambda: h.build_kkt(), 20 * (n + m)) if kkt == "K2" else (lambda: h.build_kkt(), 12 * nnzA + 8 * n + 12 * info["kkt_nnz"] + 12 * info["n_products"]),
     "rhs K9 (k_set_rhs predictive)": (lambda: h.set_predictive_rhs(), 8 * (5 * n + 2 * m + 4 * (nlb + nub)) + 4 * (nlb + nub)),
     "kkt_mul K5 (3 spmv + tail)": (lambda: h.kkt_mul("W1", "D", -1.0, 1.0), spmv_bytes(nnzA, m, n) + spmv_bytes(nnzA, n, m) + (spmv_bytes(nnzQ, n, n) if nnzQ else 0) + 8 * 4 * L),
     "eval_model K8 (k_eval_model)": (lambda: h.eval_model(0.0, want_obj=False), spmv_bytes(nnzA, m, n) + spmv_bytes(nnzQ, n, n) + 8 * (2 * n + m)),
@@ -76,7 +77,7 @@ for kname, spec in KERNELS.items():
         fn()
     h.synchronize()
     tc, tw = timed(fn, True), timed(fn, False)
-    print(json.dumps(dict(workload=wl, kernel=kname, algorithmic_MB=nbytes / 1e6, cold_us=tc * 1e6, warm_us=tw * 1e6,
+    print(json.dumps(dict(workload=wl if scale == 1.0 else f"{wl} x{scale:g}", kernel=kname, algorithmic_MB=nbytes / 1e6, cold_us=tc * 1e6, warm_us=tw * 1e6,
                           cold_GBs=nbytes / tc / 1e9, warm_GBs=nbytes / tw / 1e9, peak_GBs=peak,
                           frac_cold=nbytes / tc / 1e9 / peak, frac_warm=nbytes / tw / 1e9 / peak)), flush=True)
 s.close()
