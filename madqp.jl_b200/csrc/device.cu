@@ -52,6 +52,7 @@ struct DeviceState {
     bool big_use_panel = false;
     size_t smem_big_panel = 0;
     int* big_sn = nullptr;
+    int *upd_lim = nullptr, *upd_nsrc = nullptr, *upd_src = nullptr;   // per entry of big_sn: see the grouping in device_create
     double *big_tbuf = nullptr, *big_zbuf = nullptr;
     int* big_done = nullptr;           // per (instance, big supernode of a height): blocks finished (self-resetting)
     int big_zstride = 0;
@@ -421,6 +422,51 @@ int32_t device_create(madipm_handle* h) {
     d->kkt_nnz = p.kkt_colptr.back();
     d->lx_stride = s.nnz_stored;
     d->nsuper = s.nsuper; d->n_levels = s.n_levels;
+    // Update groups of the big supernodes.  A wide fundamental supernode that was cut into pieces of kBigTile columns is a
+    // chain s1 -> s2 -> ... whose row structures nest exactly (rows below s_q = columns of s_q+1 + rows below s_q+1).
+    // Up to kBigGroup consecutive pieces form a group: a piece updates only the columns of the later pieces of its group
+    // right away (upd_lim = that many tile columns), and the last piece applies the update of the WHOLE group to
+    // everything beyond it in one pass (upd_nsrc sources, K = sum of their widths per read-modify-write of a target
+    // tile instead of 64: the update is bound by that traffic).
+    std::vector<int> upd_lim(s.big_sn.size(), -1), upd_nsrc(s.big_sn.size(), 1), upd_src(s.big_sn.size() * kBigGroup, 0);
+    {
+        std::vector<int> where(s.nsuper, -1);
+        for (size_t q = 0; q < s.big_sn.size(); ++q) where[s.big_sn[q]] = static_cast<int>(q);
+        auto height = [&](int sn) { return static_cast<int64_t>(s.sn_rowptr[sn + 1] - s.sn_rowptr[sn]); };
+        auto width = [&](int sn) { return static_cast<int64_t>(s.sn_first[sn + 1] - s.sn_first[sn]); };
+        const char* genv = std::getenv("MADIPM_BIG_GROUP");
+        const int gmax = genv ? std::max(1, std::min(kBigGroup, std::atoi(genv))) : kBigGroup;
+        std::vector<char> taken(s.nsuper, 0);
+        for (size_t q = 0; q < s.big_sn.size(); ++q) {                     // big_sn is sorted by height
+            const int first = s.big_sn[q];
+            if (taken[first]) continue;
+            std::vector<int> grp{first};
+            taken[first] = 1;
+            while (static_cast<int>(grp.size()) < gmax) {
+                const int c = grp.back(), par = s.sn_parent[c];
+                if (par < 0 || where[par] < 0 || taken[par] || width(c) != kBigTile || width(par) != kBigTile ||
+                    height(c) - width(c) != height(par)) break;      // (tile columns must coincide with pieces)
+                if (height(par) - width(par) < kBigGroupMinRows) break;   // small remainder: too few tiles to be worth deferring
+                grp.push_back(par);
+                taken[par] = 1;
+            }
+            const int ng = static_cast<int>(grp.size());
+            for (int j = 0; j < ng; ++j) {
+                const int qq = where[grp[j]];
+                if (j + 1 < ng) {                                          // narrow: the columns of the later pieces
+                    int64_t cols = 0;
+                    for (int k = j + 1; k < ng; ++k) cols += width(grp[k]);
+                    upd_lim[qq] = static_cast<int>((cols + kBigTile - 1) / kBigTile);
+                    upd_nsrc[qq] = 1;
+                    upd_src[qq * kBigGroup] = grp[j];
+                } else {                                                   // wide: the whole group onto the rest
+                    upd_lim[qq] = -1;
+                    upd_nsrc[qq] = ng;
+                    for (int k = 0; k < ng; ++k) upd_src[qq * kBigGroup + k] = grp[k];
+                }
+            }
+        }
+    }
     // grid sizes of the multi-block kernels, per height (max over the big supernodes of that height)
     d->big_ptr.assign(s.big_ptr.begin(), s.big_ptr.end());
     for (int l = 0; l < s.n_levels; ++l) {
@@ -431,7 +477,12 @@ int32_t device_create(madipm_handle* h) {
             const int64_t nb = hs - ws, nt = (nb + kBigTile - 1) / kBigTile;
             rb = std::max<int>(rb, static_cast<int>(nt));
             rb512 = std::max<int>(rb512, static_cast<int>((nb + 511) / 512));
-            tiles = std::max<int>(tiles, static_cast<int>(nt * (nt + 1) / 2));
+            int64_t ntile = nt * (nt + 1) / 2;
+            if (upd_lim[q] >= 0) {
+                ntile = 0;
+                for (int64_t tj = 0; tj < std::min<int64_t>(upd_lim[q], nt); ++tj) ntile += nt - tj;
+            }
+            tiles = std::max<int>(tiles, static_cast<int>(ntile));
             if (ws < kPanelThreads) pb = std::max<int>(pb, static_cast<int>((nb + (kPanelThreads - ws) - 1) / (kPanelThreads - ws)));
         }
         d->big_panelblocks.push_back(pb);
@@ -470,6 +521,7 @@ int32_t device_create(madipm_handle* h) {
     UP(int64_t, row_colbase, s.row_colbase); UP(int64_t, row_relbase, s.row_relbase); UP(int, rel, s.rel);
     UP(int, perm, s.perm); UP(int, iperm, s.iperm);
     UP(int, big_sn, s.big_sn);
+    UP(int, upd_lim, upd_lim); UP(int, upd_nsrc, upd_nsrc); UP(int, upd_src, upd_src);
     UP(int, par_pos, s.par_pos);
     {
         std::vector<SnMeta> meta(std::max<size_t>(1, s.task_sn.size()));      // in task order
@@ -603,7 +655,7 @@ int32_t device_create(madipm_handle* h) {
         const size_t mw = static_cast<size_t>(s.max_w);
         d->smem_big_diag = (2 * mw * mw + mw) * sizeof(double);
         d->smem_big_trsm = 2 * mw * kBigTileLd * sizeof(double);
-        d->smem_big_update = (2 * kBigStage + ((mw + 1) & ~size_t(1))) * sizeof(double) + 2 * kBigTile * sizeof(int64_t);
+        d->smem_big_update = (2 * kBigStage + kBigGroup * std::max<size_t>(kBigTile, (mw + 1) & ~size_t(1))) * sizeof(double) + 2 * kBigTile * sizeof(int64_t);
         if (!s.big_sn.empty()) {
             if (d->smem_big_trsm > 220 * 1024) { h->error = "max_width too large for the big-front kernels"; return MADIPM_BAD_ARGUMENT; }
             CUDA_OK(h, cudaFuncSetAttribute(k_big_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_big_diag));
@@ -995,8 +1047,11 @@ int32_t madipm_factorize(madipm_handle* h, int32_t* n_failed) {
                     if (d->big_rowblocks[l] > 0)
                         LAUNCH(h, k_big_trsm, dim3(d->big_rowblocks[l], nbig, B), 128, d->smem_big_trsm, F, list, d->big_zbuf, d->big_zstride);
                 }
-                if (d->big_rowblocks[l] > 0)
-                    LAUNCH(h, k_big_update, dim3(d->big_tiles[l], nbig, B), 128, d->smem_big_update, F, list, exclusive);
+                if (d->big_rowblocks[l] > 0) {
+                    const int b0 = d->big_ptr[l];
+                    LAUNCH(h, k_big_update, dim3(d->big_tiles[l], nbig, B), 128, d->smem_big_update, F, list, d->upd_lim + b0,
+                           d->upd_nsrc + b0, d->upd_src + static_cast<size_t>(b0) * kBigGroup, exclusive);
+                }
             }
         }
         if (light) cudaEventRecord(d->ev1, d->stream);

@@ -19,6 +19,8 @@
 namespace madipm {
 
 constexpr int kBigTile = 64;          // output tile edge of k_big_update
+constexpr int kBigGroupMinRows = 2048; // ... only while that many rows remain below the group
+constexpr int kBigGroup = 8;          // pieces of a cut supernode whose updates are applied together (K up to 512)
 constexpr int kBigTileLd = 68;        // 64 + 4: leading dimension = 4 mod 16 doubles
 
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
@@ -225,8 +227,9 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
 }
 
-__global__ void __launch_bounds__(128)
-k_big_update(FactorView F, const int* __restrict__ big_sn, int exclusive) {
+__global__ void __launch_bounds__(128, 5)
+k_big_update(FactorView F, const int* __restrict__ big_sn, const int* __restrict__ upd_lim, const int* __restrict__ upd_nsrc,
+             const int* __restrict__ upd_src, int exclusive) {
     const int inst = blockIdx.z;
     const int s = big_sn[blockIdx.y];
     double* Lx = F.Lx + inst * F.lx_stride;
@@ -235,29 +238,59 @@ k_big_update(FactorView F, const int* __restrict__ big_sn, int exclusive) {
     const int h = static_cast<int>(F.sn_rowptr[s + 1] - F.sn_rowptr[s]);
     const int nb = h - w;
     const int nt = (nb + kBigTile - 1) / kBigTile;
+    const int lim = upd_lim[blockIdx.y];                   // >= 0: only the first lim tile columns (the later pieces of the group)
+    const int nsrc = upd_nsrc[blockIdx.y];                 // sources: this supernode, or every piece of its group (it is the last)
     // decode the linear tile index t -> (ti, tj), ti >= tj
-    const int t = blockIdx.x;
-    if (t >= nt * (nt + 1) / 2) return;
-    int ti = static_cast<int>((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-    while (ti * (ti + 1) / 2 > t) --ti;
-    const int tj = t - ti * (ti + 1) / 2;
-    const int64_t ld = h;
-    const double* P = Lx + F.sn_xoff[s];
+    int t = blockIdx.x, ti, tj;
+    if (lim < 0) {
+        if (t >= nt * (nt + 1) / 2) return;
+        ti = static_cast<int>((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+        while (ti * (ti + 1) / 2 > t) --ti;
+        tj = t - ti * (ti + 1) / 2;
+    } else {                                               // column by column
+        tj = 0;
+        while (tj < lim && tj < nt && t >= nt - tj) { t -= nt - tj; ++tj; }
+        if (tj >= lim || tj >= nt) return;
+        ti = tj + t;
+    }
     const int* rows = F.sn_rows + F.sn_rowptr[s];
     double* stage = madipm_smem;
-    double* Ds = stage + 2 * kBigStage;
-    int64_t* colb = reinterpret_cast<int64_t*>(Ds + ((w + 1) & ~1));
+    double* Ds = stage + 2 * kBigStage;                    // [nsrc][kBigTile] (one source: [w])
+    const int dsz = nsrc > 1 ? kBigGroup * kBigTile : ((w + 1) & ~1);
+    int64_t* colb = reinterpret_cast<int64_t*>(Ds + dsz);
     int64_t* relb = colb + kBigTile;
     const int i0 = w + ti * kBigTile, j0 = w + tj * kBigTile;
     const int ni = min(kBigTile, h - i0), nj = min(kBigTile, h - j0);
+    // source q: panel, leading dimension, width, and where the target rows (the rows below s) start in it
+    __shared__ int64_t src_xoff[kBigGroup];
+    __shared__ int src_ld[kBigGroup], src_w[kBigGroup], src_chunk0[kBigGroup + 1];
+    if (tid == 0) {
+        int c = 0;
+        for (int q = 0; q < nsrc; ++q) {
+            const int sq = nsrc > 1 ? upd_src[blockIdx.y * kBigGroup + q] : s;
+            src_xoff[q] = F.sn_xoff[sq];
+            src_ld[q] = static_cast<int>(F.sn_rowptr[sq + 1] - F.sn_rowptr[sq]);
+            src_w[q] = F.sn_first[sq + 1] - F.sn_first[sq];
+            src_chunk0[q] = c;
+            c += (src_w[q] + kBigKc - 1) / kBigKc;
+        }
+        src_chunk0[nsrc] = c;
+    }
+    __syncthreads();
+    const int nchunk = src_chunk0[nsrc];
     auto issue = [&](int c) {                              // chunk c -> stage c & 1
         double* As = stage + (c & 1) * kBigStage;
         double* Bs = As + kBigKc * kBigTileLd;
-        const int k0 = c * kBigKc;
+        int q = 0;
+        while (c >= src_chunk0[q + 1]) ++q;
+        const int k0 = (c - src_chunk0[q]) * kBigKc;
+        const int64_t ld = src_ld[q];
+        const int wq = src_w[q];
+        const double* P = Lx + src_xoff[q] + (ld - nb - w);    // row r of s's panel is row r + (ld - h) of this one
         for (int idx = tid; idx < kBigKc * kBigTile; idx += 128) {
             const int r = idx % kBigTile, k = idx / kBigTile;
-            const bool kin = k0 + k < w;
+            const bool kin = k0 + k < wq;
             if (kin && r < ni) cp_async8(&As[k * kBigTileLd + r], &P[i0 + r + (k0 + k) * ld]);
             else As[k * kBigTileLd + r] = 0.0;
             if (kin && r < nj) cp_async8(&Bs[k * kBigTileLd + r], &P[j0 + r + (k0 + k) * ld]);
@@ -265,14 +298,17 @@ k_big_update(FactorView F, const int* __restrict__ big_sn, int exclusive) {
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    const int nchunk = (w + kBigKc - 1) / kBigKc;
     issue(0);
     if (tid < kBigTile) {
         const int jj = j0 + tid;
         colb[tid] = (tid < nj) ? F.row_colbase[F.sn_rowptr[s] + jj] : 0;
         relb[tid] = (tid < nj) ? F.row_relbase[F.sn_rowptr[s] + jj] : 0;
     }
-    for (int k = tid; k < w; k += 128) Ds[k] = ldcg(&P[k + k * ld]);
+    for (int q = 0; q < nsrc; ++q) {
+        const double* Pq = Lx + src_xoff[q];
+        const int64_t ld = src_ld[q];
+        for (int k = tid; k < src_w[q]; k += 128) Ds[q * kBigTile + k] = ldcg(&Pq[k + k * ld]);
+    }
     const int lane = tid & 31, warp = tid >> 5;
     const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;     // warp's 32 x 32 corner inside the tile
     const int fr = lane >> 2, fk = lane & 3;                   // fragment row / k (A), n / k (B)
@@ -291,11 +327,15 @@ k_big_update(FactorView F, const int* __restrict__ big_sn, int exclusive) {
         __syncthreads();
         const double* As = stage + (c & 1) * kBigStage;
         const double* Bs = As + kBigKc * kBigTileLd;
+        int sq = 0;
+        while (c >= src_chunk0[sq + 1]) ++sq;
+        const double* Dq = Ds + sq * kBigTile + (c - src_chunk0[sq]) * kBigKc;
+        const int kleft = src_w[sq] - (c - src_chunk0[sq]) * kBigKc;      // valid k of this chunk (the rest is zero-filled)
 #pragma unroll
         for (int k0 = 0; k0 < kBigKc; k0 += 4) {
             double af[4], bf[4];
             const int kk = k0 + fk;
-            const double dk = Ds[min(c * kBigKc + kk, w - 1)];
+            const double dk = Dq[min(kk, kleft - 1)];
 #pragma unroll
             for (int a = 0; a < 4; ++a) af[a] = As[kk * kBigTileLd + wm + a * 8 + fr];
 #pragma unroll

@@ -626,6 +626,10 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
         S.row_colbase.assign(nr, 0);
         S.row_relbase.assign(nr, Symbolic::kRelSearch);
         S.rel.assign(4096, 0);   // padding keeps every table base (size - jb, jb <= 4096) non-negative
+        // Tall supernodes (more than 4096 rows) get tabulated positions too while the tables stay below a budget
+        // (default 1e9 entries = 4 GB of the 180 GB): the alternative is a binary search per updated entry.
+        const char* benv = std::getenv("MADIPM_REL_BUDGET");
+        const double rel_budget = benv ? std::atof(benv) : 1.0e9;
         std::vector<int32_t> pos;
         for (int32_t s = 0; s < ns; ++s) {
             const int64_t r0 = S.sn_rowptr[s];
@@ -655,7 +659,7 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
                 if (shift) {
                     const int64_t c = static_cast<int64_t>(pos[0]) - jb;     // position = i + c
                     relbase = -(c + Symbolic::kRelShift) - 1;
-                } else if (hs <= 4096) {
+                } else if (hs <= 4096 || static_cast<double>(S.rel.size()) + (hs - jb) <= rel_budget) {
                     relbase = static_cast<int64_t>(S.rel.size()) - jb;      // rel[relbase + i]
                     S.rel.insert(S.rel.end(), pos.begin(), pos.end());
                 } else {
