@@ -30,6 +30,11 @@ struct ArgMin {
 __device__ __forceinline__ ArgMin argmin_combine(ArgMin a, ArgMin b) {   // a earlier than b
     return (a.v < b.v) ? a : b;
 }
+// The same fold as a total order (smaller value; on ties the larger index), so that partial results can be combined
+// in any order: identical to the left fold for every input without NaN (a NaN direction aborts the solve anyway).
+__device__ __forceinline__ ArgMin argmin_merge(ArgMin a, ArgMin b) {
+    return (b.v < a.v || (b.v == a.v && b.i > a.i)) ? b : a;
+}
 
 template <int K>
 struct RedVals {
@@ -95,14 +100,21 @@ __device__ void grid_reduce(RedVals<K> r, double* scratch, unsigned int* counter
         if (warp < K) {
             const int k = warp;
             const double* base = scratch + static_cast<size_t>(inst) * gridDim.x * K;
-            double v = (ops[k] == RED_SUM) ? 0.0 : ((ops[k] == RED_MAX) ? -1.0 : __longlong_as_double(0x7ff0000000000000LL));
-            bool any = false;
-            for (unsigned int b = lane; b < gridDim.x; b += 32) {
-                double u = __ldcg(base + static_cast<size_t>(b) * K + k);
-                if (!any) { v = u; any = true; }
-                else if (ops[k] == RED_SUM) v = v + u;
-                else if (ops[k] == RED_MAX) v = nanmax(v, u);
-                else v = (u < v) ? u : v;
+            const double neutral = (ops[k] == RED_SUM) ? 0.0 : ((ops[k] == RED_MAX) ? -1.0 : __longlong_as_double(0x7ff0000000000000LL));
+            double v = neutral;
+            for (unsigned int b0 = lane; b0 < gridDim.x; b0 += 256) {     // eight partials per lane in flight, combined in block order
+                double u[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const unsigned int b = b0 + 32 * j;
+                    u[j] = b < gridDim.x ? __ldcg(base + static_cast<size_t>(b) * K + k) : neutral;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (ops[k] == RED_SUM) v = v + u[j];
+                    else if (ops[k] == RED_MAX) v = nanmax(v, u[j]);
+                    else v = (u[j] < v) ? u[j] : v;
+                }
             }
             // lanes without a block hold the neutral element of the op (0 for sums; -1 / +inf never win
             // because the reduced quantities are >= 0 for MAX and <= +inf for MIN)
@@ -387,13 +399,10 @@ k_ratio_test(VecView V, const double* __restrict__ d, const double* __restrict__
     // once, as the leftmost element, by the finalising block.
 #pragma unroll
     for (int q = 0; q < 4; ++q) { a[q].v = inf; a[q].i = 0; }
-    // each thread owns a CONTIGUOUS chunk so that "earlier/later" is preserved by the tree
+    // coalesced grid-stride pass: a thread folds its elements in increasing order (= the reference's left fold on its
+    // subset); the partial results are merged with the order-free form of the same rule
     const int top = max(V.nlb, V.nub);
-    const int total_threads = gridDim.x * blockDim.x;
-    const int chunk = (top + total_threads - 1) / total_threads;
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lo = gid * chunk, hi = min(top, lo + chunk);
-    for (int i = lo; i < hi; ++i) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < top; i += gridDim.x * blockDim.x) {
         if (i < V.nlb) {
             const int j = V.ind_lb[i];
             const double dxi = dx[j];
@@ -418,7 +427,6 @@ k_ratio_test(VecView V, const double* __restrict__ d, const double* __restrict__
             a[3] = argmin_combine(a[3], e);
         }
     }
-    // warp: lane l is earlier than lane l + o
     __shared__ double sv[4][kVecThreads / 32];
     __shared__ int si[4][kVecThreads / 32];
     __shared__ bool is_last;
@@ -430,7 +438,7 @@ k_ratio_test(VecView V, const double* __restrict__ d, const double* __restrict__
             ArgMin b;
             b.v = __shfl_down_sync(0xffffffffu, a[q].v, o);
             b.i = __shfl_down_sync(0xffffffffu, a[q].i, o);
-            if (lane + o < 32 && ((lane & (2 * o - 1)) == 0)) a[q] = argmin_combine(a[q], b);
+            if (lane + o < 32 && ((lane & (2 * o - 1)) == 0)) a[q] = argmin_merge(a[q], b);
         }
         if (lane == 0) { sv[q][warp] = a[q].v; si[q][warp] = a[q].i; }
     }
@@ -439,7 +447,7 @@ k_ratio_test(VecView V, const double* __restrict__ d, const double* __restrict__
     if (threadIdx.x < 4) {
         const int q = threadIdx.x;
         ArgMin r; r.v = sv[q][0]; r.i = si[q][0];
-        for (int w = 1; w < kVecThreads / 32; ++w) { ArgMin b; b.v = sv[q][w]; b.i = si[q][w]; r = argmin_combine(r, b); }
+        for (int w = 1; w < kVecThreads / 32; ++w) { ArgMin b; b.v = sv[q][w]; b.i = si[q][w]; r = argmin_merge(r, b); }
         my[q] = r.v;
         my[4 + q] = static_cast<double>(r.i);
     }
@@ -450,22 +458,31 @@ k_ratio_test(VecView V, const double* __restrict__ d, const double* __restrict__
     if (is_last) {
         __threadfence();
         if (warp < 4) {
-            // warp q combines slot q: lane l owns a contiguous run of blocks (order preserved), then the
-            // ordered tree; the reference's init element (1.0, 0) is applied last, as the leftmost element
+            // warp q merges slot q (eight partial results per lane in flight); the reference's init element (1.0, 0) is
+            // applied last, as the leftmost element
             const int q = warp;
             const double* base = scratch + static_cast<size_t>(inst) * gridDim.x * 8;
-            const unsigned int per = (gridDim.x + 31) / 32;
             ArgMin r; r.v = inf; r.i = 0;
-            for (unsigned int b = lane * per; b < min(gridDim.x, (lane + 1) * per); ++b) {
-                ArgMin e; e.v = __ldcg(base + b * 8 + q); e.i = static_cast<int>(__ldcg(base + b * 8 + 4 + q));
-                if (e.i != 0) r = argmin_combine(r, e);   // blocks that saw no element report (+inf, 0)
+            for (unsigned int b0 = lane; b0 < gridDim.x; b0 += 256) {
+                double ev[8], ei[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const unsigned int b = b0 + 32 * u;
+                    ev[u] = b < gridDim.x ? __ldcg(base + b * 8 + q) : inf;
+                    ei[u] = b < gridDim.x ? __ldcg(base + b * 8 + 4 + q) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    ArgMin e; e.v = ev[u]; e.i = static_cast<int>(ei[u]);
+                    if (e.i != 0) r = argmin_merge(r, e);   // blocks that saw no element report (+inf, 0)
+                }
             }
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 ArgMin b2;
                 b2.v = __shfl_down_sync(0xffffffffu, r.v, o);
                 b2.i = __shfl_down_sync(0xffffffffu, r.i, o);
-                if (lane + o < 32 && ((lane & (2 * o - 1)) == 0) && b2.i != 0) r = argmin_combine(r, b2);
+                if (lane + o < 32 && ((lane & (2 * o - 1)) == 0) && b2.i != 0) r = argmin_merge(r, b2);
             }
             if (lane == 0) {
                 ArgMin init; init.v = 1.0; init.i = 0;
