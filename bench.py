@@ -295,11 +295,26 @@ def run_ours(args):
                         share_of_step=sub_ms / 1e3 / res["sec"] if res["sec"] > 0 else None,
                         factor_phase_ms_avg=fac_ms / max(fac_calls, 1),
                         factor_tflops=info["factor_flops"] * B / ((fac_ms / max(fac_calls, 1)) / 1e3) / 1e12 if fac_ms > 0 else None)
+        traffic = {}
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            roofline["traffic"] = traffic.get("k_tree_factor_dram_bytes_per_launch")
         except (OSError, ValueError):
             pass
+        roofline["traffic"] = traffic.get("k_tree_factor_dram_bytes_per_launch")
+        if info["n_big"] > 0 and fac_ms > 2.0 * sub_ms:
+            # workloads whose factorisation lives in the multi-block fronts (C4, C2): the dominant kernel is the DMMA Schur
+            # update, bound by the FP64 tensor pipe.  achieved = factor flops / factor phase (panel factorisations and
+            # narrow updates included); peak = the DMMA rate at 100 % pipe activity derived from the ncu capture
+            # (profiles/traffic.json), else the nominal 40 TFLOP/s.
+            tf = roofline["factor_tflops"]
+            peak_tf = float(traffic.get("fp64_dmma_peak_tflops", 40.0))
+            roofline = dict(bound="tensor", kernel="k_big_update (FP64 DMMA Schur updates of the multi-block fronts)", achieved=tf,
+                            peak=peak_tf, unit="TFLOP/s", frac=tf / peak_tf,
+                            traffic=traffic.get("k_big_update_dram_bytes_per_launch"),
+                            peak_source="profiles/traffic.json fp64_dmma_peak_tflops (ncu: achieved / pipe activity)" if "fp64_dmma_peak_tflops" in traffic else "nominal FP64 tensor peak",
+                            flops_per_factorisation=info["factor_flops"] * B, factor_phase_ms_avg=fac_ms / max(fac_calls, 1),
+                            launches=fac_calls, share_of_step=fac_ms / 1e3 / res["sec"] if res["sec"] > 0 else None,
+                            factor_tflops=tf)
         cpu = None
         if world == 1 and not args.no_cpu:
             v, desc, _ = cpu_sample(qps[0], kkt, budget_s=args.cpu_budget)
