@@ -44,6 +44,9 @@ def make_workload(name, scale=1.0, seed=0):
     if name == "C3":
         qp = problems.banded_qp(seed=seed, n=int(500_000 * s), m=int(250_000 * s))
         return [qp], "K2", "C3: synthetic convex QP n=500k m=250k, 1M nnz A + pentadiagonal Q, K2 augmented LDL'"
+    if name == "C3-K2.5":   # same instance through MadNLP.ScaledSparseKKTSystem; not the headline
+        qp = problems.banded_qp(seed=seed, n=int(500_000 * s), m=int(250_000 * s))
+        return [qp], "K2.5", "C3 through the K2.5 scaled augmented system (ScaledSparseKKTSystem)"
     if name == "C2":
         qp = problems.sparse_lp(seed=seed, n=int(200_000 * s), m=int(100_000 * s))
         return [qp], "NORMAL", "C2: synthetic sparse LP n=200k m=100k, 1M nnz, normal-equations Cholesky"
@@ -108,8 +111,8 @@ def cpu_perm(qp, kkt):
     from madqp_jl_b200 import _lib
     from madqp_jl_b200.mpc import get_index_constraints
     ic = get_index_constraints(qp.lvar, qp.uvar, qp.lcon, qp.ucon)
-    h = _lib.Handle(kkt_kind=_lib.KKT_K2 if kkt == "K2" else _lib.KKT_NORMAL, ordering=_lib.ORDER_AMD)
-    if kkt == "K2":
+    h = _lib.Handle(kkt_kind=_lib.KKT_NORMAL if kkt == "NORMAL" else _lib.KKT_K2, ordering=_lib.ORDER_AMD)
+    if kkt != "NORMAL":
         h.set_pattern_k2(qp.nvar, qp.ncon, qp.H_rows + 1, qp.H_cols + 1, qp.A_rows + 1, qp.A_cols + 1, ic.ind_ineq + 1)
     else:
         h.set_pattern_normal(qp.nvar, qp.ncon, qp.A_rows + 1, qp.A_cols + 1, ic.ind_ineq + 1)

@@ -40,12 +40,16 @@ enum {
 };
 
 /* ---- configuration ------------------------------------------------------------------- */
-enum { MADIPM_KKT_K2 = 0, MADIPM_KKT_NORMAL = 1 };
+enum { MADIPM_KKT_K2 = 0, MADIPM_KKT_NORMAL = 1, MADIPM_KKT_K2_SCALED = 2 };
 enum { MADIPM_ORDER_AMD = 0, MADIPM_ORDER_NATURAL = 1, MADIPM_ORDER_ND = 2 /* nested dissection, AMD leaves (default) */ };
 
 typedef struct {
     int32_t kkt_kind;       /* MADIPM_KKT_K2: MadNLP.SparseKKTSystem (default, /root/reference/src/utils.jl:108);
-                               MADIPM_KKT_NORMAL: MadIPM.NormalKKTSystem (/root/reference/src/KKT/normalkkt.jl) */
+                               MADIPM_KKT_NORMAL: MadIPM.NormalKKTSystem (/root/reference/src/KKT/normalkkt.jl);
+                               MADIPM_KKT_K2_SCALED: MadNLP.ScaledSparseKKTSystem ("K2.5": the K2 system scaled
+                               symmetrically by sqrt of the bound slacks; /root/reference/src/kernels.jl:149-165,
+                               /root/reference/scripts/cuda_wrapper.jl:90-116, /root/reference/test/runtests.jl:102-115).
+                               Same pattern entry point, symbolic analysis and factor kernels as MADIPM_KKT_K2 */
     int32_t ordering;
     int32_t max_width;      /* supernode width cap */
     int32_t relax_small;    /* relaxed amalgamation, see csrc/symbolic.hpp */
@@ -172,6 +176,7 @@ enum {
     MADIPM_VEC_U_DIAG, MADIPM_VEC_U_LOWER,                                          /* nub */
     MADIPM_VEC_KKT_NZVAL,                                                           /* kkt_nnz (aug_com.nzval) */
     MADIPM_VEC_CON_SCALE,                                                           /* ncon (set_scaling!, see madipm_load_problem) */
+    MADIPM_VEC_SCALING,                                                             /* n_tot (K2.5 kkt.scaling_factor; ones otherwise) */
     MADIPM_VEC_COUNT
 };
 int32_t madipm_vec_len(const madipm_handle* h, int32_t vec, int64_t* len);     /* per instance */
@@ -185,12 +190,16 @@ void* madipm_stream(madipm_handle* h);                                         /
 /* ---- AbstractKKTSystem / linear-solver operations --------------------------------------- */
 /* MadNLP.initialize!(kkt), /root/reference/src/KKT/normalkkt.jl:136-147 */
 int32_t madipm_kkt_initialize(madipm_handle* h);
-/* K1 set_aug_diagonal_reg!, /root/reference/src/kernels.jl:128-146 (one fused kernel) */
+/* K1 set_aug_diagonal_reg!, /root/reference/src/kernels.jl:128-146 (one fused kernel).
+ * MADIPM_KKT_K2_SCALED: the ScaledSparseKKTSystem method, /root/reference/src/kernels.jl:149-165 (l_diag = x - xl,
+ * u_diag = xu - x, both positive) fused with MadNLP._set_aug_diagonal! (scaling_factor, pr_diag) */
 int32_t madipm_set_aug_diagonal_reg(madipm_handle* h, double del_w, double del_c);
 /* solver.jl:16-18: reg = pr_diag = del_w, du_diag = del_c */
 int32_t madipm_set_initial_regularization(madipm_handle* h, double del_w, double del_c);
 /* K2a / K2b build_kkt!: K2 transfer! (/root/reference/scripts/cuda_wrapper.jl:17-28) or
- * normal-equations assembly (/root/reference/src/utils.jl:266-298) into aug_com.nzval */
+ * normal-equations assembly (/root/reference/src/utils.jl:266-298) into aug_com.nzval.
+ * MADIPM_KKT_K2_SCALED: _build_scale_augmented_system_coo! (/root/reference/scripts/cuda_wrapper.jl:90-116)
+ * + transfer!, one pass over the nonzeros of aug_com */
 int32_t madipm_build_kkt(madipm_handle* h);
 /* factorize!: supernodal LDL' (K2) / Cholesky-as-LDL' (normal).  *n_failed = instances whose
  * factorisation broke down; status MADIPM_FACTOR_BREAKDOWN when > 0. Synchronises. */

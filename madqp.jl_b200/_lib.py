@@ -17,13 +17,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MADIPM_LIB") or os.path.join(_HERE, "libmadipm_b200.so")
 
 OK, FACTOR_BREAKDOWN, NONFINITE, CUDA_ERROR, BAD_ARGUMENT, INTERNAL = range(6)
-KKT_K2, KKT_NORMAL = 0, 1
+KKT_K2, KKT_NORMAL, KKT_K2_SCALED = 0, 1, 2
 ORDER_AMD, ORDER_NATURAL, ORDER_ND = 0, 1, 2
 OP_A, OP_AT, OP_Q = 0, 1, 2
 
 VEC_NAMES = [
     "X", "XL", "XU", "ZL", "ZU", "F", "JACL", "COST", "Y", "C", "RHS", "D", "P", "W1", "W2",
     "CORR_LB", "CORR_UB", "REG", "PR_DIAG", "DU_DIAG", "L_DIAG", "L_LOWER", "U_DIAG", "U_LOWER", "KKT_NZVAL", "CON_SCALE",
+    "SCALING",
 ]
 VEC = {name: i for i, name in enumerate(VEC_NAMES)}
 

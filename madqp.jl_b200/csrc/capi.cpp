@@ -47,7 +47,8 @@ int32_t madipm_create(const madipm_config* cfg, madipm_handle** out) {
     if (!h) return MADIPM_INTERNAL;
     if (cfg) h->cfg = *cfg;
     else madipm_default_config(&h->cfg);
-    if (h->cfg.batch < 1 || h->cfg.max_width < 1 || h->cfg.max_width > 256) { delete h; return MADIPM_BAD_ARGUMENT; }
+    if (h->cfg.batch < 1 || h->cfg.max_width < 1 || h->cfg.max_width > 256 || h->cfg.kkt_kind < MADIPM_KKT_K2 ||
+        h->cfg.kkt_kind > MADIPM_KKT_K2_SCALED) { delete h; return MADIPM_BAD_ARGUMENT; }
     *out = h;
     return MADIPM_OK;
 }
@@ -66,7 +67,7 @@ int32_t madipm_set_pattern_k2(madipm_handle* h, int32_t nvar, int32_t ncon,
                               int64_t nnzj, const int32_t* jac_I, const int32_t* jac_J,
                               int32_t n_slack, const int64_t* ind_ineq) {
     if (!h || nvar < 0 || ncon < 0 || nnzh < 0 || nnzj < 0 || n_slack < 0) return MADIPM_BAD_ARGUMENT;
-    if (h->cfg.kkt_kind != MADIPM_KKT_K2) { h->error = "handle was configured for the normal-equations system"; return MADIPM_BAD_ARGUMENT; }
+    if (h->cfg.kkt_kind != MADIPM_KKT_K2 && h->cfg.kkt_kind != MADIPM_KKT_K2_SCALED) { h->error = "handle was configured for the normal-equations system"; return MADIPM_BAD_ARGUMENT; }
     MADIPM_TRY(h, build_k2_pattern(nvar, ncon, nnzh, hess_I, hess_J, nnzj, jac_I, jac_J, n_slack, ind_ineq, h->pat));
     h->has_pattern = true;
     h->analyzed = false;
@@ -127,7 +128,7 @@ int32_t madipm_get_info(const madipm_handle* h, madipm_info* out) {
     if (!h || !out) return MADIPM_BAD_ARGUMENT;
     std::memset(out, 0, sizeof(*out));
     const KktPattern& p = h->pat;
-    out->kkt_kind = p.kind;
+    out->kkt_kind = h->cfg.kkt_kind == MADIPM_KKT_K2_SCALED ? MADIPM_KKT_K2_SCALED : p.kind;
     out->nvar = p.nx;
     out->n_slack = p.n_slack;
     out->n_tot = p.n_tot;

@@ -24,6 +24,9 @@ struct DeviceState {
     cudaStream_t stream = nullptr;
     int B = 1;
     int n = 0, m = 0, nlb = 0, nub = 0, N = 0, kind = 0;
+    bool scaled = false;               // K2.5 (MADIPM_KKT_K2_SCALED): kind == 0 pattern, values rescaled every iteration
+    int *kkt_row = nullptr, *kkt_col = nullptr;   // scaled only: coordinates of every nonzero of aug_com
+    double* nz_base = nullptr;                    // scaled only: the unscaled constant part of aug_com.nzval
     int64_t L = 0;
     int64_t nnzA = 0, nnzQ = 0, nnzh = 0, nnzj = 0, nnzJfull = 0, kkt_nnz = 0, lx_stride = 0;
     int nsuper = 0, n_levels = 0;
@@ -167,6 +170,7 @@ VecView make_view(const DeviceState& d) {
     V.l_diag = d.vec[MADIPM_VEC_L_DIAG]; V.l_lower = d.vec[MADIPM_VEC_L_LOWER];
     V.u_diag = d.vec[MADIPM_VEC_U_DIAG]; V.u_lower = d.vec[MADIPM_VEC_U_LOWER];
     V.corr_lb = d.vec[MADIPM_VEC_CORR_LB]; V.corr_ub = d.vec[MADIPM_VEC_CORR_UB];
+    V.scaling = d.vec[MADIPM_VEC_SCALING]; V.dsg = d.scaled ? -1.0 : 1.0;
     V.sn = d.n; V.sm = d.m; V.slb = d.nlb; V.sub = d.nub; V.sL = d.L;
     return V;
 }
@@ -267,6 +271,28 @@ __global__ void k_build_kkt_k2(int n, int m, const int* __restrict__ diag_slot, 
     nzval += inst * nz_stride;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n + m; i += gridDim.x * blockDim.x)
         nzval[diag_slot[i]] = ((i < n) ? pr_diag[i] : du_diag[i - n]) + const_diag[i];
+}
+
+// K2.5 build_kkt!: _build_scale_augmented_system_coo! (/root/reference/scripts/cuda_wrapper.jl:90-116) followed by
+// transfer! (:17-28), restated per nonzero of aug_com: Hessian block base * s[row] * s[col], Jacobian block
+// base * s[col], diagonal slots + pr_diag / du_diag (unscaled).  `base` holds the constant part with duplicates merged.
+__global__ void k_build_kkt_k25(int64_t nnz, int n, int m, const int* __restrict__ row, const int* __restrict__ col,
+                                const double* __restrict__ base, const double* __restrict__ scaling,
+                                const double* __restrict__ pr_diag, const double* __restrict__ du_diag,
+                                double* __restrict__ nzval) {
+    const int inst = blockIdx.y;
+    base += inst * nnz; nzval += inst * nnz;
+    scaling += static_cast<int64_t>(inst) * n;
+    pr_diag += static_cast<int64_t>(inst) * n;
+    du_diag += static_cast<int64_t>(inst) * m;
+    for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < nnz; k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int i = row[k], j = col[k];
+        double v = base[k];
+        if (i < n) v = __dmul_rn(__dmul_rn(v, scaling[i]), scaling[j]);
+        else if (j < n) v = __dmul_rn(v, scaling[j]);
+        if (i == j) v = __dadd_rn(v, i < n ? pr_diag[i] : du_diag[i - n]);
+        nzval[k] = v;
+    }
 }
 
 // K2a with a panel image: dperm[k] = (pr_diag | du_diag)[perm[k]], k in pivot order (coalesced writes, gathers from
@@ -415,6 +441,7 @@ int32_t device_create(madipm_handle* h) {
     }
     d->B = h->cfg.batch;
     d->n = p.n_tot; d->m = p.m; d->nlb = h->nlb; d->nub = h->nub; d->N = p.N; d->kind = p.kind;
+    d->scaled = p.kind == 0 && h->cfg.kkt_kind == MADIPM_KKT_K2_SCALED;
     d->L = static_cast<int64_t>(p.n_tot) + p.m + h->nlb + h->nub;
     d->nnzA = p.A_rowptr.back(); d->nnzQ = p.Q_rowptr.empty() ? 0 : p.Q_rowptr.back();
     d->nnzh = p.nnzh; d->nnzj = p.nnzj; d->nnzJfull = p.nnzj + p.n_slack;
@@ -572,7 +599,14 @@ int32_t device_create(madipm_handle* h) {
             diag_pos[j] = s.sn_xoff[sn] + static_cast<int64_t>(j - s.sn_first[sn]) * (hs + 1);
     }
     UP(int64_t, diag_pos, diag_pos);
-    if (p.kind == 0 && s.n_big == 0) {
+    if (d->scaled) {                                       // no panel image: every entry moves every iteration
+        std::vector<int> kcol(p.kkt_colptr.back());
+        for (int j = 0; j < d->N; ++j)
+            for (int64_t k = p.kkt_colptr[j]; k < p.kkt_colptr[j + 1]; ++k) kcol[k] = j;
+        UP(int, kkt_col, kcol);
+        UP(int, kkt_row, p.kkt_rowval);
+        if ((rc = dev_alloc(h, &d->nz_base, static_cast<size_t>(h->cfg.batch) * p.kkt_colptr.back()))) return rc;
+    } else if (p.kind == 0 && s.n_big == 0) {
         std::vector<int64_t> diag_lx(d->N);
         for (int i = 0; i < d->N; ++i) diag_lx[i] = s.asm_map[p.diag_slot[i]];
         UP(int64_t, diag_lx, diag_lx);
@@ -679,7 +713,7 @@ int32_t device_create(madipm_handle* h) {
     const int64_t n = d->n, m = d->m;
     int64_t* vl = d->veclen;
     for (int v : {MADIPM_VEC_X, MADIPM_VEC_XL, MADIPM_VEC_XU, MADIPM_VEC_ZL, MADIPM_VEC_ZU, MADIPM_VEC_F, MADIPM_VEC_JACL,
-                  MADIPM_VEC_COST, MADIPM_VEC_REG, MADIPM_VEC_PR_DIAG}) vl[v] = n;
+                  MADIPM_VEC_COST, MADIPM_VEC_REG, MADIPM_VEC_PR_DIAG, MADIPM_VEC_SCALING}) vl[v] = n;
     for (int v : {MADIPM_VEC_Y, MADIPM_VEC_C, MADIPM_VEC_RHS, MADIPM_VEC_DU_DIAG, MADIPM_VEC_CON_SCALE}) vl[v] = m;
     for (int v : {MADIPM_VEC_D, MADIPM_VEC_P, MADIPM_VEC_W1, MADIPM_VEC_W2}) vl[v] = d->L;
     vl[MADIPM_VEC_CORR_LB] = vl[MADIPM_VEC_L_DIAG] = vl[MADIPM_VEC_L_LOWER] = d->nlb;
@@ -767,6 +801,8 @@ static int32_t compress_values(madipm_handle* h) {
         if (d->nnzJfull)
             LAUNCH(h, k_scatter_add, dim3(vec_blocks(d->nnzJfull), B), kVecThreads, 0, d->nnzJfull, d->aug_map + d->n + d->nnzh, d->jacV, d->nnzJfull, nz, d->kkt_nnz);
         LAUNCH(h, k_extract_diag, dim3(vec_blocks(d->N), B), kVecThreads, 0, d->N, d->diag_slot, nz, d->kkt_nnz, d->const_diag);
+        if (d->scaled)
+            CUDA_OK(h, cudaMemcpyAsync(d->nz_base, nz, sizeof(double) * B * d->kkt_nnz, cudaMemcpyDeviceToDevice, d->stream));
         if (d->P0) {                                       // panel image of the constant part
             CUDA_OK(h, cudaMemsetAsync(d->P0, 0, sizeof(double) * B * d->lx_stride, d->stream));
             LAUNCH(h, k_assemble_panels, dim3(vec_blocks(d->kkt_nnz) * 4, B), kVecThreads, 0, d->kkt_nnz, d->asm_map, nz, d->kkt_nnz, d->P0,
@@ -969,7 +1005,7 @@ int32_t madipm_kkt_initialize(madipm_handle* h) {
     if (rc) return rc;
     const struct { int v; double x; } init[] = {
         {MADIPM_VEC_REG, 1.0}, {MADIPM_VEC_PR_DIAG, 1.0}, {MADIPM_VEC_DU_DIAG, 0.0}, {MADIPM_VEC_L_LOWER, 0.0},
-        {MADIPM_VEC_U_LOWER, 0.0}, {MADIPM_VEC_L_DIAG, 1.0}, {MADIPM_VEC_U_DIAG, 1.0}};
+        {MADIPM_VEC_U_LOWER, 0.0}, {MADIPM_VEC_L_DIAG, 1.0}, {MADIPM_VEC_U_DIAG, 1.0}, {MADIPM_VEC_SCALING, 1.0}};
     for (auto& it : init)
         if ((rc = madipm_vec_fill(h, it.v, it.x))) return rc;
     return MADIPM_OK;
@@ -980,7 +1016,10 @@ int32_t madipm_set_aug_diagonal_reg(madipm_handle* h, double del_w, double del_c
     if (rc) return rc;
     DeviceState* d = h->dev;
     Timer t(h, MADIPM_T_ASSEMBLY);
-    LAUNCH(h, k_set_aug_diagonal_reg, dim3(vec_blocks(std::max(d->n, d->m)), d->B), kVecThreads, 0, make_view(*d), del_w, del_c);
+    if (d->scaled)
+        LAUNCH(h, k_set_aug_diagonal_scaled, dim3(vec_blocks(std::max(d->n, d->m)), d->B), kVecThreads, 0, make_view(*d), del_w, del_c);
+    else
+        LAUNCH(h, k_set_aug_diagonal_reg, dim3(vec_blocks(std::max(d->n, d->m)), d->B), kVecThreads, 0, make_view(*d), del_w, del_c);
     return MADIPM_OK;
 }
 
@@ -997,7 +1036,11 @@ int32_t madipm_build_kkt(madipm_handle* h) {
     DeviceState* d = h->dev;
     Timer t(h, MADIPM_T_ASSEMBLY);
     double* nz = d->vec[MADIPM_VEC_KKT_NZVAL];
-    if (d->kind == 0 && d->image_valid) {
+    if (d->scaled) {
+        LAUNCH(h, k_build_kkt_k25, dim3(vec_blocks(d->kkt_nnz), d->B), kVecThreads, 0, d->kkt_nnz, d->n, d->m, d->kkt_row, d->kkt_col,
+               d->nz_base, d->vec[MADIPM_VEC_SCALING], d->vec[MADIPM_VEC_PR_DIAG], d->vec[MADIPM_VEC_DU_DIAG], nz);
+        d->nzval_diag_stale = false;
+    } else if (d->kind == 0 && d->image_valid) {
         LAUNCH(h, k_build_kkt_k2_perm, dim3(vec_blocks(d->N), d->B), kVecThreads, 0, d->n, d->m, d->perm,
                d->vec[MADIPM_VEC_PR_DIAG], d->vec[MADIPM_VEC_DU_DIAG], d->dperm);
         d->nzval_diag_stale = true;
@@ -1119,7 +1162,11 @@ int32_t madipm_kkt_solve(madipm_handle* h, int32_t vec_w) {
     VecView V = make_view(*d);
     double* w = d->vec[vec_w];
     const dim3 gN(vec_blocks(d->N), d->B), gn(vec_blocks(d->n), d->B), gm(vec_blocks(d->m), d->B);
-    if (d->kind == 0) {
+    if (d->scaled) {
+        LAUNCH(h, k_k25_presolve, gN, kVecThreads, 0, V, w, d->perm, d->N, d->xw, (int64_t)d->N);
+        if ((rc = tri_solve(h))) return rc;
+        LAUNCH(h, k_k25_postsolve, gN, kVecThreads, 0, V, w, d->iperm, d->N, d->xw, (int64_t)d->N);
+    } else if (d->kind == 0) {
         LAUNCH(h, k_k2_presolve, gN, kVecThreads, 0, V, w, d->perm, d->N, d->xw, (int64_t)d->N);
         if ((rc = tri_solve(h))) return rc;
         LAUNCH(h, k_k2_postsolve, gN, kVecThreads, 0, V, w, d->iperm, d->N, d->xw, (int64_t)d->N);

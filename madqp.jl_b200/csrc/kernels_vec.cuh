@@ -248,6 +248,8 @@ struct VecView {
     double *x, *xl, *xu, *zl, *zu, *f, *jacl, *cost, *y, *c, *rhs;
     double *reg, *pr_diag, *du_diag, *l_diag, *l_lower, *u_diag, *u_lower;
     double *corr_lb, *corr_ub;
+    double* scaling;                // K2.5 scaling_factor [n] (unused otherwise)
+    double dsg;                     // sign convention of l_diag / u_diag: +1 (K2, normal: xl - x, x - xu), -1 (K2.5: x - xl, xu - x)
     int64_t sn, sm, slb, sub, sL;   // strides (doubles) between instances
 };
 
@@ -258,6 +260,7 @@ __device__ __forceinline__ VecView shift(VecView v, int inst) {
     v.reg += inst * v.sn; v.pr_diag += inst * v.sn; v.du_diag += inst * v.sm;
     v.l_diag += inst * v.slb; v.l_lower += inst * v.slb; v.u_diag += inst * v.sub; v.u_lower += inst * v.sub;
     v.corr_lb += inst * v.slb; v.corr_ub += inst * v.sub;
+    v.scaling += inst * v.sn;
     return v;
 }
 
@@ -289,6 +292,44 @@ __global__ void k_set_aug_diagonal_reg(VecView V, double del_w, double del_c) {
                 pr -= ul / ud;
             }
             V.pr_diag[i] = pr;
+        }
+        if (i < V.m) V.du_diag[i] = del_c;
+    }
+}
+
+// ---- K1 for the K2.5 system: set_aug_diagonal_reg!(::ScaledSparseKKTSystem) (/root/reference/src/kernels.jl:149-165)
+// fused with MadNLP._set_aug_diagonal! [MadNLP 0.8.7, un-vendored; RECALLED, algebra forced by the symmetric scaling
+// S = diag(sqrt(x - xl) * sqrt(xu - x)) of the K2 system]:  l_diag = x - xl, u_diag = xu - x (positive),
+// scaling_factor = sqrt(l_diag) [* sqrt(u_diag)],  pr_diag = xlzu + xuzl + reg * scaling_factor^2  with
+// xlzu = zu * (l_diag or 1), xuzl = zl * (u_diag or 1).
+__global__ void k_set_aug_diagonal_scaled(VecView V, double del_w, double del_c) {
+    V = shift(V, blockIdx.y);
+    const int top = max(V.n, V.m);
+    MADIPM_GRID_STRIDE(i, top) {
+        if (i < V.n) {
+            V.reg[i] = del_w;
+            const int kl = V.lb_of[i], ku = V.ub_of[i];
+            double sf = 1.0, xlzu = 0.0, xuzl = 0.0, ld = 1.0, ud = 1.0;
+            if (kl >= 0) {
+                ld = V.x[i] - V.xl[i];
+                const double ll = V.zl[i];
+                V.l_diag[kl] = ld;
+                V.l_lower[kl] = ll;
+                xuzl = ll;
+                sf = __dmul_rn(sf, sqrt(ld));
+            }
+            if (ku >= 0) {
+                ud = V.xu[i] - V.x[i];
+                const double ul = V.zu[i];
+                V.u_diag[ku] = ud;
+                V.u_lower[ku] = ul;
+                xlzu = ul;
+                xuzl = __dmul_rn(xuzl, ud);
+                sf = __dmul_rn(sf, sqrt(ud));
+            }
+            if (kl >= 0) xlzu = __dmul_rn(xlzu, ld);
+            V.scaling[i] = sf;
+            V.pr_diag[i] = __dadd_rn(__dadd_rn(xlzu, xuzl), __dmul_rn(del_w, __dmul_rn(sf, sf)));
         }
         if (i < V.m) V.du_diag[i] = del_c;
     }
@@ -351,11 +392,11 @@ __global__ void k_kktmul_tail(VecView V, double* __restrict__ w, const double* _
             const int kl = V.lb_of[i], ku = V.ub_of[i];
             if (kl >= 0) {
                 acc -= alpha * vzl[kl];
-                wzl[kl] = beta * wzl[kl] + alpha * (vx[i] * V.l_lower[kl] - vzl[kl] * V.l_diag[kl]);
+                wzl[kl] = beta * wzl[kl] + alpha * (vx[i] * V.l_lower[kl] - vzl[kl] * (V.dsg * V.l_diag[kl]));
             }
             if (ku >= 0) {
                 acc += alpha * vzu[ku];
-                wzu[ku] = beta * wzu[ku] + alpha * (vx[i] * V.u_lower[ku] + vzu[ku] * V.u_diag[ku]);
+                wzu[ku] = beta * wzu[ku] + alpha * (vx[i] * V.u_lower[ku] + vzu[ku] * (V.dsg * V.u_diag[ku]));
             }
             wx[i] = acc;
         }
@@ -912,6 +953,53 @@ __global__ void k_k2_postsolve(VecView V, double* __restrict__ w, const int* __r
             if (kl >= 0) wzl[kl] = (-wzl[kl] + V.l_lower[kl] * v) / V.l_diag[kl];
             if (ku >= 0) wzu[ku] = (wzu[ku] - V.u_lower[ku] * v) / V.u_diag[ku];
         }
+    }
+}
+
+// K2.5 pre-solve [MadNLP solve!(::ScaledSparseKKTSystem, w), un-vendored; RECALLED, algebra forced]: with a = x - xl,
+// b = xu - x, s = scaling_factor, the reduced and scaled right-hand side is  s*wx + wzl*s/a + wzu*s/b  where s/a is
+// evaluated as sqrt(b)/sqrt(a) (or 1/sqrt(a)) so that a slack going to zero never meets its own square root twice.
+__global__ void k_k25_presolve(VecView V, const double* __restrict__ w, const int* __restrict__ perm, int N,
+                               double* __restrict__ xw, int64_t xw_stride) {
+    const int inst = blockIdx.y;
+    V = shift(V, inst);
+    w += inst * V.sL;
+    xw += inst * xw_stride;
+    const double* wzl = w + V.n + V.m;
+    const double* wzu = wzl + V.nlb;
+    MADIPM_GRID_STRIDE(k, N) {
+        const int i = perm[k];
+        double v = w[i];
+        if (i < V.n) {
+            const int kl = V.lb_of[i], ku = V.ub_of[i];
+            v *= V.scaling[i];
+            const double sa = kl >= 0 ? sqrt(V.l_diag[kl]) : 1.0;
+            const double sb = ku >= 0 ? sqrt(V.u_diag[ku]) : 1.0;
+            if (kl >= 0) v += wzl[kl] * sb / sa;
+            if (ku >= 0) v += wzu[ku] * sa / sb;
+        }
+        xw[k] = v;
+    }
+}
+
+// K2.5 post-solve: dx = s * xw[iperm], dy = xw[iperm]; dzl = (wzl - zl*dx) / (x - xl), dzu = (zu*dx - wzu) / (xu - x)
+__global__ void k_k25_postsolve(VecView V, double* __restrict__ w, const int* __restrict__ iperm, int N,
+                                const double* __restrict__ xw, int64_t xw_stride) {
+    const int inst = blockIdx.y;
+    V = shift(V, inst);
+    w += inst * V.sL;
+    xw += inst * xw_stride;
+    double* wzl = w + V.n + V.m;
+    double* wzu = wzl + V.nlb;
+    MADIPM_GRID_STRIDE(i, N) {
+        double v = xw[iperm[i]];
+        if (i < V.n) {
+            v *= V.scaling[i];
+            const int kl = V.lb_of[i], ku = V.ub_of[i];
+            if (kl >= 0) wzl[kl] = (wzl[kl] - V.l_lower[kl] * v) / V.l_diag[kl];
+            if (ku >= 0) wzu[ku] = (V.u_lower[ku] * v - wzu[ku]) / V.u_diag[ku];
+        }
+        w[i] = v;
     }
 }
 

@@ -67,11 +67,15 @@ class AdaptiveRegularization:
     delta_min: float = 1e-9
 
 
+_KKT_KINDS = {"K2": _lib.KKT_K2, "NORMAL": _lib.KKT_NORMAL, "K2.5": _lib.KKT_K2_SCALED}
+
+
 @dataclass
 class IPMOptions:
     """/root/reference/src/utils.jl:69-103 (fields that reach the hot path)."""
     tol: float = 1e-8
-    kkt_system: str = "K2"               # "K2" = MadNLP.SparseKKTSystem (default), "NORMAL" = MadIPM.NormalKKTSystem
+    kkt_system: str = "K2"               # "K2" = MadNLP.SparseKKTSystem (default), "NORMAL" = MadIPM.NormalKKTSystem,
+                                         # "K2.5" = MadNLP.ScaledSparseKKTSystem (kernels.jl:149-165, runtests.jl:102-115)
     max_iter: int = 3000
     scaling: bool = True
     bound_push: float = 1e-2
@@ -198,12 +202,14 @@ class MPCSolver:
         self.nlb, self.nub = ic.ind_lb.size, ic.ind_ub.size
         if opt.kkt_system == "NORMAL" and q0.nnzh > 0:
             raise ValueError("The KKT system NormalKKTSystem supports only linear programs.")   # normalkkt.jl:43-46
-        kind = _lib.KKT_K2 if opt.kkt_system == "K2" else _lib.KKT_NORMAL
+        if opt.kkt_system not in _KKT_KINDS:
+            raise ValueError(f"unknown kkt_system {opt.kkt_system!r}; expected one of {sorted(_KKT_KINDS)}")
+        kind = _KKT_KINDS[opt.kkt_system]
         self.h = Handle(kkt_kind=kind, batch=self.B, device=opt.device, ordering=opt.ordering,
                         max_width=opt.max_width, block_panel=opt.block_panel, nd_leaf=opt.nd_leaf,
                         **({'relax_small': opt.relax_small} if opt.relax_small else {}),
                         **({'relax_zeros': opt.relax_zeros} if opt.relax_zeros else {}))
-        if kind == _lib.KKT_K2:
+        if kind != _lib.KKT_NORMAL:
             self.h.set_pattern_k2(self.nx, self.m, q0.H_rows + 1, q0.H_cols + 1, q0.A_rows + 1, q0.A_cols + 1,
                                   ic.ind_ineq + 1)
         else:

@@ -252,7 +252,7 @@ class Options:
     mu_min: float = 1e-11
     tol_linear_solve: float = 1e-8
     check_residual: bool = False
-    kkt_system: str = "K2"                            # "K2" | "NORMAL"
+    kkt_system: str = "K2"                            # "K2" | "NORMAL" | "K2.5" (MadNLP.ScaledSparseKKTSystem)
 
 
 class MPCOracle:
@@ -270,8 +270,12 @@ class MPCOracle:
         self.nx, self.ns, self.n, self.m = nx, ns, n, m
         self.ind_lb, self.ind_ub = ic.ind_lb, ic.ind_ub
         self.nlb, self.nub = ic.ind_lb.size, ic.ind_ub.size
+        if opt.kkt_system not in ("K2", "NORMAL", "K2.5"):
+            raise ValueError(f"unknown kkt_system {opt.kkt_system!r}")
         if opt.kkt_system == "NORMAL" and qp.nnzh > 0:
             raise ValueError("NormalKKTSystem supports only linear programs")   # normalkkt.jl:43-46
+        self._k2 = opt.kkt_system in ("K2", "K2.5")        # both share the augmented pattern
+        self._scaled = opt.kkt_system == "K2.5"
 
         # ---- Jacobian incl. slack columns, COO -> CSR (normalkkt.jl:67-91)
         nnzj = qp.nnzj
@@ -291,7 +295,8 @@ class MPCOracle:
         self.u_diag = np.zeros(self.nub)
         self.l_lower = np.zeros(self.nlb)
         self.u_lower = np.zeros(self.nub)
-        if opt.kkt_system == "K2":
+        self.scaling_factor = np.ones(n)                    # ScaledSparseKKTSystem.scaling_factor
+        if self._k2:
             # aug COO: pr_diag | hess | jac | slack | du_diag  [RECALLED; cuda_wrapper.jl:95-107]
             hI = np.maximum(qp.H_rows, qp.H_cols) + 1
             hJ = np.minimum(qp.H_rows, qp.H_cols) + 1
@@ -299,6 +304,7 @@ class MPCOracle:
             aI = np.concatenate([np.arange(1, n + 1), hI, I.astype(np.int64) + n, np.arange(n + 1, n + m + 1)])
             aJ = np.concatenate([np.arange(1, n + 1), hJ, J.astype(np.int64), np.arange(n + 1, n + m + 1)])
             self.aug_V = np.zeros(aI.size)
+            self._aug_I, self._aug_J = aI, aJ               # K2.5 scales the COO values by block (cuda_wrapper.jl:90-116)
             self._off_hess, self._off_jac, self._off_du = n, n + nh, n + nh + nnzj + ns
             self.aug_colptr, self.aug_rowval, self.aug_csc_map = coo_to_csc(n + m, n + m, aI, aJ)
             self.aug_nzval = np.zeros(self.aug_rowval.size)
@@ -411,6 +417,7 @@ class MPCOracle:
         # MadNLP.initialize!(kkt)  (normalkkt.jl:136-147) + init_regularization! (kernels.jl:380-408)
         self.reg[:] = 1.0; self.pr_diag[:] = 1.0; self.du_diag[:] = 0.0
         self.l_lower[:] = 0.0; self.u_lower[:] = 0.0; self.l_diag[:] = 1.0; self.u_diag[:] = 1.0
+        self.scaling_factor[:] = 1.0
         kind = opt.regularization[0]
         self.del_w = 1.0
         self.del_c = 0.0 if kind == "none" else opt.regularization[2]
@@ -423,7 +430,7 @@ class MPCOracle:
         self.AT_nzval[:] = self.jac_V[self.A_csr_map - 1]
         self._Amat = self._A()
         self._Hs = None
-        if opt.kkt_system == "K2":
+        if self._k2:
             self.hess_V[:] = qp.H_vals * self.obj_scale
             self.aug_V[:] = 0.0
             self.aug_V[self._off_hess:self._off_hess + qp.nnzh] = self.hess_V
@@ -440,7 +447,22 @@ class MPCOracle:
 
     # ---- KKT system operations ---------------------------------------------------------------
     def build_kkt(self):
-        if self.opt.kkt_system == "K2":
+        if self._scaled:
+            # MadNLP.build_kkt!(::ScaledSparseKKTSystem) [RECALLED] = _build_scale_augmented_system_coo!
+            # (/root/reference/scripts/cuda_wrapper.jl:90-116, in repo) + transfer! (:17-28)
+            n, m = self.n, self.m
+            src = self.aug_V
+            src[:n] = self.pr_diag
+            src[self._off_du:] = self.du_diag
+            i, j, s = self._aug_I, self._aug_J, self.scaling_factor
+            k = np.arange(1, src.size + 1)
+            dest = src.copy()                                   # k <= n and the dual-regularisation block: copied
+            hess = (k > n) & (i <= n) & (j <= n)
+            dest[hess] = src[hess] * s[i[hess] - 1] * s[j[hess] - 1]
+            jac = (k > n) & (i >= n + 1) & (i <= n + m) & (j <= n)
+            dest[jac] = src[jac] * s[j[jac] - 1]
+            transfer(self.aug_nzval, dest, self.aug_csc_map)
+        elif self._k2:
             n = self.n
             self.aug_V[:n] = self.pr_diag                       # views into the COO values [RECALLED]
             self.aug_V[self._off_du:] = self.du_diag
@@ -463,10 +485,12 @@ class MPCOracle:
     def kkt_solve(self, w):
         """MadNLP.solve!(kkt, w): K2 [RECALLED, SURVEY 8a K4'] / Normal (normalkkt.jl:182-205)."""
         wx, wy, wzl, wzu = self._views(w)
+        if self._scaled:
+            return self._kkt_solve_scaled(w)
         # reduce_rhs!
         wx[self.ind_lb] -= wzl / self.l_diag
         wx[self.ind_ub] -= wzu / self.u_diag
-        if self.opt.kkt_system == "K2":
+        if self._k2:
             self.linear_solver.solve(w[:self.n + self.m])
         else:
             r1, r2, S = self.buffer_n, self.buffer_m, self.pr_diag
@@ -483,19 +507,41 @@ class MPCOracle:
         wzu[:] = (wzu - self.u_lower * wx[self.ind_ub]) / self.u_diag
         return w
 
+    def _kkt_solve_scaled(self, w):
+        """MadNLP.solve!(::ScaledSparseKKTSystem, w) [MadNLP 0.8.7, un-vendored; RECALLED].  The algebra is forced: the
+        K2.5 matrix is T*K2*T with T = diag(scaling_factor, I) (build_kkt above, in repo), the unreduced rows are
+        zl*dx + (x-xl)*dzl = wzl and zu*dx - (xu-x)*dzu = wzu (kernels.jl:38-39,58-59 with l_diag = x-xl, u_diag = xu-x
+        of kernels.jl:158-159), so  rhs = s*wx + wzl*s/l_diag + wzu*s/u_diag,  dx = s*dx~,  and the back-substitution
+        below.  s/l_diag is evaluated as sqrt(u_diag)/sqrt(l_diag) (1/sqrt(l_diag) without an upper bound)."""
+        wx, wy, wzl, wzu = self._views(w)
+        n = self.n
+        sa = np.ones(n); sb = np.ones(n)
+        sa[self.ind_lb] = np.sqrt(self.l_diag)
+        sb[self.ind_ub] = np.sqrt(self.u_diag)
+        r = wx * self.scaling_factor
+        r[self.ind_lb] += wzl * sb[self.ind_lb] / sa[self.ind_lb]
+        r[self.ind_ub] += wzu * sa[self.ind_ub] / sb[self.ind_ub]
+        wx[:] = r
+        self.linear_solver.solve(w[:n + self.m])
+        wx *= self.scaling_factor
+        wzl[:] = (wzl - self.l_lower * wx[self.ind_lb]) / self.l_diag
+        wzu[:] = (self.u_lower * wx[self.ind_ub] - wzu) / self.u_diag
+        return w
+
     def kkt_mul(self, w, v, alpha=1.0, beta=0.0):
         """mul!(w, kkt, v, alpha, beta): normalkkt.jl:207-219 + _kktmul! [RECALLED, SURVEY K5]."""
         wx, wy, wzl, wzu = self._views(w)
         vx, vy, vzl, vzu = self._views(v)
-        hx = self._Hsym() @ vx if self.opt.kkt_system == "K2" and self.qp.nnzh else 0.0
+        hx = self._Hsym() @ vx if self._k2 and self.qp.nnzh else 0.0
         wx[:] = alpha * (hx + self._Amat.T @ vy) + beta * wx
         wy[:] = alpha * (self._Amat @ vx) + beta * wy
         wx += alpha * self.reg * vx
         wy += alpha * self.du_diag * vy
         wx[self.ind_lb] -= alpha * vzl
         wx[self.ind_ub] += alpha * vzu
-        wzl[:] = beta * wzl + alpha * (vx[self.ind_lb] * self.l_lower - vzl * self.l_diag)
-        wzu[:] = beta * wzu + alpha * (vx[self.ind_ub] * self.u_lower + vzu * self.u_diag)
+        sg = -1.0 if self._scaled else 1.0                  # K2.5 stores l_diag = x - xl, u_diag = xu - x (kernels.jl:158-159)
+        wzl[:] = beta * wzl + alpha * (vx[self.ind_lb] * self.l_lower - vzl * (sg * self.l_diag))
+        wzu[:] = beta * wzu + alpha * (vx[self.ind_ub] * self.u_lower + vzu * (sg * self.u_diag))
         return w
 
     def solve_system(self, d, p):
@@ -515,9 +561,26 @@ class MPCOracle:
 
     # ---- kernels.jl --------------------------------------------------------------------------
     def set_aug_diagonal_reg(self):
-        """/root/reference/src/kernels.jl:128-146."""
+        """/root/reference/src/kernels.jl:128-146; ScaledSparseKKTSystem method: kernels.jl:149-165."""
         self.reg[:] = self.del_w
         self.du_diag[:] = self.del_c
+        if self._scaled:
+            self.l_diag[:] = self.x[self.ind_lb] - self.xl[self.ind_lb]     # (X - Xl), kernels.jl:158
+            self.u_diag[:] = self.xu[self.ind_ub] - self.x[self.ind_ub]     # (Xu - X), kernels.jl:159
+            self.l_lower[:] = self.zl[self.ind_lb]
+            self.u_lower[:] = self.zu[self.ind_ub]
+            # MadNLP._set_aug_diagonal!(::ScaledSparseKKTSystem) [MadNLP 0.8.7, un-vendored; RECALLED]
+            xlzu = np.zeros(self.n); xuzl = np.zeros(self.n)
+            xlzu[self.ind_ub] = self.u_lower
+            xlzu[self.ind_lb] *= self.l_diag
+            xuzl[self.ind_lb] = self.l_lower
+            xuzl[self.ind_ub] *= self.u_diag
+            self.pr_diag[:] = xlzu + xuzl
+            self.scaling_factor[:] = 1.0
+            self.scaling_factor[self.ind_lb] *= np.sqrt(self.l_diag)
+            self.scaling_factor[self.ind_ub] *= np.sqrt(self.u_diag)
+            self.pr_diag += self.reg * (self.scaling_factor * self.scaling_factor)
+            return
         self.l_diag[:] = self.xl[self.ind_lb] - self.x[self.ind_lb]
         self.u_diag[:] = self.x[self.ind_ub] - self.xu[self.ind_ub]
         self.l_lower[:] = self.zl[self.ind_lb]

@@ -32,8 +32,8 @@ def analyze_handle(qp, kkt="K2", **cfg):
     from madqp_jl_b200 import _lib
     from madqp_jl_b200.mpc import get_index_constraints
     ic = get_index_constraints(qp.lvar, qp.uvar, qp.lcon, qp.ucon)
-    h = _lib.Handle(kkt_kind=_lib.KKT_K2 if kkt == "K2" else _lib.KKT_NORMAL, **cfg)
-    if kkt == "K2":
+    h = _lib.Handle(kkt_kind={"K2": _lib.KKT_K2, "NORMAL": _lib.KKT_NORMAL, "K2.5": _lib.KKT_K2_SCALED}[kkt], **cfg)
+    if kkt != "NORMAL":
         h.set_pattern_k2(qp.nvar, qp.ncon, qp.H_rows + 1, qp.H_cols + 1, qp.A_rows + 1, qp.A_cols + 1, ic.ind_ineq + 1)
     else:
         h.set_pattern_normal(qp.nvar, qp.ncon, qp.A_rows + 1, qp.A_cols + 1, ic.ind_ineq + 1)

@@ -21,6 +21,10 @@ CASES = {
     "banded_k2": (lambda: P.banded_qp(seed=2, n=4000, m=2000), "K2"),
     "lp_normal": (lambda: P.sparse_lp(seed=4, n=1200, m=600), "NORMAL"),
     "lp_k2": (lambda: P.sparse_lp(seed=5, n=800, m=400), "K2"),
+    # K2.5 = MadNLP.ScaledSparseKKTSystem (/root/reference/src/kernels.jl:149-165, scripts/cuda_wrapper.jl:90-116)
+    "qp_k25": (lambda: P.maros_meszaros_like(seed=1, n=300, m=150, nnz=1500), "K2.5"),
+    "ineq_k25": (lambda: P.inequality_qp(seed=3, n=60, m=40, n_ineq=14), "K2.5"),
+    "banded_k25": (lambda: P.banded_qp(seed=2, n=4000, m=2000), "K2.5"),
 }
 
 
@@ -72,23 +76,29 @@ def test_spmv_matches_scipy(state):
     np.testing.assert_allclose(h.vec_get("C"), A @ x, rtol=1e-13, atol=1e-13)
     h.spmv(_lib.OP_AT, "JACL", "Y")
     np.testing.assert_allclose(h.vec_get("JACL"), A.T @ y, rtol=1e-13, atol=1e-13)
-    if kkt == "K2":
+    if kkt != "NORMAL":
         h.spmv(_lib.OP_Q, "F", "X")
         np.testing.assert_allclose(h.vec_get("F"), o._Hsym() @ x, rtol=1e-13, atol=1e-13)
     h.vec_set("X", o.x); h.vec_set("Y", o.y); h.vec_set("C", o.c); h.vec_set("JACL", o.jacl); h.vec_set("F", o.f)
 
 
 def test_set_aug_diagonal_reg_bit_exact(state):
-    """K1, /root/reference/src/kernels.jl:128-146: same operations in the same order -> identical bits."""
+    """K1, /root/reference/src/kernels.jl:128-146 (K2.5: 149-165 + _set_aug_diagonal!): same operations in the same
+    order -> identical bits, including the K2.5 scaling factors (IEEE square roots on both sides)."""
     qp, kkt, o, s, h = state
     h.set_aug_diagonal_reg(o.del_w, o.del_c)
     for name, ref in (("REG", o.reg), ("PR_DIAG", o.pr_diag), ("DU_DIAG", o.du_diag), ("L_DIAG", o.l_diag),
                       ("U_DIAG", o.u_diag), ("L_LOWER", o.l_lower), ("U_LOWER", o.u_lower)):
         assert np.array_equal(h.vec_get(name), ref), name
+    if kkt == "K2.5":
+        assert np.array_equal(h.vec_get("SCALING"), o.scaling_factor)
+        assert (h.vec_get("L_DIAG") > 0).all() and (h.vec_get("U_DIAG") > 0).all()      # kernels.jl:148
+        assert (h.vec_get("PR_DIAG") > 0).all()
 
 
 def test_build_kkt_bit_exact(state):
-    """K2a (transfer!) and K2b (assemble_normal_system!) produce the reference's nzval bit for bit."""
+    """K2a (transfer!), K2b (assemble_normal_system!) and the K2.5 scaled build
+    (_build_scale_augmented_system_coo! + transfer!) produce the reference's nzval bit for bit."""
     qp, kkt, o, s, h = state
     h.set_aug_diagonal_reg(o.del_w, o.del_c)
     h.build_kkt()
@@ -122,7 +132,7 @@ def test_factor_and_solve_residual(state):
     assert res <= max(1e-10, 10 * res_o), (res, res_o)
     pos, zero, neg = h.inertia()
     assert (pos, zero, neg) == o.linear_solver.inertia()
-    if kkt == "K2":
+    if kkt != "NORMAL":
         assert (pos, zero, neg) == (o.n, 0, o.m)
     else:
         assert (pos, zero, neg) == (o.m, 0, 0)
@@ -377,6 +387,7 @@ def test_full_size_c3_factor_solve_properties():
     (P.inequality_qp, dict(seed=1, n=60, m=40, n_ineq=15), "K2"),
     (P.maros_meszaros_like, dict(seed=3, n=300, m=150, nnz=1500), "K2"),
     (P.sparse_lp, dict(n=3000, m=1500), "NORMAL"),
+    (P.inequality_qp, dict(seed=1, n=60, m=40, n_ineq=15), "K2.5"),
 ])
 @pytest.mark.parametrize("scaling", [True, False])
 def test_load_problem_matches_host_preparation(maker, kw, kkt, scaling):
@@ -396,7 +407,7 @@ def test_load_problem_matches_host_preparation(maker, kw, kkt, scaling):
         assert np.array_equal(np.isinf(x), np.isinf(y)), v
         f = np.isfinite(x)
         assert np.allclose(y[f], x[f], rtol=1e-14, atol=1e-300), v
-    if kkt == "K2":
+    if kkt != "NORMAL":
         assert np.allclose(b.h.vec_get("KKT_NZVAL"), a.h.vec_get("KKT_NZVAL"), rtol=1e-14, atol=1e-300)
     sa, sb = a.solve(), b.solve()
     assert sa.status == sb.status and abs(int(sa.iter[0]) - int(sb.iter[0])) <= 1

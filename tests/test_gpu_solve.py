@@ -96,9 +96,40 @@ def test_regularisation_variants(reg):
     (P.sparse_lp, dict(n=4000, m=2000), dict(kkt_system="K2")),
     (P.transportation_lp, dict(n_src=60, n_dst=80, n_arcs=1500), dict(kkt_system="NORMAL")),        # C4 shape
     (P.small_qp, dict(instance=3), dict()),                                                         # C5 member
+    (P.maros_meszaros_like, dict(), dict(kkt_system="K2.5")),                                       # C1, K2.5
+    (P.banded_qp, dict(n=20000, m=10000), dict(kkt_system="K2.5")),                                 # C3 shape, K2.5
+    (P.inequality_qp, dict(seed=2), dict(kkt_system="K2.5", max_ncorr=3)),
 ])
 def test_config_shapes_match_oracle(maker, kw, opts):
     compare(maker(**kw), regularization=FixedRegularization(1e-8, -1e-8), **opts)
+
+
+def test_k25_matches_k2():
+    """/root/reference/test/runtests.jl:102-115: ScaledSparseKKTSystem reaches the same solution in the same number of
+    iterations as the default K2 system (unregularised there; both are run with NoRegularization here)."""
+    qp = P.inequality_qp(seed=4)
+    ref, _ = compare(qp, regularization=NoRegularization())
+    k25, _ = compare(qp, regularization=NoRegularization(), kkt_system="K2.5")
+    assert k25.status[0] == "SOLVE_SUCCEEDED"
+    assert int(k25.iter[0]) == int(ref.iter[0])
+    assert abs(k25.objective[0] - ref.objective[0]) <= 1e-6
+    np.testing.assert_allclose(k25.solution, ref.solution, atol=1e-6)
+    np.testing.assert_allclose(k25.multipliers, ref.multipliers, atol=1e-6)
+
+
+def test_k25_batch_matches_single():
+    """Batched K2.5 (instance = blockIdx.y in the scaled build / pre / post kernels) equals one-by-one solves."""
+    qps = [P.small_qp(instance=i) for i in range(5)]
+    s = MPCSolver(qps, kkt_system="K2.5", regularization=FixedRegularization(1e-8, -1e-8))
+    st = s.solve()
+    s.close()
+    for i, qp in enumerate(qps):
+        one = MPCSolver(qp, kkt_system="K2.5", regularization=FixedRegularization(1e-8, -1e-8))
+        r = one.solve()
+        one.close()
+        assert st.status[i] == r.status[0] == "SOLVE_SUCCEEDED"
+        assert abs(int(st.iter[i]) - int(r.iter[0])) <= 1
+        assert abs(st.objective[i] - r.objective[0]) <= 1e-8 * max(1.0, abs(r.objective[0]))
 
 
 @pytest.mark.parametrize("ordering", [_lib.ORDER_AMD, _lib.ORDER_ND, _lib.ORDER_NATURAL])
