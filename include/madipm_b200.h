@@ -291,6 +291,29 @@ enum { MADIPM_T_ASSEMBLY = 0, MADIPM_T_FACTOR, MADIPM_T_SOLVE, MADIPM_T_SPMV, MA
 int32_t madipm_profile(madipm_handle* h, int32_t enable);
 int32_t madipm_profile_read(madipm_handle* h, double* ms, int64_t* calls, int32_t reset);
 
+/* ---- preprocessing --------------------------------------------------------------- */
+/* scale_qp, /root/reference/scripts/common.jl:38-100: Ruiz equilibration of the constraint matrix in the infinity
+ * norm, As = A ./ (Dr_i * Dc_j) with row and column norms close to 1, and the matching rescaling of the model
+ * (H ./ (Dc_i*Dc_j), c ./ Dc, lvar/uvar/x0 .* Dc, lcon/ucon/y0 ./ Dr).  The reference takes (Dr, Dc) from
+ * HSL.mc77(A, 0) (proprietary, un-vendored); this restates the published simultaneous row/column iteration (Ruiz,
+ * RAL-TR-2001-034).  Needs no handle.  1-based COO triplets; every value array is rescaled IN PLACE on the host side
+ * (the work is done on the device: upload, max_iter sweeps, rescale, download); any of c, lvar, uvar, lcon, ucon, x0,
+ * y0, Dr, Dc may be NULL.  `tol <= 0`: all max_iter sweeps; otherwise stop once max |1 - norm| <= tol.
+ * *final_err = that deviation as seen by the last sweep.  opt->launches returns the number of kernels launched. */
+typedef struct {
+    int32_t device;
+    int32_t max_iter;   /* default 10 */
+    double tol;         /* default 0 */
+    int64_t launches;   /* out */
+} madipm_scale_options;
+void madipm_default_scale_options(madipm_scale_options* opt);
+int32_t madipm_scale_qp(madipm_scale_options* opt, int32_t nvar, int32_t ncon,
+                        int64_t nnzj, const int32_t* jac_I, const int32_t* jac_J, double* jac_V,
+                        int64_t nnzh, const int32_t* hess_I, const int32_t* hess_J, double* hess_V,
+                        double* c, double* lvar, double* uvar, double* lcon, double* ucon, double* x0, double* y0,
+                        double* Dr, double* Dc, int32_t* sweeps_done, double* final_err);
+const char* madipm_scale_last_error(void);   /* of the calling thread's last madipm_scale_qp */
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,10 @@ class LoadOptions(C.Structure):
                 ("scaling", C.c_int32), ("reserved", C.c_int32)]
 
 
+class ScaleOptions(C.Structure):
+    _fields_ = [("device", C.c_int32), ("max_iter", C.c_int32), ("tol", C.c_double), ("launches", C.c_int64)]
+
+
 class Info(C.Structure):
     _fields_ = ([(n, C.c_int32) for n in "kkt_kind nvar n_slack n_tot ncon nlb nub batch kkt_order".split()]
                 + [(n, C.c_int64) for n in "nnzh nnzj kkt_nnz aug_coo_len nnz_L nnz_stored".split()]
@@ -124,6 +128,10 @@ _SIGNATURES = {
     "madipm_launch_count": ([], C.c_int64),
     "madipm_profile": ([C.c_int32], C.c_int32),
     "madipm_profile_read": ([_PD, _P64, C.c_int32], C.c_int32),
+    "madipm_default_scale_options": (None, [C.POINTER(ScaleOptions)], None),
+    "madipm_scale_qp": (None, [C.POINTER(ScaleOptions), C.c_int32, C.c_int32, C.c_int64, _P32, _P32, _PD, C.c_int64, _P32, _P32, _PD,
+                               _PD, _PD, _PD, _PD, _PD, _PD, _PD, _PD, _PD, _P32, _PD], C.c_int32),
+    "madipm_scale_last_error": (None, [], C.c_char_p),
 }
 
 EXPORTED_SYMBOLS = sorted(_SIGNATURES)

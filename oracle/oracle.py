@@ -130,6 +130,39 @@ def coo_to_csc(m, n, I, J):
 # ---------------------------------------------------------------------------------------------
 # LDLSolver restatement (MadNLP.LDLSolver -> LDLFactorizations.jl, un-vendored)
 # ---------------------------------------------------------------------------------------------
+def scale_qp(qp, max_iter=10, tol=0.0):
+    """scale_qp, /root/reference/scripts/common.jl:46-100.  (Dr, Dc) = HSL.mc77(A, 0) there: HSL is proprietary and
+    un-vendored, so the published algorithm is restated (D. Ruiz, RAL-TR-2001-034: simultaneous row / column sweeps
+    D <- D * sqrt(inf-norm of the currently scaled row / column); [RECALLED] MC77 defaults: 10 sweeps, no convergence
+    test).  Parity with MC77's exact factors is unpinned; the rescaling formulas are the reference's (l.38-44, 70-97).
+    Returns (scaled copy of qp, Dr, Dc, sweeps, err)."""
+    import dataclasses
+    m, n = qp.ncon, qp.nvar
+    I, J, V = qp.A_rows, qp.A_cols, np.asarray(qp.A_vals, dtype=np.float64)
+    Dr, Dc = np.ones(m), np.ones(n)
+    sweeps, err = 0, 0.0
+    for _ in range(max_iter):
+        v = np.abs(V) / (Dr[I] * Dc[J])
+        rmax, cmax = np.zeros(m), np.zeros(n)
+        np.maximum.at(rmax, I, v)
+        np.maximum.at(cmax, J, v)
+        err = 0.0
+        for D, mx in ((Dr, rmax), (Dc, cmax)):
+            nz = mx > 0.0
+            D[nz] = D[nz] * np.sqrt(mx[nz])
+            if nz.any():
+                err = max(err, float(np.max(np.abs(1.0 - mx[nz]))))
+        sweeps += 1
+        if tol > 0.0 and err <= tol:
+            break
+    out = dataclasses.replace(
+        qp, name=qp.name + "-ruiz", A_vals=V / (Dr[I] * Dc[J]),                       # _scale_coo!(As, Dr, Dc)
+        H_vals=np.asarray(qp.H_vals, dtype=np.float64) / (Dc[qp.H_rows] * Dc[qp.H_cols]),   # _scale_coo!(Hs, Dc, Dc)
+        c=qp.c / Dc, lvar=qp.lvar * Dc, uvar=qp.uvar * Dc, lcon=qp.lcon / Dr, ucon=qp.ucon / Dr,
+        x0=qp.x0 * Dc, y0=qp.y0 / Dr, meta=dict(qp.meta, ruiz=True))
+    return out, Dr, Dc, sweeps, err
+
+
 class LDLSolver:
     """Scalar up-looking LDL' on a fixed fill-reducing permutation, no pivoting.
 
