@@ -204,6 +204,9 @@ int32_t madipm_build_kkt(madipm_handle* h);
 /* factorize!: supernodal LDL' (K2) / Cholesky-as-LDL' (normal).  *n_failed = instances whose
  * factorisation broke down; status MADIPM_FACTOR_BREAKDOWN when > 0. Synchronises. */
 int32_t madipm_factorize(madipm_handle* h, int32_t* n_failed);
+/* (n_failed == NULL: the call does not synchronise; the breakdown flags are collected by the next call that
+ *  synchronises anyway -- any call returning scalars, madipm_is_factorized, madipm_synchronize -- and the status is
+ *  then read with madipm_is_factorized.  The retry of linear_solver.jl:8-16 still sees every failure, one call later.) */
 /* is_factorized per instance (0/1), /root/reference/src/utils.jl:54-62 */
 int32_t madipm_is_factorized(madipm_handle* h, int32_t* flags);
 /* inertia of the last factorisation of instance `inst`: signs of D */
@@ -290,6 +293,19 @@ enum { MADIPM_T_ASSEMBLY = 0, MADIPM_T_FACTOR, MADIPM_T_SOLVE, MADIPM_T_SPMV, MA
  *             madipm_factorize performs anyway -- cheap enough to leave on inside a timed region. */
 int32_t madipm_profile(madipm_handle* h, int32_t enable);
 int32_t madipm_profile_read(madipm_handle* h, double* ms, int64_t* calls, int32_t reset);
+
+/* ---- fused iteration phases: one host synchronisation each ------------------------------------------ */
+/* The reference synchronises once per reduction (~22 per iteration); the separate entry points above once per returned
+ * group of scalars (7 per iteration); these three bring an iteration of mpc! (solver.jl:254-345) to 3. */
+/* solver.jl:259-274 + the objective left on the device by the last madipm_eval_model(h, c0, NULL) (solver.jl:338) */
+int32_t madipm_phase_residuals_obj(madipm_handle* h, double c0, double* out4, double* obj);
+/* affine_direction!, solver.jl:294-297: set_predictive_rhs! + solve_system!(d, solver, p) + ratio tests at tau = 1 +
+ * affine complementarity + get_correction!.  norms: 3 per instance as madipm_solve_system, out: 4 per instance as
+ * madipm_phase_affine.  MADIPM_NONFINITE as madipm_solve_system. */
+int32_t madipm_phase_predictor(madipm_handle* h, double* norms, double* out4);
+/* mpc_direction! without Gondzio corrections, solver.jl:307-311, + the ratio tests of update_step! (kernels.jl:290-305):
+ * set_correction_rhs!(mu) + solve_system! + ratio tests at tau.  ratio: 8 per instance as madipm_ratio_test. */
+int32_t madipm_phase_corrector(madipm_handle* h, const double* mu, const double* tau, double* norms, double* ratio8);
 
 /* ---- preprocessing --------------------------------------------------------------- */
 /* scale_qp, /root/reference/scripts/common.jl:38-100: Ruiz equilibration of the constraint matrix in the infinity

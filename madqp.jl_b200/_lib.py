@@ -128,6 +128,9 @@ _SIGNATURES = {
     "madipm_launch_count": ([], C.c_int64),
     "madipm_profile": ([C.c_int32], C.c_int32),
     "madipm_profile_read": ([_PD, _P64, C.c_int32], C.c_int32),
+    "madipm_phase_residuals_obj": ([C.c_double, _PD, _PD], C.c_int32),
+    "madipm_phase_predictor": ([_PD, _PD], C.c_int32),
+    "madipm_phase_corrector": ([_PD, _PD, _PD, _PD], C.c_int32),
     "madipm_default_scale_options": (None, [C.POINTER(ScaleOptions)], None),
     "madipm_scale_qp": (None, [C.POINTER(ScaleOptions), C.c_int32, C.c_int32, C.c_int64, _P32, _P32, _PD, C.c_int64, _P32, _P32, _PD,
                                _PD, _PD, _PD, _PD, _PD, _PD, _PD, _PD, _PD, _P32, _PD], C.c_int32),
@@ -323,6 +326,11 @@ class Handle:
         self._check(self.lib.madipm_factorize(self._h, C.byref(n)), allow=(FACTOR_BREAKDOWN,))
         return n.value
 
+    def factorize_async(self):
+        """madipm_factorize(h, NULL): no synchronisation; read the outcome with is_factorized() after the next call that
+        returns scalars."""
+        self._check(self.lib.madipm_factorize(self._h, None))
+
     def is_factorized(self):
         f = np.zeros(self.batch, dtype=np.int32)
         self._check(self.lib.madipm_is_factorized(self._h, _p32(f)))
@@ -360,6 +368,23 @@ class Handle:
         out = np.zeros(4 * self.batch)
         self._check(self.lib.madipm_phase_residuals(self._h, _pd(out)))
         return out.reshape(self.batch, 4)
+
+    def phase_residuals_obj(self, c0=0.0):
+        out, obj = np.zeros(4 * self.batch), np.zeros(self.batch)
+        self._check(self.lib.madipm_phase_residuals_obj(self._h, c0, _pd(out), _pd(obj)))
+        return out.reshape(self.batch, 4), obj
+
+    def phase_predictor(self):
+        norms, out = np.zeros(3 * self.batch), np.zeros(4 * self.batch)
+        rc = self._check(self.lib.madipm_phase_predictor(self._h, _pd(norms), _pd(out)), allow=(NONFINITE,))
+        return rc, norms.reshape(self.batch, 3), out.reshape(self.batch, 4)
+
+    def phase_corrector(self, mu, tau):
+        mu = _f64(np.broadcast_to(mu, (self.batch,)))
+        tau = _f64(np.broadcast_to(tau, (self.batch,)))
+        norms, ratio = np.zeros(3 * self.batch), np.zeros(8 * self.batch)
+        rc = self._check(self.lib.madipm_phase_corrector(self._h, _pd(mu), _pd(tau), _pd(norms), _pd(ratio)), allow=(NONFINITE,))
+        return rc, norms.reshape(self.batch, 3), ratio.reshape(self.batch, 8)
 
     def set_initial_primal_rhs(self):
         self._check(self.lib.madipm_set_initial_primal_rhs(self._h))

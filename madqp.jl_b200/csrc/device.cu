@@ -94,6 +94,11 @@ struct DeviceState {
     int *perm = nullptr, *iperm = nullptr;
     int* fail = nullptr;
     std::vector<int> h_fail;
+    // madipm_factorize(h, NULL) does not synchronise: the breakdown flags (and, with light profiling, the event times)
+    // are collected by the next call that synchronises anyway (any fetch, madipm_is_factorized, madipm_synchronize)
+    int* h_fail_pinned = nullptr;
+    bool fail_pending = false, prof_pending = false, prof_tree_pending = false;
+    double *d_norms = nullptr, *d_obj = nullptr;   // outputs of the fused phases that share one synchronisation
 
     double* vec[MADIPM_VEC_COUNT] = {};
     int64_t veclen[MADIPM_VEC_COUNT] = {};
@@ -223,11 +228,38 @@ struct Timer {
     }
 };
 
+// what an asynchronous factorisation left behind: enqueue before a synchronisation, collect after it
+int32_t pending_enqueue(madipm_handle* h) {
+    DeviceState* d = h->dev;
+    if (d->fail_pending)
+        CUDA_OK(h, cudaMemcpyAsync(d->h_fail_pinned, d->fail, sizeof(int) * d->B, cudaMemcpyDeviceToHost, d->stream));
+    return MADIPM_OK;
+}
+
+void pending_collect(madipm_handle* h) {
+    DeviceState* d = h->dev;
+    if (d->fail_pending) {
+        for (int i = 0; i < d->B; ++i) d->h_fail[i] = d->h_fail_pinned[i];
+        d->fail_pending = false;
+    }
+    if (d->prof_pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, d->ev0, d->ev1) == cudaSuccess) { d->t_ms[MADIPM_T_FACTOR] += ms; d->t_calls[MADIPM_T_FACTOR] += 1; }
+        if (d->prof_tree_pending && cudaEventElapsedTime(&ms, d->ev2, d->ev3) == cudaSuccess) {
+            d->t_ms[MADIPM_T_FACTOR_TREE] += ms; d->t_calls[MADIPM_T_FACTOR_TREE] += 1;
+        }
+        d->prof_pending = d->prof_tree_pending = false;
+    }
+}
+
 int32_t fetch(madipm_handle* h, const double* dsrc, double* hdst, size_t count) {
     DeviceState* d = h->dev;
+    int32_t rc;
+    if ((rc = pending_enqueue(h))) return rc;
     CUDA_OK(h, cudaMemcpyAsync(d->h_out, dsrc, count * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
     CUDA_OK(h, cudaStreamSynchronize(d->stream));
     CUDA_OK(h, cudaGetLastError());
+    pending_collect(h);
     std::memcpy(hdst, d->h_out, count * sizeof(double));
     return MADIPM_OK;
 }
@@ -731,6 +763,9 @@ int32_t device_create(madipm_handle* h) {
     CUDA_OK(h, cudaMemsetAsync(d->red_counter, 0, B * sizeof(unsigned int), d->stream));
     if ((rc = dev_alloc(h, &d->d_out, static_cast<size_t>(B) * 16))) return rc;
     if ((rc = dev_alloc(h, &d->d_out2, static_cast<size_t>(B) * 16))) return rc;
+    if ((rc = dev_alloc(h, &d->d_norms, static_cast<size_t>(B) * 4))) return rc;
+    if ((rc = dev_alloc(h, &d->d_obj, static_cast<size_t>(B) * 2))) return rc;
+    CUDA_OK(h, cudaMallocHost(reinterpret_cast<void**>(&d->h_fail_pinned), static_cast<size_t>(B) * sizeof(int)));
     if ((rc = dev_alloc(h, &d->d_steps, static_cast<size_t>(B) * 2))) return rc;
     if ((rc = dev_alloc(h, &d->d_mu, B))) return rc;
     if ((rc = dev_alloc(h, &d->d_tau, B))) return rc;
@@ -751,6 +786,7 @@ void device_destroy(madipm_handle* h) {
     if (d->stream) cudaStreamSynchronize(d->stream);
     for (void* p : d->allocs) cudaFree(p);
     if (d->h_out) cudaFreeHost(d->h_out);
+    if (d->h_fail_pinned) cudaFreeHost(d->h_fail_pinned);
     if (d->ev0) cudaEventDestroy(d->ev0);
     if (d->ev1) cudaEventDestroy(d->ev1);
     if (d->ev2) cudaEventDestroy(d->ev2);
@@ -961,7 +997,9 @@ int32_t madipm_vec_device_ptr(madipm_handle* h, int32_t vec, void** dev) {
 int32_t madipm_synchronize(madipm_handle* h) {
     int32_t rc = check(h);
     if (rc) return rc;
+    if ((rc = pending_enqueue(h))) return rc;
     CUDA_OK(h, cudaStreamSynchronize(h->dev->stream));
+    pending_collect(h);
     return MADIPM_OK;
 }
 
@@ -1098,6 +1136,13 @@ int32_t madipm_factorize(madipm_handle* h, int32_t* n_failed) {
             }
         }
         if (light) cudaEventRecord(d->ev1, d->stream);
+        if (!n_failed) {                                   // asynchronous: flags and event times ride on the next synchronisation
+            d->fail_pending = true;
+            d->prof_pending = light;
+            d->prof_tree_pending = light && !first_tree;
+            return MADIPM_OK;
+        }
+        d->fail_pending = d->prof_pending = d->prof_tree_pending = false;
         CUDA_OK(h, cudaMemcpyAsync(d->h_fail.data(), d->fail, sizeof(int) * B, cudaMemcpyDeviceToHost, d->stream));
         CUDA_OK(h, cudaStreamSynchronize(d->stream));
         if (light) {
@@ -1121,6 +1166,11 @@ int32_t madipm_is_factorized(madipm_handle* h, int32_t* flags) {
     int32_t rc = check(h);
     if (rc) return rc;
     if (!flags) return MADIPM_BAD_ARGUMENT;
+    if (h->dev->fail_pending || h->dev->prof_pending) {
+        if ((rc = pending_enqueue(h))) return rc;
+        CUDA_OK(h, cudaStreamSynchronize(h->dev->stream));
+        pending_collect(h);
+    }
     for (int i = 0; i < h->dev->B; ++i) flags[i] = h->dev->h_fail[i] == 0;
     return MADIPM_OK;
 }
@@ -1200,26 +1250,36 @@ int32_t madipm_kkt_mul(madipm_handle* h, int32_t vec_w, int32_t vec_v, double al
     return MADIPM_OK;
 }
 
-int32_t madipm_solve_system(madipm_handle* h, int32_t vec_d, int32_t vec_p, double* norms) {
-    int32_t rc = check(h, true);
-    if (rc) return rc;
+// solve_system! up to the three norms, which stay on the device in `norms_dev` (3 per instance)
+static int32_t solve_system_enqueue(madipm_handle* h, int32_t vec_d, int32_t vec_p, double* norms_dev) {
+    int32_t rc;
     DeviceState* d = h->dev;
-    if (!norms || vec_d == MADIPM_VEC_W1 || vec_p == MADIPM_VEC_W1) return MADIPM_BAD_ARGUMENT;
     if ((rc = madipm_vec_copy(h, vec_d, vec_p))) return rc;                 // linear_solver.jl:25
     if ((rc = madipm_kkt_solve(h, vec_d))) return rc;                       // :26
     if ((rc = madipm_vec_copy(h, MADIPM_VEC_W1, vec_p))) return rc;         // :30
     if ((rc = madipm_kkt_mul(h, MADIPM_VEC_W1, vec_d, -1.0, 1.0))) return rc;   // :31
-    {
-        Timer t(h, MADIPM_T_VECTOR);
-        LAUNCH(h, k_norms3, dim3(vec_blocks(d->L), d->B), kVecThreads, 0, d->L, d->vec[MADIPM_VEC_W1], d->vec[vec_p],
-               d->vec[vec_d], d->L, d->red_scratch, d->red_counter, d->d_out);
-    }
-    if ((rc = fetch(h, d->d_out, norms, 3 * d->B))) return rc;
+    Timer t(h, MADIPM_T_VECTOR);
+    LAUNCH(h, k_norms3, dim3(vec_blocks(d->L), d->B), kVecThreads, 0, d->L, d->vec[MADIPM_VEC_W1], d->vec[vec_p],
+           d->vec[vec_d], d->L, d->red_scratch, d->red_counter, norms_dev);
+    return MADIPM_OK;
+}
+
+static int32_t norms_status(const DeviceState* d, const double* norms) {
     for (int i = 0; i < d->B; ++i) {
         double ratio = norms[3 * i] / std::max(1.0, norms[3 * i + 1]);
         if (std::isnan(ratio)) return MADIPM_NONFINITE;                     // :41-43
     }
     return MADIPM_OK;
+}
+
+int32_t madipm_solve_system(madipm_handle* h, int32_t vec_d, int32_t vec_p, double* norms) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (!norms || vec_d == MADIPM_VEC_W1 || vec_p == MADIPM_VEC_W1) return MADIPM_BAD_ARGUMENT;
+    if ((rc = solve_system_enqueue(h, vec_d, vec_p, d->d_out))) return rc;
+    if ((rc = fetch(h, d->d_out, norms, 3 * d->B))) return rc;
+    return norms_status(d, norms);
 }
 
 int32_t madipm_spmv_ptr(madipm_handle* h, int32_t op, double* dev_out, int64_t so, const double* dev_in, int64_t si) {
@@ -1253,11 +1313,11 @@ int32_t madipm_eval_model(madipm_handle* h, double c0, double* obj) {
     {
         Timer t(h, MADIPM_T_SPMV);
         LAUNCH(h, k_eval_model, dim3(vec_blocks(std::max(d->n, d->m)), d->B), kVecThreads, 0, make_view(*d), d->Q_rp, d->Q_ci,
-               d->Q_val, d->nnzQ, d->A_rp, d->A_ci, d->A_val, d->nnzA, d->red_scratch, d->red_counter, d->d_out);
+               d->Q_val, d->nnzQ, d->A_rp, d->A_ci, d->A_val, d->nnzA, d->red_scratch, d->red_counter, d->d_obj);
     }
     if (obj) {
         std::vector<double> tmp(2 * d->B);
-        if ((rc = fetch(h, d->d_out, tmp.data(), 2 * d->B))) return rc;
+        if ((rc = fetch(h, d->d_obj, tmp.data(), 2 * d->B))) return rc;
         for (int i = 0; i < d->B; ++i) obj[i] = c0 + tmp[2 * i] + 0.5 * tmp[2 * i + 1];
     }
     return MADIPM_OK;
@@ -1274,6 +1334,82 @@ int32_t madipm_phase_residuals(madipm_handle* h, double* out) {
                d->AT_val, d->nnzA, d->vec[MADIPM_VEC_D], d->red_scratch, d->red_counter, d->d_out);
     }
     return fetch(h, d->d_out, out, 4 * d->B);
+}
+
+// phase_residuals + the objective of the last madipm_eval_model(h, c0, NULL): one synchronisation for both
+int32_t madipm_phase_residuals_obj(madipm_handle* h, double c0, double* out, double* obj) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (!out || !obj) return MADIPM_BAD_ARGUMENT;
+    {
+        Timer t(h, MADIPM_T_SPMV);
+        LAUNCH(h, k_residuals, dim3(vec_blocks(std::max(d->n, d->m)), d->B), kVecThreads, 0, make_view(*d), d->AT_rp, d->AT_ci,
+               d->AT_val, d->nnzA, d->vec[MADIPM_VEC_D], d->red_scratch, d->red_counter, d->d_out);
+    }
+    double* hobj = d->h_out + 24 * d->B;
+    CUDA_OK(h, cudaMemcpyAsync(hobj, d->d_obj, sizeof(double) * 2 * d->B, cudaMemcpyDeviceToHost, d->stream));
+    if ((rc = fetch(h, d->d_out, out, 4 * d->B))) return rc;
+    for (int i = 0; i < d->B; ++i) obj[i] = c0 + hobj[2 * i] + 0.5 * hobj[2 * i + 1];
+    return MADIPM_OK;
+}
+
+static int32_t set_rhs(madipm_handle* h, int mode, const double* mu);
+static void launch_ratio(madipm_handle* h, const double* tau_dev, double* out_dev);
+
+// affine_direction! (solver.jl:294-297) with one synchronisation: set_predictive_rhs!, solve_system!(d, solver, p),
+// ratio tests at tau = 1, affine complementarity, get_correction!.  norms[3] and out[4] per instance as in
+// madipm_solve_system / madipm_phase_affine.
+int32_t madipm_phase_predictor(madipm_handle* h, double* norms, double* out) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (!norms || !out) return MADIPM_BAD_ARGUMENT;
+    if ((rc = set_rhs(h, 2, nullptr))) return rc;
+    if ((rc = solve_system_enqueue(h, MADIPM_VEC_D, MADIPM_VEC_P, d->d_norms))) return rc;
+    {
+        Timer t(h, MADIPM_T_VECTOR);
+        launch_ratio(h, d->d_ones, d->d_out2);                                                   // tau = 1 (solver.jl:295)
+        LAUNCH(h, k_steps_from_ratio, (d->B + 127) / 128, 128, 0, d->B, d->d_out2, d->d_steps);
+        LAUNCH(h, k_complementarity, dim3(vec_blocks(std::max(d->nlb, d->nub)), d->B), kVecThreads, 0, make_view(*d),
+               d->vec[MADIPM_VEC_D], d->d_steps, 1, d->red_scratch, d->red_counter, d->d_out);   // solver.jl:296-297
+    }
+    double* hst = d->h_out + 16 * d->B;
+    double* hno = d->h_out + 20 * d->B;
+    std::vector<double> tmp(4 * d->B);
+    CUDA_OK(h, cudaMemcpyAsync(hst, d->d_steps, sizeof(double) * 2 * d->B, cudaMemcpyDeviceToHost, d->stream));
+    CUDA_OK(h, cudaMemcpyAsync(hno, d->d_norms, sizeof(double) * 3 * d->B, cudaMemcpyDeviceToHost, d->stream));
+    if ((rc = fetch(h, d->d_out, tmp.data(), 4 * d->B))) return rc;
+    std::memcpy(norms, hno, sizeof(double) * 3 * d->B);
+    const int nb = d->nlb + d->nub;
+    for (int i = 0; i < d->B; ++i) {
+        out[4 * i] = hst[2 * i];
+        out[4 * i + 1] = hst[2 * i + 1];
+        out[4 * i + 2] = nb ? (tmp[4 * i] + tmp[4 * i + 1]) / nb : 0.0;
+        out[4 * i + 3] = nb ? (tmp[4 * i + 2] + tmp[4 * i + 3]) / nb : 0.0;
+    }
+    return norms_status(d, norms);
+}
+
+// mpc_direction! without Gondzio corrections (solver.jl:307-311) + the ratio tests of update_step! (solver.jl:329,
+// kernels.jl:290-305) with one synchronisation: set_correction_rhs!(mu), solve_system!, ratio tests at tau.
+int32_t madipm_phase_corrector(madipm_handle* h, const double* mu, const double* tau, double* norms, double* ratio) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (!mu || !tau || !norms || !ratio) return MADIPM_BAD_ARGUMENT;
+    if ((rc = set_rhs(h, 3, mu))) return rc;
+    if ((rc = solve_system_enqueue(h, MADIPM_VEC_D, MADIPM_VEC_P, d->d_norms))) return rc;
+    {
+        Timer t(h, MADIPM_T_VECTOR);
+        CUDA_OK(h, cudaMemcpyAsync(d->d_tau, tau, sizeof(double) * d->B, cudaMemcpyHostToDevice, d->stream));
+        launch_ratio(h, d->d_tau, d->d_out);
+    }
+    double* hno = d->h_out + 20 * d->B;
+    CUDA_OK(h, cudaMemcpyAsync(hno, d->d_norms, sizeof(double) * 3 * d->B, cudaMemcpyDeviceToHost, d->stream));
+    if ((rc = fetch(h, d->d_out, ratio, 8 * d->B))) return rc;
+    std::memcpy(norms, hno, sizeof(double) * 3 * d->B);
+    return norms_status(d, norms);
 }
 
 static int32_t set_rhs(madipm_handle* h, int mode, const double* mu) {

@@ -92,6 +92,7 @@ class IPMOptions:
     ordering: int = _lib.ORDER_ND
     max_width: int = 64
     block_panel: int = 0            # 0 = library default (csrc/symbolic.hpp)
+    fused_phases: bool = True       # 3 host synchronisations per iteration (madipm_phase_*) instead of 7; same arithmetic
     device_prepare: bool = True     # initialize! / set_scaling! on the device (madipm_load_problem) instead of numpy
     relax_small: int = 0            # relaxed amalgamation (0 / None = library defaults)
     relax_zeros: tuple = None
@@ -385,9 +386,9 @@ class MPCSolver:
         self.kkt.build_kkt()
         return self.kkt.factorize()
 
-    def factorize_regularized_system(self):
+    def factorize_regularized_system(self, tries=3):
         """/root/reference/src/linear_solver.jl:6-17."""
-        for _ in range(3):
+        for _ in range(tries):
             self.h.set_aug_diagonal_reg(self.del_w, self.del_c)
             self.factorize_wrapper()
             if np.all(self.kkt.is_factorized()[self.active.astype(bool)]):
@@ -398,6 +399,9 @@ class MPCSolver:
     def solve_system(self):
         """/root/reference/src/linear_solver.jl:19-45 on (d, p)."""
         rc, norms = self.h.solve_system("D", "P")
+        self._check_solve_norms(norms)
+
+    def _check_solve_norms(self, norms):
         ratio = norms[:, 0] / np.maximum(1.0, norms[:, 1])
         act = self.active.astype(bool)
         self.last_residual_ratio = ratio
@@ -477,8 +481,16 @@ class MPCSolver:
     # ---- solver.jl:254-345 -----------------------------------------------------------------------------
     def mpc(self):
         opt, h = self.opt, self.h
+        self._obj_pending = False
         while True:
-            res = h.phase_residuals()                                   # l.259-274
+            if self._obj_pending:                                       # l.259-274 + the objective of l.338
+                res, obj = h.phase_residuals_obj(float(self._c0[0]) if self.B == 1 else 0.0)
+                if self.B > 1:
+                    obj = obj + self._c0
+                self.obj_val = np.where(self.active.astype(bool), obj, self.obj_val)
+                self._obj_pending = False
+            else:
+                res = h.phase_residuals()                               # l.259-274
             self.inf_pr = res[:, 0] / np.maximum(1.0, self.norm_b)
             self.inf_du = res[:, 1] / np.maximum(1.0, self.norm_c)
             self.inf_compl = res[:, 2] / np.maximum(1.0, self.norm_c)
@@ -496,22 +508,48 @@ class MPCSolver:
             if not self.active.any():
                 return
             self._update_regularization()                               # l.288
-            self.factorize_regularized_system()                         # l.289
-            h.set_predictive_rhs()                                      # l.294 affine_direction!
-            self.solve_system()
-            aff = h.phase_affine()                                      # l.295-297
+            fused = opt.fused_phases
+            if fused:
+                # first try of factorize_regularized_system without a synchronisation: the breakdown flags come back with
+                # the scalars of the predictor phase; a failure (rare) re-enters the reference's retry loop
+                h.set_aug_diagonal_reg(self.del_w, self.del_c)
+                self.kkt.build_kkt()
+                h.factorize_async()
+                rc, norms, aff = h.phase_predictor()                    # l.294-297 affine_direction!
+                if not np.all(self.kkt.is_factorized()[self.active.astype(bool)]):
+                    self.del_w *= 100.0
+                    self.del_c *= 100.0
+                    self.factorize_regularized_system(tries=2)
+                    rc, norms, aff = h.phase_predictor()
+                self._check_solve_norms(norms)
+            else:
+                self.factorize_regularized_system()                     # l.289
+                h.set_predictive_rhs()                                  # l.294 affine_direction!
+                self.solve_system()
+                aff = h.phase_affine()                                  # l.295-297
             mu_affine, mu_curr = aff[:, 2], aff[:, 3]
             self.update_barrier(mu_affine, mu_curr)                     # l.302
-            h.set_correction_rhs(self.mu)                               # l.307-311
-            self.solve_system()
-            if opt.max_ncorr > 0:                                       # l.316-324
-                self.gondzio_correction_direction(mu_curr, opt.max_ncorr)
-            self.update_step()                                          # l.329
+            rule = opt.step_rule
+            if fused and opt.max_ncorr == 0 and isinstance(rule, (ConservativeStep, AdaptiveStep)):
+                tau = rule.tau if isinstance(rule, ConservativeStep) else np.maximum(1 - self.mu, rule.tau_min)
+                rc, norms, r = h.phase_corrector(self.mu, tau)          # l.307-311 + l.329
+                self._check_solve_norms(norms)
+                self.alpha_p, self.alpha_d = np.minimum(r[:, 0], r[:, 1]), np.minimum(r[:, 2], r[:, 3])
+            else:
+                h.set_correction_rhs(self.mu)                           # l.307-311
+                self.solve_system()
+                if opt.max_ncorr > 0:                                   # l.316-324
+                    self.gondzio_correction_direction(mu_curr, opt.max_ncorr)
+                self.update_step()                                      # l.329
             h.update_iterate(self.alpha_p, self.alpha_d, self.mu,       # l.332-335 and 342
                              None if self.B == 1 else self.active)
-            obj = self._eval_callbacks()                                # l.338-340
-            act = self.active.astype(bool)
-            self.obj_val = np.where(act, obj, self.obj_val)
+            if fused:
+                h.eval_model(want_obj=False)                            # l.338-340; the objective is read with the next residuals
+                self._obj_pending = True
+            else:
+                obj = self._eval_callbacks()
+                act = self.active.astype(bool)
+                self.obj_val = np.where(act, obj, self.obj_val)
             self.k += 1
 
     # ---- solver.jl:347-403 -------------------------------------------------------------------------------

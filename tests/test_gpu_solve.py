@@ -192,3 +192,61 @@ def test_small_front_factor_is_bit_reproducible():
         outs.append(h.vec_get("D").copy())
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
     s.close()
+
+
+@pytest.mark.parametrize("maker,kw,opts", [
+    (P.maros_meszaros_like, dict(), dict()),
+    (P.banded_qp, dict(n=20000, m=10000), dict()),
+    (P.inequality_qp, dict(seed=2), dict(step_rule=ConservativeStep(0.99))),
+    (P.inequality_qp, dict(seed=2), dict(max_ncorr=3)),                          # predictor fused, corrector separate
+    (P.inequality_qp, dict(seed=2), dict(step_rule=MehrotraAdaptiveStep(0.99))),
+    (P.sparse_lp, dict(n=4000, m=2000), dict(kkt_system="NORMAL")),
+    (P.maros_meszaros_like, dict(), dict(kkt_system="K2.5")),
+])
+def test_fused_phases_are_the_same_arithmetic(maker, kw, opts):
+    """madipm_phase_residuals_obj / _predictor / _corrector + the asynchronous factorisation launch the same kernels in
+    the same order as the separate entry points (3 host synchronisations per iteration instead of 7): identical traces."""
+    qp = maker(**kw)
+    out = []
+    for fused in (True, False):
+        s = MPCSolver(qp, regularization=FixedRegularization(1e-8, -1e-8), fused_phases=fused, **opts)
+        st = s.solve()
+        out.append((st, s.trace, s.h.launch_count()))
+        s.close()
+    (a, ta, la), (b, tb, lb) = out
+    assert a.status == b.status and int(a.iter[0]) == int(b.iter[0])
+    assert a.objective[0] == b.objective[0]
+    assert np.array_equal(a.solution, b.solution) and np.array_equal(a.multipliers, b.multipliers)
+    assert len(ta) == len(tb)
+    for x, y in zip(ta, tb):
+        for key in ("obj", "inf_pr", "inf_du", "inf_compl", "mu", "alpha_p", "alpha_d"):
+            assert np.array_equal(x[key], y[key]), (x["k"], key)
+    assert la == lb                                                              # same kernels, fewer synchronisations
+
+
+def test_fused_phases_keep_the_factorisation_retry():
+    """linear_solver.jl:8-16 with the flags read one call later: a KKT matrix that breaks down without regularisation
+    ends in the same status and after the same iterations on both paths."""
+    qp = P.simple_lp()
+    free = P.QPData(name="free-var", nvar=qp.nvar, ncon=qp.ncon, c=qp.c, c0=qp.c0, H_rows=qp.H_rows, H_cols=qp.H_cols,
+                    H_vals=qp.H_vals, A_rows=qp.A_rows, A_cols=qp.A_cols, A_vals=qp.A_vals, lcon=qp.lcon, ucon=qp.ucon,
+                    lvar=np.full(qp.nvar, -np.inf), uvar=np.full(qp.nvar, np.inf), x0=qp.x0, y0=qp.y0)
+    res = []
+    for fused in (True, False):
+        s = MPCSolver(free, regularization=NoRegularization(), fused_phases=fused, max_iter=5)
+        st = s.solve()
+        res.append((st.status[0], int(st.iter[0]), s.del_w, s.del_c))
+        s.close()
+    assert res[0] == res[1], res
+
+
+def test_fused_batch_matches_unfused():
+    qps = [P.small_qp(instance=i) for i in range(7)]
+    res = []
+    for fused in (True, False):
+        s = MPCSolver(qps, regularization=FixedRegularization(1e-8, -1e-8), fused_phases=fused)
+        st = s.solve()
+        res.append(st)
+        s.close()
+    assert res[0].status == res[1].status and np.array_equal(res[0].iter, res[1].iter)
+    assert np.array_equal(res[0].objective, res[1].objective) and np.array_equal(res[0].solution, res[1].solution)
