@@ -10,10 +10,19 @@
 // the vertices that touch the next level.  When a region has no thin separator
 // (expander-like graphs) it is handed to AMD whole, so the hybrid never does
 // worse than AMD by more than the separators already placed.
+//
+// The two halves of a dissection are independent, so the first few levels of the recursion run them on separate host
+// threads.  The result does not depend on the schedule: a region of k vertices owns a fixed range of k positions of the
+// order (first half, second half, separator), region labels and BFS stamps come from atomic counters (only their
+// uniqueness matters), and all per-vertex scratch is touched only for the vertices of the task's own region.
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
+#include <cstdlib>
+#include <exception>
 #include <numeric>
 #include <stdexcept>
+#include <thread>
 #include <vector>
 
 #include "symbolic.hpp"
@@ -32,26 +41,32 @@ struct Dissector {
     const Graph& g;
     int32_t leaf_size;
     double max_sep_frac;
-    std::vector<int32_t> region;   // region id of every vertex (-1 = already ordered)
+    int par_depth;                                // recursion levels that fork a host thread
+    std::vector<std::atomic<int32_t>> region;     // region id of every vertex (-1 = already ordered); neighbours in other
+                                                  // regions are read while their owner relabels them (never to our id)
     std::vector<int32_t> level;    // BFS level scratch (valid only for stamped vertices)
     std::vector<int32_t> stamp;
-    int32_t cur_stamp = 0;
-    int32_t next_region = 1;
-    std::vector<int32_t> order;    // output: elimination order (old indices)
+    std::atomic<int32_t> stamp_counter{0};
+    std::atomic<int32_t> next_region{1};
+    std::vector<int32_t> order;    // output: elimination order (old indices), written by position
     std::vector<int32_t> local;    // old -> local index scratch for leaf AMD
 
-    Dissector(const Graph& gr, int32_t leaf, double frac)
-        : g(gr), leaf_size(leaf), max_sep_frac(frac), region(gr.n, 0), level(gr.n, 0), stamp(gr.n, 0), local(gr.n, -1) {
-        order.reserve(gr.n);
+    Dissector(const Graph& gr, int32_t leaf, double frac, int pdepth)
+        : g(gr), leaf_size(leaf), max_sep_frac(frac), par_depth(pdepth), region(gr.n), level(gr.n, 0), stamp(gr.n, 0),
+          order(gr.n, -1), local(gr.n, -1) {
+        for (auto& r : region) r.store(0, std::memory_order_relaxed);
     }
 
-    // BFS inside region `rid` from `root`; fills `out` in BFS order, returns #levels
-    int32_t bfs(int32_t root, int32_t rid, std::vector<int32_t>& out, std::vector<int32_t>& level_start) {
-        ++cur_stamp;
+    int32_t reg(int32_t v) const { return region[v].load(std::memory_order_relaxed); }
+    void set_reg(int32_t v, int32_t r) { region[v].store(r, std::memory_order_relaxed); }
+
+    // BFS inside region `rid` from `root`; fills `out` in BFS order, returns #levels; `st` = the stamp it used
+    int32_t bfs(int32_t root, int32_t rid, std::vector<int32_t>& out, std::vector<int32_t>& level_start, int32_t& st) {
+        st = stamp_counter.fetch_add(1, std::memory_order_relaxed) + 1;
         out.clear();
         level_start.clear();
         out.push_back(root);
-        stamp[root] = cur_stamp;
+        stamp[root] = st;
         level[root] = 0;
         size_t head = 0;
         level_start.push_back(0);
@@ -62,8 +77,8 @@ struct Dissector {
             ++head;
             for (int64_t p = g.ptr[v]; p < g.ptr[v + 1]; ++p) {
                 int32_t u = g.adj[p];
-                if (region[u] == rid && stamp[u] != cur_stamp) {
-                    stamp[u] = cur_stamp;
+                if (reg(u) == rid && stamp[u] != st) {
+                    stamp[u] = st;
                     level[u] = level[v] + 1;
                     out.push_back(u);
                 }
@@ -73,10 +88,11 @@ struct Dissector {
         return static_cast<int32_t>(level_start.size()) - 1;
     }
 
-    void order_leaf(const std::vector<int32_t>& verts) {
+    // the vertices of a leaf take positions [base, base + |verts|) of the order
+    void order_leaf(const std::vector<int32_t>& verts, int64_t base) {
         const int32_t k = static_cast<int32_t>(verts.size());
         if (k <= 2) {
-            for (int32_t v : verts) { order.push_back(v); region[v] = -1; }
+            for (int32_t i = 0; i < k; ++i) { order[base + i] = verts[i]; set_reg(verts[i], -1); }
             return;
         }
         for (int32_t i = 0; i < k; ++i) local[verts[i]] = i;
@@ -92,25 +108,27 @@ struct Dissector {
         }
         std::vector<int32_t> p;
         amd_order(k, cp.data(), ri.data(), p, 10.0);
-        for (int32_t i = 0; i < k; ++i) order.push_back(verts[p[i]]);
-        for (int32_t v : verts) { local[v] = -1; region[v] = -1; }
+        for (int32_t i = 0; i < k; ++i) order[base + i] = verts[p[i]];
+        for (int32_t v : verts) { local[v] = -1; set_reg(v, -1); }
     }
 
-    void dissect(std::vector<int32_t> verts, int32_t rid, int depth) {
+    void dissect(std::vector<int32_t> verts, int32_t rid, int depth, int64_t base) {
         const int32_t k = static_cast<int32_t>(verts.size());
         if (k == 0) return;
-        if (k <= leaf_size || depth > 48) { order_leaf(verts); return; }
+        if (k <= leaf_size || depth > 48) { order_leaf(verts, base); return; }
         // connected components of the region
         std::vector<int32_t> bfs_out, lstart;
-        bfs(verts[0], rid, bfs_out, lstart);
+        int32_t st = 0;
+        bfs(verts[0], rid, bfs_out, lstart, st);
         if (static_cast<int32_t>(bfs_out.size()) < k) {
             std::vector<std::pair<std::vector<int32_t>, int32_t>> comps;
             for (int32_t v0 : verts) {
-                if (region[v0] != rid) continue;
+                if (reg(v0) != rid) continue;
                 std::vector<int32_t> comp, ls;
-                bfs(v0, rid, comp, ls);
-                int32_t crid = next_region++;
-                for (int32_t v : comp) region[v] = crid;
+                int32_t st2 = 0;
+                bfs(v0, rid, comp, ls, st2);
+                int32_t crid = next_region.fetch_add(1, std::memory_order_relaxed);
+                for (int32_t v : comp) set_reg(v, crid);
                 comps.emplace_back(std::move(comp), crid);
             }
             verts.clear();
@@ -118,7 +136,12 @@ struct Dissector {
             // biggest last, so the heavy component sits next to whatever follows
             std::stable_sort(comps.begin(), comps.end(),
                              [](const auto& a, const auto& b) { return a.first.size() < b.first.size(); });
-            for (auto& c : comps) dissect(std::move(c.first), c.second, depth + 1);
+            int64_t at = base;
+            for (auto& c : comps) {
+                const int64_t sz = static_cast<int64_t>(c.first.size());
+                dissect(std::move(c.first), c.second, depth + 1, at);
+                at += sz;
+            }
             return;
         }
         // pseudo-peripheral root: walk to a min-degree vertex of the last level while depth grows
@@ -133,17 +156,18 @@ struct Dissector {
                 if (d < bestdeg) { bestdeg = d; best = v; }
             }
             std::vector<int32_t> out2, ls2;
-            int32_t nl2 = bfs(best, rid, out2, ls2);
-            if (nl2 > nlev) { root = best; nlev = nl2; bfs_out.swap(out2); lstart.swap(ls2); }
+            int32_t st2 = 0;
+            int32_t nl2 = bfs(best, rid, out2, ls2, st2);
+            if (nl2 > nlev) { root = best; nlev = nl2; bfs_out.swap(out2); lstart.swap(ls2); st = st2; }
             else { // keep the deeper structure; level[] must match bfs_out
                 std::vector<int32_t> o3, l3;
-                bfs(root, rid, o3, l3);
+                bfs(root, rid, o3, l3, st);
                 bfs_out.swap(o3);
                 lstart.swap(l3);
                 break;
             }
         }
-        if (nlev < 3) { order_leaf(verts); return; }
+        if (nlev < 3) { order_leaf(verts, base); return; }
         // middle level by vertex count
         int32_t mid = 1;
         {
@@ -162,23 +186,34 @@ struct Dissector {
             bool touches = false;
             for (int64_t p = g.ptr[v]; p < g.ptr[v + 1] && !touches; ++p) {
                 int32_t u = g.adj[p];
-                if (region[u] == rid && stamp[u] == cur_stamp && level[u] == mid + 1) touches = true;
+                if (reg(u) == rid && stamp[u] == st && level[u] == mid + 1) touches = true;
             }
             if (touches) sep.push_back(v);
             else partA.push_back(v);
         }
-        if (static_cast<double>(sep.size()) > max_sep_frac * k) { order_leaf(verts); return; }
+        if (static_cast<double>(sep.size()) > max_sep_frac * k) { order_leaf(verts, base); return; }
         for (int32_t q = 0; q < lstart[mid]; ++q) partA.push_back(bfs_out[q]);
         for (int32_t q = lstart[mid + 1]; q < k; ++q) partB.push_back(bfs_out[q]);
-        int32_t ra = next_region++, rb = next_region++;
-        for (int32_t v : partA) region[v] = ra;
-        for (int32_t v : partB) region[v] = rb;
-        for (int32_t v : sep) region[v] = -1;
+        int32_t ra = next_region.fetch_add(2, std::memory_order_relaxed), rb = ra + 1;
+        for (int32_t v : partA) set_reg(v, ra);
+        for (int32_t v : partB) set_reg(v, rb);
+        for (int32_t v : sep) set_reg(v, -1);
         verts.clear();
         verts.shrink_to_fit();
-        dissect(std::move(partA), ra, depth + 1);
-        dissect(std::move(partB), rb, depth + 1);
-        for (int32_t v : sep) order.push_back(v);
+        const int64_t na = static_cast<int64_t>(partA.size()), nb = static_cast<int64_t>(partB.size());
+        if (depth < par_depth && std::min(na, nb) >= 4096) {
+            std::exception_ptr err;
+            std::thread ta([&, this]() {
+                try { dissect(std::move(partA), ra, depth + 1, base); } catch (...) { err = std::current_exception(); }
+            });
+            try { dissect(std::move(partB), rb, depth + 1, base + na); } catch (...) { ta.join(); throw; }
+            ta.join();
+            if (err) std::rethrow_exception(err);
+        } else {
+            dissect(std::move(partA), ra, depth + 1, base);
+            dissect(std::move(partB), rb, depth + 1, base + na);
+        }
+        for (size_t i = 0; i < sep.size(); ++i) order[base + na + nb + static_cast<int64_t>(i)] = sep[i];
     }
 };
 
@@ -210,11 +245,20 @@ void nd_order(int32_t n, const int64_t* colptr, const int32_t* rowval, std::vect
                 g.adj[at[j]++] = i;
             }
     }
-    Dissector d(g, std::max(8, leaf_size), max_sep_frac);
+    // host threads for the first levels of the recursion: 2^depth leaves of work, at most 16 threads;
+    // MADIPM_ND_THREADS=1 keeps everything on the calling thread (same ordering either way)
+    int par_depth = 0;
+    {
+        unsigned hc = std::thread::hardware_concurrency();
+        if (const char* e = std::getenv("MADIPM_ND_THREADS")) hc = static_cast<unsigned>(std::max(1, std::atoi(e)));
+        while ((2u << par_depth) <= hc && par_depth < 4) ++par_depth;
+    }
+    Dissector d(g, std::max(8, leaf_size), max_sep_frac, par_depth);
     std::vector<int32_t> all(n);
     std::iota(all.begin(), all.end(), 0);
-    d.dissect(std::move(all), 0, 0);
-    if (static_cast<int32_t>(d.order.size()) != n) throw std::runtime_error("nd_order: incomplete ordering");
+    d.dissect(std::move(all), 0, 0, 0);
+    for (int32_t v : d.order)
+        if (v < 0) throw std::runtime_error("nd_order: incomplete ordering");
     perm = d.order;
 }
 

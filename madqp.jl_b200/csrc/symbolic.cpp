@@ -1,6 +1,9 @@
 // Host-side symbolic analysis.  See symbolic.hpp for the reference citations.
 #include "symbolic.hpp"
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <climits>
 #include <cstring>
@@ -361,6 +364,19 @@ void column_counts(int32_t n, const PermutedPattern& pp, const std::vector<int32
 
 }  // namespace
 
+namespace {
+struct StepClock {   // MADIPM_TIMING=1: wall time of every step of analyze on stderr (development aid)
+    bool on = std::getenv("MADIPM_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        if (!on) return;
+        auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[madipm analyze] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
+}  // namespace
+
 void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const SymbolicOptions& opt, Symbolic& S,
              const uint8_t* delayed) {
     S = Symbolic();
@@ -368,6 +384,7 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
     S.nnz_lower = colptr[n];
     if (n == 0) { S.sn_first.assign(1, 0); S.sn_rowptr.assign(1, 0); S.sn_xoff.assign(1, 0); S.child_ptr.assign(1, 0); S.sn_coff.assign(1, 0); S.phase_ptr.assign(1, 0); S.big_ptr.assign(1, 0); return; }
 
+    StepClock clk;
     // ---- 1. fill-reducing permutation
     std::vector<int32_t> perm0;
     if (opt.ordering == 1) { perm0.resize(n); std::iota(perm0.begin(), perm0.end(), 0); }
@@ -382,6 +399,7 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
         if (perm0[k] < 0 || perm0[k] >= n || ip0[perm0[k]] != -1) throw std::runtime_error("analyze: invalid permutation");
         ip0[perm0[k]] = k;
     }
+    clk.lap("ordering");
     // ---- 1b. delay flagged nodes (K2 constraint rows) until just after a partner neighbour.
     // Partners are DISTINCT (a bipartite matching): at every stage the eliminated constraints then
     // have a structurally nonsingular block against the eliminated variables, so no pivot is
@@ -454,6 +472,7 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
         perm0 = order;
         for (int32_t k = 0; k < n; ++k) ip0[perm0[k]] = k;
     }
+    clk.lap("constraint delay");
     // ---- 2. etree + counts in the AMD numbering, then one postorder that puts the
     //         heaviest child last (so it can chain into its parent's supernode)
     {
@@ -488,6 +507,7 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
     PermutedPattern pp;
     permute_pattern(n, colptr, rowval, S.iperm, pp);
 
+    clk.lap("etree + counts + postorder");
     // ---- 3. supernodes: maximal chains parent[j] == j+1 with nested structure, width-capped
     const int32_t maxw = std::max(1, opt.max_width);
     std::vector<int32_t> first;   // first column of each initial supernode
@@ -562,6 +582,7 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
         S.sn_parent[s] = pc == -1 ? -1 : S.sn_of[pc];
     }
 
+    clk.lap("supernodes + amalgamation");
     // ---- 5. row structures: own columns, then the union of A's columns and the children's tails
     std::vector<int32_t> chead(ns, -1), cnext(ns, -1);
     for (int32_t s = ns - 1; s >= 0; --s)
@@ -592,6 +613,7 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
         S.sn_rowptr[s + 1] = static_cast<int64_t>(S.sn_rows.size());
     }
 
+    clk.lap("row structures");
     // ---- 6. panel offsets (h x w column-major, start aligned to 16 bytes)
     S.sn_xoff.assign(static_cast<size_t>(ns) + 1, 0);
     S.max_h = S.max_w = 0;
@@ -605,6 +627,7 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
     }
     S.nnz_stored = S.sn_xoff[ns];
 
+    clk.lap("panel offsets");
     // ---- 7. assembly map: CSC nz (i, j) -> slot of (max(pi,pj), min(pi,pj)) in its panel
     S.asm_map.assign(S.nnz_lower, -1);
     for (int32_t j = 0; j < n; ++j)
@@ -620,6 +643,7 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
             S.asm_map[p] = S.sn_xoff[s] + static_cast<int64_t>(c - S.sn_first[s]) * hs + (it - rb);
         }
 
+    clk.lap("assembly map");
     // ---- 7b. scatter tables for the right-looking update
     {
         const size_t nr = S.sn_rows.size();
@@ -674,6 +698,7 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
         }
     }
 
+    clk.lap("scatter tables");
     // ---- 8. schedule by height (see symbolic.hpp)
     S.sn_level.assign(ns, 0);
     for (int32_t s = 0; s < ns; ++s) {
@@ -789,6 +814,7 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
     S.n_block_tasks = 0;
     for (int32_t l = 0; l < S.n_levels; ++l) S.n_block_tasks += S.phase_nblock[l];
     S.n_warp_tasks = static_cast<int32_t>(S.task_sn.size()) - S.n_block_tasks;
+    clk.lap("schedule");
 }
 
 }  // namespace madipm

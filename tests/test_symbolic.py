@@ -260,3 +260,21 @@ def test_contribution_block_tables_reproduce_the_factor(ordering):
     Kp = K[np.ix_(perm, perm)]
     L, d = _multifrontal_emulation(h, Kp)
     assert np.abs(L @ np.diag(d) @ L.T - Kp).max() <= 1e-10 * np.abs(Kp).max()
+
+
+def test_nested_dissection_does_not_depend_on_host_threads(monkeypatch):
+    """csrc/dissection.cpp runs the halves of the first dissection levels on separate host threads; every region owns a
+    fixed range of the order, so the permutation is the same for any thread count (and from run to run)."""
+    qp = P.banded_qp(seed=3, n=60000, m=30000)
+    perms = []
+    for threads in ("1", "2", "16", None):
+        if threads is None:
+            monkeypatch.delenv("MADIPM_ND_THREADS", raising=False)
+        else:
+            monkeypatch.setenv("MADIPM_ND_THREADS", threads)
+        h, _ = analyze_handle(qp, "K2", ordering=_lib.ORDER_ND)
+        perms.append(h.symbolic("PERM"))
+        h.close()
+    assert sorted(perms[0].tolist()) == list(range(perms[0].size))
+    for p in perms[1:]:
+        assert np.array_equal(p, perms[0])
