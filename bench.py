@@ -173,7 +173,7 @@ def run_reference(args):
                 cpu_baseline=dict(value=value, unit=UNIT, cores=1, kind="port", sample=desc),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0, detail=detail)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -342,13 +342,27 @@ def run_ours(args):
             iterations_per_solve=iters_per_solve, time_to_tol_s=res["sec"] / args.steps, converged=ok,
             analysis_s=solver.analysis_time, wall_s_resident=res["wall"], gondzio_max_ncorr_3=ncorr3,
         )
-        print(json.dumps(line), flush=True)
+        emit(line)
     solver.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    sys.stdout.flush()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    # stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner under torchrun, make's
+    # chatter from build()) is sent to stderr instead
+    global _RESULT_FD
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
