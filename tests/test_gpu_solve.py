@@ -234,20 +234,30 @@ def test_fused_phases_are_the_same_arithmetic(maker, kw, opts):
     assert la == lb                                                              # same kernels, fewer synchronisations
 
 
+def free_pair_lp():
+    """min x1 + x2  s.t.  x1 + x2 + x3 = 1,  x3 - x4 = 0,  x1, x2 >= 0,  x3, x4 free: without regularisation the free
+    variables have a zero KKT diagonal and the factorisation of every mpc! iteration breaks down."""
+    return P.QPData(name="free-pair", nvar=4, ncon=2, c=np.array([1.0, 1.0, 0.0, 0.0]), c0=0.0, H_rows=np.zeros(0, int),
+                    H_cols=np.zeros(0, int), H_vals=np.zeros(0), A_rows=np.array([0, 0, 0, 1, 1]), A_cols=np.array([0, 1, 2, 2, 3]),
+                    A_vals=np.array([1.0, 1.0, 1.0, 1.0, -1.0]), lcon=np.array([1.0, 0.0]), ucon=np.array([1.0, 0.0]),
+                    lvar=np.array([0.0, 0.0, -np.inf, -np.inf]), uvar=np.full(4, np.inf), x0=np.zeros(4), y0=np.zeros(2))
+
+
 def test_fused_phases_keep_the_factorisation_retry():
-    """linear_solver.jl:8-16 with the flags read one call later: a KKT matrix that breaks down without regularisation
-    ends in the same status and after the same iterations on both paths."""
-    qp = P.simple_lp()
-    free = P.QPData(name="free-var", nvar=qp.nvar, ncon=qp.ncon, c=qp.c, c0=qp.c0, H_rows=qp.H_rows, H_cols=qp.H_cols,
-                    H_vals=qp.H_vals, A_rows=qp.A_rows, A_cols=qp.A_cols, A_vals=qp.A_vals, lcon=qp.lcon, ucon=qp.ucon,
-                    lvar=np.full(qp.nvar, -np.inf), uvar=np.full(qp.nvar, np.inf), x0=qp.x0, y0=qp.y0)
+    """linear_solver.jl:8-16 with the flags read one call later: a KKT matrix that breaks down on all three tries ends
+    in the same status, iteration and regularisation on both paths (and in the oracle); with regularisation it solves."""
+    qp = free_pair_lp()
     res = []
     for fused in (True, False):
-        s = MPCSolver(free, regularization=NoRegularization(), fused_phases=fused, max_iter=5)
+        s = MPCSolver(qp, regularization=NoRegularization(), fused_phases=fused, max_iter=8)
         st = s.solve()
         res.append((st.status[0], int(st.iter[0]), s.del_w, s.del_c))
+        assert not s.kkt.is_factorized().all()
+        ref = O.MPCOracle(qp, perm=s.h.symbolic("PERM"), regularization=("none",), max_iter=8).solve()
+        assert (st.status[0], int(st.iter[0])) == (ref.status, ref.k) == ("ERROR_IN_STEP_COMPUTATION", 0)
         s.close()
     assert res[0] == res[1], res
+    compare(qp, regularization=FixedRegularization(1e-8, -1e-8))
 
 
 def test_fused_batch_matches_unfused():
