@@ -1,7 +1,10 @@
 // Host-side symbolic analysis.  See symbolic.hpp for the reference citations.
 #include "symbolic.hpp"
 
+#include <atomic>
 #include <chrono>
+#include <exception>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
@@ -628,20 +631,43 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
     S.nnz_stored = S.sn_xoff[ns];
 
     clk.lap("panel offsets");
-    // ---- 7. assembly map: CSC nz (i, j) -> slot of (max(pi,pj), min(pi,pj)) in its panel
+    // ---- 7. assembly map: CSC nz (i, j) -> slot of (max(pi,pj), min(pi,pj)) in its panel.
+    // Independent per column: computed by a few host threads while steps 7b and 8 run on this one (joined before return).
     S.asm_map.assign(S.nnz_lower, -1);
-    for (int32_t j = 0; j < n; ++j)
-        for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
-            int32_t a = S.iperm[rowval[p]], b = S.iperm[j];
-            int32_t r = std::max(a, b), c = std::min(a, b);
-            int32_t s = S.sn_of[c];
-            const int32_t* rb = S.sn_rows.data() + S.sn_rowptr[s];
-            const int32_t* re = S.sn_rows.data() + S.sn_rowptr[s + 1];
-            const int32_t* it = std::lower_bound(rb, re, r);
-            if (it == re || *it != r) throw std::runtime_error("analyze: entry outside the symbolic structure");
-            int64_t hs = re - rb;
-            S.asm_map[p] = S.sn_xoff[s] + static_cast<int64_t>(c - S.sn_first[s]) * hs + (it - rb);
+    std::exception_ptr asm_err;
+    std::atomic<bool> asm_failed{false};
+    auto asm_range = [&](int32_t j0, int32_t j1) {
+        try {
+            for (int32_t j = j0; j < j1; ++j)
+                for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
+                    int32_t a = S.iperm[rowval[p]], b = S.iperm[j];
+                    int32_t r = std::max(a, b), c = std::min(a, b);
+                    int32_t s = S.sn_of[c];
+                    const int32_t* rb = S.sn_rows.data() + S.sn_rowptr[s];
+                    const int32_t* re = S.sn_rows.data() + S.sn_rowptr[s + 1];
+                    const int32_t* it = std::lower_bound(rb, re, r);
+                    if (it == re || *it != r) throw std::runtime_error("analyze: entry outside the symbolic structure");
+                    int64_t hs = re - rb;
+                    S.asm_map[p] = S.sn_xoff[s] + static_cast<int64_t>(c - S.sn_first[s]) * hs + (it - rb);
+                }
+        } catch (...) {
+            if (!asm_failed.exchange(true)) asm_err = std::current_exception();
         }
+    };
+    std::vector<std::thread> asm_threads;
+    {
+        const unsigned hc = std::max(1u, std::thread::hardware_concurrency());
+        const int32_t nt = n < 50000 ? 0 : static_cast<int32_t>(std::min(4u, hc > 1 ? hc - 1 : 1u));
+        if (nt == 0) asm_range(0, n);
+        for (int32_t t = 0; t < nt; ++t)
+            asm_threads.emplace_back(asm_range, static_cast<int32_t>(static_cast<int64_t>(n) * t / nt),
+                                     static_cast<int32_t>(static_cast<int64_t>(n) * (t + 1) / nt));
+    }
+    struct Joiner {   // the threads are joined on every way out of analyze
+        std::vector<std::thread>& ts;
+        ~Joiner() { for (auto& t : ts) if (t.joinable()) t.join(); }
+    } asm_join{asm_threads};
+    if (asm_failed.load() && asm_threads.empty()) std::rethrow_exception(asm_err);
 
     clk.lap("assembly map");
     // ---- 7b. scatter tables for the right-looking update
@@ -815,6 +841,9 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
     for (int32_t l = 0; l < S.n_levels; ++l) S.n_block_tasks += S.phase_nblock[l];
     S.n_warp_tasks = static_cast<int32_t>(S.task_sn.size()) - S.n_block_tasks;
     clk.lap("schedule");
+    for (auto& t : asm_threads) t.join();
+    if (asm_failed.load()) std::rethrow_exception(asm_err);
+    clk.lap("assembly map (joined)");
 }
 
 }  // namespace madipm
