@@ -130,6 +130,21 @@ def coo_to_csc(m, n, I, J):
 # ---------------------------------------------------------------------------------------------
 # LDLSolver restatement (MadNLP.LDLSolver -> LDLFactorizations.jl, un-vendored)
 # ---------------------------------------------------------------------------------------------
+def scale_augmented_system_coo(I, J, src_V, scaling, n, m):
+    """_scale_augmented_system_coo_kernel! (/root/reference/scripts/cuda_wrapper.jl:90-111), all entries at once
+    (1-based I, J; k = position in the COO arrays): k <= n copied (pr_diag), Hessian block V * s_i * s_j, Jacobian
+    block V * s_j, dual-regularisation block copied.  Returns dest_V."""
+    I, J = np.asarray(I), np.asarray(J)
+    src_V = np.asarray(src_V, dtype=np.float64)
+    k = np.arange(1, src_V.size + 1)
+    dest = src_V.copy()
+    hess = (k > n) & (I <= n) & (J <= n)
+    dest[hess] = src_V[hess] * scaling[I[hess] - 1] * scaling[J[hess] - 1]
+    jac = (k > n) & (I >= n + 1) & (I <= n + m) & (J <= n)
+    dest[jac] = src_V[jac] * scaling[J[jac] - 1]
+    return dest
+
+
 def scale_qp(qp, max_iter=10, tol=0.0):
     """scale_qp, /root/reference/scripts/common.jl:46-100.  (Dr, Dc) = HSL.mc77(A, 0) there: HSL is proprietary and
     un-vendored, so the published algorithm is restated (D. Ruiz, RAL-TR-2001-034: simultaneous row / column sweeps
@@ -487,13 +502,7 @@ class MPCOracle:
             src = self.aug_V
             src[:n] = self.pr_diag
             src[self._off_du:] = self.du_diag
-            i, j, s = self._aug_I, self._aug_J, self.scaling_factor
-            k = np.arange(1, src.size + 1)
-            dest = src.copy()                                   # k <= n and the dual-regularisation block: copied
-            hess = (k > n) & (i <= n) & (j <= n)
-            dest[hess] = src[hess] * s[i[hess] - 1] * s[j[hess] - 1]
-            jac = (k > n) & (i >= n + 1) & (i <= n + m) & (j <= n)
-            dest[jac] = src[jac] * s[j[jac] - 1]
+            dest = scale_augmented_system_coo(self._aug_I, self._aug_J, src, self.scaling_factor, n, m)
             transfer(self.aug_nzval, dest, self.aug_csc_map)
         elif self._k2:
             n = self.n

@@ -10,6 +10,7 @@ dense / brute-force Python that shares no code with oracle/ or the product:
   transfer!            (scripts/cuda_wrapper.jl:17-28)         = dest[map[k]] += src[k]
   get_alpha_max_*      (kernels.jl:242-288)                    = left fold with init (1.0, 0)
   simple_lp            (test/runtests.jl:24-55)                = objective 1.0 (analytic)
+  _scale_augmented_system_coo_kernel! (scripts/cuda_wrapper.jl:90-111) = its branch list, entry by entry (K2.5 build)
 
 Values are small integers / dyadic rationals so every product and sum is exact in binary64 and
 the fixtures can be compared bit-for-bit.  Run:  python tests/golden/make_golden.py
@@ -69,6 +70,22 @@ def fold_argmin(vals):
     return acc
 
 
+def golden_scale_aug_coo(I, J, V, scaling, n, m):
+    """cuda_wrapper.jl:90-111, one entry at a time exactly as the kernel's branches read (1-based k, i, j)."""
+    dest = [None] * len(V)
+    for k in range(1, len(V) + 1):
+        i, j = int(I[k - 1]), int(J[k - 1])
+        if k <= n:                                             # primal regularisation pr_diag
+            dest[k - 1] = float(V[k - 1])
+        elif i <= n and j <= n:                                # Hessian block
+            dest[k - 1] = float(V[k - 1] * scaling[i - 1] * scaling[j - 1])
+        elif n + 1 <= i <= n + m and j <= n:                   # Jacobian block
+            dest[k - 1] = float(V[k - 1] * scaling[j - 1])
+        elif n + 1 <= i <= n + m and n + 1 <= j <= n + m:      # dual regularisation du_diag
+            dest[k - 1] = float(V[k - 1])
+    return dest
+
+
 def main():
     out = {}
     cases = []
@@ -96,6 +113,19 @@ def main():
         v, i = fold_argmin(vals)
         folds.append(dict(vals=[("inf" if np.isinf(x) else x) for x in vals], value=v, index=i))
     out["argmin_fold"] = folds
+    # K2.5: aug COO in the block order pr_diag | tril(H) | J (rows + n) | slack | du_diag (cuda_wrapper.jl:95-107)
+    n, m = 4, 3
+    rng = np.random.default_rng(11)
+    hI, hJ = [1, 2, 3, 3, 4, 4], [1, 1, 2, 3, 1, 4]                       # lower triangle incl. some diagonal entries
+    jI, jJ = [1, 1, 2, 2, 3, 3], [1, 3, 2, 4, 1, 4]
+    I = list(range(1, n + 1)) + hI + [i + n for i in jI] + [n + 2] + list(range(n + 1, n + m + 1))
+    J = list(range(1, n + 1)) + hJ + jJ + [4] + list(range(n + 1, n + m + 1))   # one slack-like extra Jacobian entry (row 2, col 4)
+    V = rng.integers(-6, 7, len(I)).astype(float)
+    V[V == 0] = 2.0
+    scaling = (2.0 ** rng.integers(-3, 4, n)).tolist()                    # dyadic: every product is exact
+    out["scale_aug_coo"] = dict(n=n, m=m, I=I, J=J, V=V.tolist(), scaling=scaling,
+                                dest=golden_scale_aug_coo(I, J, V, scaling, n, m),
+                                source="/root/reference/scripts/cuda_wrapper.jl:90-111")
     out["simple_lp"] = dict(objective=1.0, solution=[0.5, 0.5], source="/root/reference/test/runtests.jl:24-55")
     with open(os.path.join(HERE, "reference_definitions.json"), "w") as f:
         json.dump(out, f, indent=1)

@@ -135,3 +135,16 @@ def test_normal_kkt_system_consistency():
     s.set_predictive_rhs()
     s.solve_system(s.d, s.p)
     assert s.last_residual_ratio <= 1e-10
+
+
+def test_scale_augmented_system_coo_golden(golden):
+    """K2.5 build, /root/reference/scripts/cuda_wrapper.jl:90-111: the oracle against the kernel's branch list applied
+    entry by entry (dyadic values, exact products -> bit-exact)."""
+    g = golden["scale_aug_coo"]
+    dest = O.scale_augmented_system_coo(np.array(g["I"]), np.array(g["J"]), np.array(g["V"]), np.array(g["scaling"]), g["n"], g["m"])
+    assert None not in g["dest"]                       # every entry of the fixture falls in one of the four blocks
+    assert np.array_equal(dest, np.array(g["dest"]))
+    # blocks: first n copied, last m copied, something in between actually scaled
+    n, m = g["n"], g["m"]
+    assert np.array_equal(dest[:n], np.array(g["V"])[:n]) and np.array_equal(dest[-m:], np.array(g["V"])[-m:])
+    assert not np.array_equal(dest[n:-m], np.array(g["V"])[n:-m])
