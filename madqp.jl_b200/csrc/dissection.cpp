@@ -145,7 +145,6 @@ struct Dissector {
             return;
         }
         // pseudo-peripheral root: walk to a min-degree vertex of the last level while depth grows
-        int32_t root = verts[0];
         int32_t nlev = static_cast<int32_t>(lstart.size()) - 1;
         for (int it = 0; it < 6; ++it) {
             int32_t best = -1;
@@ -158,12 +157,13 @@ struct Dissector {
             std::vector<int32_t> out2, ls2;
             int32_t st2 = 0;
             int32_t nl2 = bfs(best, rid, out2, ls2, st2);
-            if (nl2 > nlev) { root = best; nlev = nl2; bfs_out.swap(out2); lstart.swap(ls2); st = st2; }
-            else { // keep the deeper structure; level[] must match bfs_out
-                std::vector<int32_t> o3, l3;
-                bfs(root, rid, o3, l3, st);
-                bfs_out.swap(o3);
-                lstart.swap(l3);
+            if (nl2 > nlev) { nlev = nl2; bfs_out.swap(out2); lstart.swap(ls2); st = st2; }
+            else { // keep the deeper structure; level[] and stamp[] must match bfs_out again: the trial BFS overwrote
+                   // them, and (bfs_out, lstart) hold everything a BFS from `root` would write, so one linear pass
+                   // restores them (same values as the BFS it replaces)
+                st = stamp_counter.fetch_add(1, std::memory_order_relaxed) + 1;
+                for (int32_t l = 0; l < nlev; ++l)
+                    for (int32_t q = lstart[l]; q < lstart[l + 1]; ++q) { level[bfs_out[q]] = l; stamp[bfs_out[q]] = st; }
                 break;
             }
         }

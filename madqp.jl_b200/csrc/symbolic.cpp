@@ -634,7 +634,7 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
     // ---- 7. assembly map: CSC nz (i, j) -> slot of (max(pi,pj), min(pi,pj)) in its panel.
     // Independent per column: computed by a few host threads while steps 7b and 8 run on this one (joined before return).
     S.asm_map.assign(S.nnz_lower, -1);
-    std::exception_ptr asm_err;
+    std::exception_ptr asm_err, sc_err;       // (declared before the joiner below: the threads write them)
     std::atomic<bool> asm_failed{false};
     auto asm_range = [&](int32_t j0, int32_t j1) {
         try {
@@ -670,8 +670,10 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
     if (asm_failed.load() && asm_threads.empty()) std::rethrow_exception(asm_err);
 
     clk.lap("assembly map");
-    // ---- 7b. scatter tables for the right-looking update
-    {
+    // ---- 7b. scatter tables for the right-looking update (reads the row structures only; step 8 does not read the
+    // tables, so for large patterns they are filled by one more host thread while the schedule is built)
+    auto scatter_tables = [&]() {
+      try {
         const size_t nr = S.sn_rows.size();
         S.row_colbase.assign(nr, 0);
         S.row_relbase.assign(nr, Symbolic::kRelSearch);
@@ -722,7 +724,11 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
                 jb = je;
             }
         }
-    }
+    
+      } catch (...) { sc_err = std::current_exception(); }
+    };
+    if (n >= 50000) asm_threads.emplace_back(scatter_tables);
+    else { scatter_tables(); if (sc_err) std::rethrow_exception(sc_err); }
 
     clk.lap("scatter tables");
     // ---- 8. schedule by height (see symbolic.hpp)
@@ -843,7 +849,8 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
     clk.lap("schedule");
     for (auto& t : asm_threads) t.join();
     if (asm_failed.load()) std::rethrow_exception(asm_err);
-    clk.lap("assembly map (joined)");
+    if (sc_err) std::rethrow_exception(sc_err);
+    clk.lap("maps + tables (joined)");
 }
 
 }  // namespace madipm
