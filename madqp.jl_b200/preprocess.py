@@ -39,3 +39,41 @@ def scale_qp(qp, max_iter=None, tol=None, device=0):
     out = dataclasses.replace(qp, name=qp.name + "-ruiz", c=c, H_vals=hV, A_vals=jV, lcon=lcon, ucon=ucon, lvar=lvar,
                               uvar=uvar, x0=x0, y0=y0, meta=dict(qp.meta, ruiz=True))
     return out, Dr, Dc, dict(sweeps=sweeps.value, err=err.value, launches=int(opt.launches))
+
+
+def standard_form_qp(qp):
+    """standard_form_qp (/root/reference/scripts/common.jl:129-288), host side like the reference's: slack variables
+    s = A x for the inequality rows (columns n+1..n+ns, entries -1), and every RANGE bound of x or s moved into an
+    equality row  x_i + w_k = xu_i  with a new nonnegative variable w_k (columns n+ns+1..).  Index and copy work only,
+    no arithmetic: the result is the reference's model entry for entry (COO order [A | slack | range pairs]).
+    Variables with only an upper bound keep it; fixed variables stay fixed (common.jl:254-257)."""
+    n, m = qp.nvar, qp.ncon
+    lvar, uvar = np.asarray(qp.lvar, dtype=np.float64), np.asarray(qp.uvar, dtype=np.float64)
+    lcon, ucon = np.asarray(qp.lcon, dtype=np.float64), np.asarray(qp.ucon, dtype=np.float64)
+    ind_ineq = np.flatnonzero(lcon < ucon)                                         # l.164-168
+    ns = ind_ineq.size
+    fixed = np.flatnonzero(lvar == uvar)                                           # l.177-179
+    rng_x = np.flatnonzero((lvar != uvar) & (-np.inf < lvar) & (lvar < uvar) & (uvar < np.inf))   # l.180-183
+    li, ui = lcon[ind_ineq], ucon[ind_ineq]
+    rng_s = np.flatnonzero((-np.inf < li) & (li < ui) & (ui < np.inf))             # l.191-195
+    ind_rng = np.concatenate([rng_x, n + rng_s])                                   # 0-based columns of [x | s]
+    xu = np.concatenate([uvar[rng_x], ui[rng_s]])
+    nw = ind_rng.size
+    nvar, ncon = n + ns + nw, m + nw
+    k = np.arange(nw)
+    A_rows = np.concatenate([qp.A_rows, ind_ineq, np.repeat(m + k, 2)])            # l.212-233
+    A_cols = np.concatenate([qp.A_cols, n + np.arange(ns), np.stack([ind_rng, n + ns + k], axis=1).ravel()])
+    A_vals = np.concatenate([np.asarray(qp.A_vals, dtype=np.float64), np.full(ns, -1.0), np.ones(2 * nw)])
+    lcon_, ucon_ = np.zeros(ncon), np.zeros(ncon)                                  # l.236-253
+    eq = ~(lcon < ucon)
+    lcon_[:m][eq], ucon_[:m][eq] = lcon[eq], ucon[eq]
+    lcon_[m:], ucon_[m:] = xu, xu
+    lvar_ = np.concatenate([lvar, li, np.zeros(nw)])                               # l.255-260
+    uvar_ = np.concatenate([uvar, ui, np.full(nw, np.inf)])
+    uvar_[ind_rng] = np.inf
+    uvar_[fixed] = uvar[fixed]
+    z = np.zeros(ns + nw)
+    return dataclasses.replace(
+        qp, name=qp.name + "-std", nvar=nvar, ncon=ncon, c=np.concatenate([qp.c, z]), A_rows=A_rows.astype(qp.A_rows.dtype),
+        A_cols=A_cols.astype(qp.A_cols.dtype), A_vals=A_vals, lcon=lcon_, ucon=ucon_, lvar=lvar_, uvar=uvar_,
+        x0=np.concatenate([qp.x0, z]), y0=np.concatenate([qp.y0, np.zeros(nw)]), meta=dict(qp.meta, standard_form=True))

@@ -145,6 +145,57 @@ def scale_augmented_system_coo(I, J, src_V, scaling, n, m):
     return dest
 
 
+def standard_form_qp(qp):
+    """standard_form_qp, /root/reference/scripts/common.jl:156-288, loop for loop (1-based inside, like the Julia)."""
+    import dataclasses
+    n, m = qp.nvar, qp.ncon
+    lvar, uvar, lcon, ucon = (np.asarray(a, dtype=np.float64) for a in (qp.lvar, qp.uvar, qp.lcon, qp.ucon))
+    ind_ineq = [i for i in range(1, m + 1) if lcon[i - 1] < ucon[i - 1]]                      # l.164-168
+    ns = len(ind_ineq)
+    ind_rng, ind_only_ub, ind_fixed, xu = [], [], [], []
+    for i in range(1, n + 1):                                                                # l.176-188
+        if lvar[i - 1] == uvar[i - 1]:
+            ind_fixed.append(i)
+        elif -np.inf < lvar[i - 1] < uvar[i - 1] < np.inf:
+            ind_rng.append(i); xu.append(uvar[i - 1])
+        elif uvar[i - 1] < np.inf:
+            ind_only_ub.append(i)
+    for k, i in enumerate(ind_ineq, start=1):                                                # l.191-199
+        if -np.inf < lcon[i - 1] < ucon[i - 1] < np.inf:
+            ind_rng.append(k + n); xu.append(ucon[i - 1])
+        elif ucon[i - 1] < np.inf:
+            ind_only_ub.append(k + n)
+    nw = len(ind_rng)
+    nvar, ncon = n + ns + nw, m + nw
+    Bi, Bj, Bx = [], [], []
+    for k, i in enumerate(ind_ineq, start=1):                                                # l.214-219
+        Bi.append(i); Bj.append(n + k); Bx.append(-1.0)
+    for k, i in enumerate(ind_rng, start=1):                                                 # l.221-230
+        Bi.append(m + k); Bj.append(i); Bx.append(1.0)
+        Bi.append(m + k); Bj.append(k + n + ns); Bx.append(1.0)
+    lcon_, ucon_ = np.zeros(ncon), np.zeros(ncon)
+    for i in range(1, m + 1):                                                                # l.238-248
+        if not (lcon[i - 1] < ucon[i - 1]):
+            lcon_[i - 1], ucon_[i - 1] = lcon[i - 1], ucon[i - 1]
+    for k, i in enumerate(ind_rng, start=1):                                                 # l.249-252
+        lcon_[m + k - 1] = xu[k - 1]; ucon_[m + k - 1] = xu[k - 1]
+    ineq0 = np.array(ind_ineq, dtype=np.int64) - 1
+    lvar_ = np.concatenate([lvar, lcon[ineq0], np.zeros(nw)])                                # l.254-259
+    uvar_ = np.concatenate([uvar, ucon[ineq0], np.full(nw, np.inf)])
+    for i in ind_rng:
+        uvar_[i - 1] = np.inf
+    for i in ind_fixed:
+        uvar_[i - 1] = uvar[i - 1]
+    z = np.zeros(ns + nw)
+    return dataclasses.replace(
+        qp, name=qp.name + "-std", nvar=nvar, ncon=ncon, c=np.concatenate([qp.c, z]),
+        A_rows=np.concatenate([qp.A_rows, np.array(Bi, dtype=np.int64) - 1]).astype(qp.A_rows.dtype),
+        A_cols=np.concatenate([qp.A_cols, np.array(Bj, dtype=np.int64) - 1]).astype(qp.A_cols.dtype),
+        A_vals=np.concatenate([np.asarray(qp.A_vals, dtype=np.float64), np.array(Bx, dtype=np.float64)]),
+        lcon=lcon_, ucon=ucon_, lvar=lvar_, uvar=uvar_, x0=np.concatenate([qp.x0, z]),
+        y0=np.concatenate([qp.y0, np.zeros(nw)]), meta=dict(qp.meta, standard_form=True))
+
+
 def scale_qp(qp, max_iter=10, tol=0.0):
     """scale_qp, /root/reference/scripts/common.jl:46-100.  (Dr, Dc) = HSL.mc77(A, 0) there: HSL is proprietary and
     un-vendored, so the published algorithm is restated (D. Ruiz, RAL-TR-2001-034: simultaneous row / column sweeps
