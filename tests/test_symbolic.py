@@ -278,3 +278,40 @@ def test_nested_dissection_does_not_depend_on_host_threads(monkeypatch):
     assert sorted(perms[0].tolist()) == list(range(perms[0].size))
     for p in perms[1:]:
         assert np.array_equal(p, perms[0])
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/madipm_b200.h must compile as C99 (what a ccall / cgo / ctypes binding
+    assumes), and a C program must link against the library and drive the host-side entry points."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "include", "madipm_b200.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    src = tmp_path / "drive.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "madipm_b200.h"
+int main(void) {
+    madipm_config cfg; madipm_handle* h = 0; madipm_info info; madipm_scale_options so;
+    madipm_default_config(&cfg);
+    cfg.kkt_kind = MADIPM_KKT_K2_SCALED;
+    if (madipm_create(&cfg, &h) != MADIPM_OK) return 1;
+    /* min x1 + x2  s.t. x1 + x2 = 1, x >= 0  (simple_lp of the reference's tests) */
+    int32_t jI[2] = {1, 1}, jJ[2] = {1, 2};
+    int64_t lb[2] = {1, 2};
+    if (madipm_set_pattern_k2(h, 2, 1, 0, 0, 0, 2, jI, jJ, 0, 0) != MADIPM_OK) return 2;
+    if (madipm_set_bounds_index(h, 2, lb, 0, 0) != MADIPM_OK) return 3;
+    if (madipm_analyze(h) != MADIPM_OK) return 4;
+    if (madipm_get_info(h, &info) != MADIPM_OK) return 5;
+    madipm_default_scale_options(&so);
+    printf("%s kind=%d order=%d nlb=%d sweeps=%d\n", madipm_version(), info.kkt_kind, info.kkt_order, info.nlb, so.max_iter);
+    return madipm_destroy(h);
+}
+''')
+    exe = tmp_path / "drive"
+    lib_dir = os.path.join(root, "madqp.jl_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                           "-L", lib_dir, "-l:libmadipm_b200.so", "-Wl,-rpath," + lib_dir])
+    out = subprocess.check_output([str(exe)], text=True)
+    assert "kind=2 order=3 nlb=2 sweeps=10" in out, out
