@@ -38,6 +38,38 @@ from madqp_jl_b200 import problems  # noqa: E402
 
 METRIC, UNIT = "ipm_iters_per_sec", "iter/s"
 
+_T0 = time.perf_counter()
+_PHASE = ["start"]
+
+
+def progress(phase):
+    """Timestamped phase marker on stderr (stdout carries only the JSON line); the guard reports the last one."""
+    _PHASE[0] = phase
+    sys.stderr.write(f"[bench {time.perf_counter() - _T0:7.1f}s] {phase}\n")
+    sys.stderr.flush()
+
+
+def start_guard(limit_s, args):
+    """Wall-clock guard: a run that is still going after limit_s prints the Python stacks and ONE JSON line with an
+    "error" key, then exits non-zero -- it never dies mute (rc 124 with empty output)."""
+    import faulthandler
+    if limit_s <= 0:
+        return
+    faulthandler.dump_traceback_later(max(1.0, limit_s - 2.0), exit=False, file=sys.stderr)
+
+    def fire():
+        line = dict(metric=METRIC, value=None, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                    error=f"bench.py guard: still in phase '{_PHASE[0]}' after {limit_s:.0f} s", phase=_PHASE[0],
+                    impl=args.impl)
+        try:
+            emit(line)
+        finally:
+            os._exit(3)
+
+    t = threading.Timer(limit_s, fire)
+    t.daemon = True
+    t.start()
+
 
 def make_workload(name, scale=1.0, seed=0):
     s = scale
@@ -195,6 +227,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    progress(f"generate workload {args.workload}")
     qps, kkt, wname = make_workload(args.workload, args.scale)
     from madqp_jl_b200 import batch
     sharded = args.workload == "C5" and world > 1
@@ -202,6 +235,7 @@ def run_ours(args):
     if sharded:   # independent instances: rank r takes a contiguous slice, no data-path collective
         lo, hi = batch.shard_range(n_items, rank, world)
         qps = qps[lo:hi]
+    progress("symbolic analysis + device setup")
     solver = MPCSolver(qps if len(qps) > 1 else qps[0], kkt_system=kkt, device=local, **solver_options())
     solver.keep_snapshot = True
     h = solver.h
@@ -210,7 +244,8 @@ def run_ours(args):
 
     # ---- warm-up (full end-to-end solves)
     stats = None
-    for _ in range(max(args.warmup, 1)):
+    for k in range(max(args.warmup, 1)):
+        progress(f"warm-up solve {k + 1}")
         stats = solver.solve()
     iters_per_solve = float(np.sum(stats.iter))
     ok = all(s == "SOLVE_SUCCEEDED" for s in stats.status)
@@ -248,7 +283,9 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    progress("timed: device-resident solves")
     res = timed(resident=True)
+    progress("timed: end-to-end solves (host buffers)")
     e2e = timed(resident=False)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -256,6 +293,7 @@ def run_ours(args):
     #      device-resident solve with them, reported beside the headline, not part of `value`
     ncorr3 = None
     if world == 1 and not sharded:
+        progress("extra: max_ncorr=3 solve")
         solver.opt.max_ncorr = 3
         solver.solve(resident=True)
         h.synchronize()
@@ -320,6 +358,7 @@ def run_ours(args):
                             factor_tflops=tf)
         cpu = None
         if world == 1 and not args.no_cpu:
+            progress("cpu_baseline sample (oracle, host cores)")
             v, desc, _ = cpu_sample(qps[0], kkt, budget_s=args.cpu_budget)
             cpu = dict(value=v, unit=UNIT, cores=1, kind="port", sample=desc)
         n_rep = world if not sharded else 1
@@ -343,6 +382,7 @@ def run_ours(args):
             analysis_s=solver.analysis_time, wall_s_resident=res["wall"], gondzio_max_ncorr_3=ncorr3,
         )
         emit(line)
+    progress("done")
     solver.close()
     if world > 1:
         dist.destroy_process_group()
@@ -373,7 +413,9 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the oracle sample")
     ap.add_argument("--cpu-iters", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--guard-s", type=float, default=1500.0, help="wall-clock limit after which an error line is printed (0 = off)")
     args = ap.parse_args()
+    start_guard(args.guard_s, args)
     if args.impl == "reference":
         run_reference(args)
     else:

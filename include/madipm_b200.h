@@ -294,6 +294,19 @@ enum { MADIPM_T_ASSEMBLY = 0, MADIPM_T_FACTOR, MADIPM_T_SOLVE, MADIPM_T_SPMV, MA
 int32_t madipm_profile(madipm_handle* h, int32_t enable);
 int32_t madipm_profile_read(madipm_handle* h, double* ms, int64_t* calls, int32_t reset);
 
+/* ---- hang guards (the reference has none: it never spins on the device) --------------------------------------------
+ * The persistent tree kernels synchronise the grid with a counter in global memory.  That spin is bounded
+ * (MADIPM_BARRIER_TIMEOUT_MS, default 2000): a block that runs out of patience raises a flag that makes the whole grid
+ * leave, and the next synchronising entry point returns MADIPM_INTERNAL with the barrier's state in madipm_last_error.
+ * Every host-side stream synchronisation is bounded as well (MADIPM_SYNC_TIMEOUT_S, default 120; 0 = unbounded); on
+ * expiry the call returns MADIPM_INTERNAL and the handle is wedged (every later numeric call fails at once).
+ * madipm_debug_barrier_state: copy of the device-written record (host-visible memory: readable while a kernel is stuck);
+ * out8 = {aborted, kernel, op, height, block, grid, seen, target}.
+ * madipm_debug_inject_barrier_fault: test hook -- the next tree launch starts with a barrier counter that can never
+ * reach its target, so the guards above can be exercised on purpose (tests/test_gpu_guards.py). */
+int32_t madipm_debug_barrier_state(madipm_handle* h, int64_t* out8);
+int32_t madipm_debug_inject_barrier_fault(madipm_handle* h);
+
 /* ---- fused iteration phases: one host synchronisation each ------------------------------------------ */
 /* The reference synchronises once per reduction (~22 per iteration); the separate entry points above once per returned
  * group of scalars (7 per iteration); these three bring an iteration of mpc! (solver.jl:254-345) to 3. */

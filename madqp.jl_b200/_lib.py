@@ -128,6 +128,8 @@ _SIGNATURES = {
     "madipm_launch_count": ([], C.c_int64),
     "madipm_profile": ([C.c_int32], C.c_int32),
     "madipm_profile_read": ([_PD, _P64, C.c_int32], C.c_int32),
+    "madipm_debug_barrier_state": ([_P64], C.c_int32),
+    "madipm_debug_inject_barrier_fault": ([], C.c_int32),
     "madipm_phase_residuals_obj": ([C.c_double, _PD, _PD], C.c_int32),
     "madipm_phase_predictor": ([_PD, _PD], C.c_int32),
     "madipm_phase_corrector": ([_PD, _PD, _PD, _PD], C.c_int32),
@@ -448,6 +450,15 @@ class Handle:
     # -- measurement
     def launch_count(self):
         return int(self.lib.madipm_launch_count(self._h))
+
+    def debug_barrier_state(self):
+        """What the first grid barrier that gave up saw (host-visible memory: readable while a kernel is stuck)."""
+        out = np.zeros(8, dtype=np.int64)
+        self._check(self.lib.madipm_debug_barrier_state(self._h, _p64(out)))
+        return dict(zip("aborted kernel op height block grid seen target".split(), (int(v) for v in out)))
+
+    def debug_inject_barrier_fault(self):
+        self._check(self.lib.madipm_debug_inject_barrier_fault(self._h))
 
     def profile(self, level=1):
         """1: every class with a sync per call (diagnostics); 2: factorisation only, no extra sync; 0: off."""

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -43,13 +44,16 @@ struct DeviceState {
     int* tickets[3] = {nullptr, nullptr, nullptr};
     int* phase_cls = nullptr;
     int num_sms = 0;
-    unsigned bar_base = 0;             // value of *bar before the next launch (barriers only ever add to it)
+    unsigned* abort_flag = nullptr;    // device: a grid barrier gave up (kernels_tree.cuh grid_barrier)
+    TreeDebug* tree_dbg = nullptr;     // mapped pinned host memory: what that barrier saw
+    unsigned aborts_seen = 0;          // value of tree_dbg->aborted already reported
+    double sync_timeout_s = 120.0;     // host-side limit for one stream synchronisation (MADIPM_SYNC_TIMEOUT_S)
+    long long spin_budget_ns = 2000000000ll;   // device-side limit for one block at one grid barrier (MADIPM_BARRIER_TIMEOUT_MS)
     int* par_pos = nullptr;
     SnMeta* sn_meta = nullptr;
     ChildRec* child_rec = nullptr;
     double *Cx = nullptr, *cvec = nullptr;
     int64_t cx_stride = 0, cv_stride = 0;
-    unsigned* bar = nullptr;
     std::vector<int> big_ptr;          // big (multi-block) supernodes, per height
     std::vector<int> big_rowblocks, big_rowblocks512, big_tiles, big_panelblocks;   // per height: grid sizes (max over its big supernodes)
     bool big_use_panel = false;
@@ -114,6 +118,8 @@ struct DeviceState {
 
     const Symbolic* sym = nullptr;
     bool values_set = false;
+    bool inject_barrier_fault = false; // test hook: see madipm_debug_inject_barrier_fault
+    bool wedged = false;               // a synchronisation timed out: the stream still holds a kernel that never returns
     int profiling = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     double t_ms[MADIPM_T_COUNT] = {};
@@ -194,7 +200,8 @@ TreeView make_tree_view(const DeviceState& d) {
     T.meta = d.sn_meta; T.crec = d.child_rec; T.par_pos = d.par_pos;
     T.Cx = d.Cx; T.cx_stride = d.cx_stride; T.cvec = d.cvec; T.cv_stride = d.cv_stride;
     T.image = nullptr; T.dperm = nullptr;
-    T.xw = d.xw; T.xw_stride = d.N; T.bar = d.bar; T.B = d.B; T.tickets = nullptr; T.phase_cls = d.phase_cls;
+    T.xw = d.xw; T.xw_stride = d.N; T.bar = nullptr; T.B = d.B; T.tickets = nullptr; T.phase_cls = d.phase_cls;
+    T.abort_flag = d.abort_flag; T.dbg = d.tree_dbg; T.spin_budget_ns = d.spin_budget_ns;
     for (int c = 0; c < 4; ++c) { T.slice[c] = d.sym->tree_slice[c]; T.cap[c] = d.sym->tree_cap[c]; T.maxh[c] = d.sym->tree_maxh[c]; }
     T.maxw = d.tree_maxw;
     {   // MADIPM_DBG_SN=a,b,...: supernodes whose stage clocks a MADIPM_TREE_TIMING build prints
@@ -228,6 +235,54 @@ struct Timer {
     }
 };
 
+// Every synchronisation of the handle's stream goes through here.  Two guards (a grid that never returned
+// pinned a GPU for 30 minutes without a word):
+//   * the wait is bounded (MADIPM_SYNC_TIMEOUT_S, default 120 s, 0 = plain cudaStreamSynchronize): on expiry the call
+//     returns MADIPM_INTERNAL with whatever the kernels left in the host-visible debug record, and the handle is marked
+//     wedged (its destructor then leaks instead of blocking in cudaFree);
+//   * a grid barrier that gave up on the device (bounded spin, kernels_tree.cuh) surfaces here as MADIPM_INTERNAL.
+std::string describe_tree_debug(const DeviceState* d) {
+    const TreeDebug g = d->tree_dbg ? *d->tree_dbg : TreeDebug{};
+    if (!g.aborted) return "no grid barrier reported a timeout";
+    static const char* kn[] = {"k_tree", "k_tree_top"};
+    static const char* on[] = {"factor", "forward", "backward"};
+    char buf[320];
+    std::snprintf(buf, sizeof(buf), "grid barrier timed out: %s<%s> after height %d, block %u of %u saw %u arrivals, waited for %u, for %.0f ms",
+                  kn[g.kernel & 1], on[g.op % 3], g.phase, g.block, g.grid, g.seen, g.target, g.waited_ns / 1e6);
+    return buf;
+}
+
+int32_t sync_stream(madipm_handle* h) {
+    DeviceState* d = h->dev;
+    if (d->wedged) { h->error = "handle is wedged by an earlier synchronisation timeout"; return MADIPM_INTERNAL; }
+    cudaError_t e;
+    if (d->sync_timeout_s <= 0.0) {
+        e = cudaStreamSynchronize(d->stream);
+    } else {
+        const auto t0 = std::chrono::steady_clock::now();
+        unsigned polls = 0;
+        while ((e = cudaStreamQuery(d->stream)) == cudaErrorNotReady) {
+            if ((++polls & 0xfffu) == 0 &&
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > d->sync_timeout_s) {
+                char buf[128];
+                std::snprintf(buf, sizeof(buf), "stream still busy after %.0f s (MADIPM_SYNC_TIMEOUT_S); ", d->sync_timeout_s);
+                h->error = std::string(buf) + describe_tree_debug(d);
+                d->wedged = true;
+                return MADIPM_INTERNAL;
+            }
+        }
+    }
+    if (e != cudaSuccess) { h->error = std::string("stream synchronisation: ") + cudaGetErrorString(e); return MADIPM_CUDA_ERROR; }
+    if (d->tree_dbg && d->tree_dbg->aborted != d->aborts_seen) {
+        d->aborts_seen = d->tree_dbg->aborted;
+        h->error = describe_tree_debug(d);
+        cudaMemsetAsync(d->abort_flag, 0, sizeof(unsigned), d->stream);      // the next launch starts clean
+        cudaStreamSynchronize(d->stream);
+        return MADIPM_INTERNAL;
+    }
+    return MADIPM_OK;
+}
+
 // what an asynchronous factorisation left behind: enqueue before a synchronisation, collect after it
 int32_t pending_enqueue(madipm_handle* h) {
     DeviceState* d = h->dev;
@@ -257,7 +312,7 @@ int32_t fetch(madipm_handle* h, const double* dsrc, double* hdst, size_t count) 
     int32_t rc;
     if ((rc = pending_enqueue(h))) return rc;
     CUDA_OK(h, cudaMemcpyAsync(d->h_out, dsrc, count * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
-    CUDA_OK(h, cudaStreamSynchronize(d->stream));
+    { int32_t rc_ = sync_stream(h); if (rc_) return rc_; }
     CUDA_OK(h, cudaGetLastError());
     pending_collect(h);
     std::memcpy(hdst, d->h_out, count * sizeof(double));
@@ -382,26 +437,33 @@ int32_t launch_tree(madipm_handle* h, const DeviceState::TreeSeg& sg) {
     T.tickets = d->tickets[OP];
     if (OP == 0 && d->image_valid) { T.image = d->P0; T.dperm = d->dperm; }
     const bool reverse = OP == 2;
+    // one memset clears everything the two launches of this segment synchronise on: the tickets of its heights and the
+    // barrier counters (slot kSyncBar of the first height each launch walks)
+    if (sg.ph1 > sg.ph0)
+        CUDA_OK(h, cudaMemsetAsync(d->tickets[OP] + kSyncStride * sg.ph0, 0, sizeof(int) * kSyncStride * (sg.ph1 - sg.ph0), d->stream));
+    if (d->inject_barrier_fault) {     // counters start at 0x80000000: no barrier of this segment can complete
+        d->inject_barrier_fault = false;
+        for (int ph : {sg.ph0, sg.split})
+            if (ph < sg.ph1)
+                CUDA_OK(h, cudaMemsetAsync(reinterpret_cast<char*>(d->tickets[OP] + kSyncStride * ph + kSyncBar) + 3, 0x80, 1, d->stream));
+    }
     auto bottom = [&]() -> int32_t {
         if (sg.split <= sg.ph0 || sg.grid[OP] <= 0) return MADIPM_OK;
-        CUDA_OK(h, cudaMemsetAsync(d->tickets[OP] + 4 * sg.ph0, 0, sizeof(int) * 4 * (sg.split - sg.ph0), d->stream));
         int b = reverse ? sg.split - 1 : sg.ph0, e = reverse ? sg.ph0 - 1 : sg.split, step = reverse ? -1 : 1;
-        unsigned base = d->bar_base;
-        void* args[] = {&T, &b, &e, &step, &base};
+        T.bar = reinterpret_cast<unsigned*>(d->tickets[OP] + kSyncStride * sg.ph0 + kSyncBar);
+        void* args[] = {&T, &b, &e, &step};
         CUDA_OK(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_tree<OP>), dim3(sg.grid[OP]), dim3(kTreeThreads), args,
                                                d->smem_tree, d->stream));
-        d->bar_base += static_cast<unsigned>(sg.grid[OP]) * static_cast<unsigned>(sg.split - sg.ph0 - 1);
         ++h->launches;
         return MADIPM_OK;
     };
     auto top = [&]() -> int32_t {
         if (sg.ph1 <= sg.split || sg.grid_top <= 0) return MADIPM_OK;
         int b = reverse ? sg.ph1 - 1 : sg.split, e = reverse ? sg.split - 1 : sg.ph1, step = reverse ? -1 : 1;
-        unsigned base = d->bar_base;
-        void* args[] = {&T, &b, &e, &step, &base};
+        T.bar = reinterpret_cast<unsigned*>(d->tickets[OP] + kSyncStride * sg.split + kSyncBar);
+        void* args[] = {&T, &b, &e, &step};
         CUDA_OK(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_tree_top<OP>), dim3(sg.grid_top), dim3(kTopThreads), args,
                                                d->smem_tree, d->stream));
-        d->bar_base += static_cast<unsigned>(sg.grid_top) * static_cast<unsigned>(sg.ph1 - sg.split - 1);
         ++h->launches;
         return MADIPM_OK;
     };
@@ -620,8 +682,8 @@ int32_t device_create(madipm_handle* h) {
         if (pc.empty()) pc.assign(5, 0);
         UP(int, phase_cls, pc);
         for (int op = 0; op < 3; ++op) {
-            if ((rc = dev_alloc(h, &d->tickets[op], static_cast<size_t>(4) * std::max(1, s.n_levels)))) return rc;
-            CUDA_OK(h, cudaMemsetAsync(d->tickets[op], 0, sizeof(int) * 4 * std::max(1, s.n_levels), d->stream));
+            if ((rc = dev_alloc(h, &d->tickets[op], static_cast<size_t>(kSyncStride) * std::max(1, s.n_levels)))) return rc;
+            CUDA_OK(h, cudaMemsetAsync(d->tickets[op], 0, sizeof(int) * kSyncStride * std::max(1, s.n_levels), d->stream));
         }
     }
     std::vector<int64_t> diag_pos(d->N);
@@ -655,9 +717,12 @@ int32_t device_create(madipm_handle* h) {
     d->cv_stride = static_cast<int64_t>(s.sn_rows.size());
     if ((rc = dev_alloc(h, &d->Cx, static_cast<size_t>(B) * d->cx_stride + 4))) return rc;
     if ((rc = dev_alloc(h, &d->cvec, static_cast<size_t>(B) * d->cv_stride))) return rc;
-    if ((rc = dev_alloc(h, &d->bar, 1))) return rc;
-    CUDA_OK(h, cudaMemsetAsync(d->bar, 0, sizeof(unsigned), d->stream));
-    d->bar_base = 0;
+    if ((rc = dev_alloc(h, &d->abort_flag, 1))) return rc;
+    CUDA_OK(h, cudaMemsetAsync(d->abort_flag, 0, sizeof(unsigned), d->stream));
+    CUDA_OK(h, cudaHostAlloc(reinterpret_cast<void**>(&d->tree_dbg), sizeof(TreeDebug), cudaHostAllocMapped | cudaHostAllocPortable));
+    std::memset(d->tree_dbg, 0, sizeof(TreeDebug));
+    if (const char* e = std::getenv("MADIPM_SYNC_TIMEOUT_S")) d->sync_timeout_s = std::max(0.0, std::atof(e));
+    if (const char* e = std::getenv("MADIPM_BARRIER_TIMEOUT_MS")) d->spin_budget_ns = std::max(1ll, std::atoll(e)) * 1000000ll;
     d->num_sms = prop.multiProcessorCount;
     {
         // shared memory of the tree kernels: one 256-thread group or 2 / 4 / 8 smaller ones (sizes: symbolic.cpp step 8)
@@ -775,7 +840,7 @@ int32_t device_create(madipm_handle* h) {
     if ((rc = dev_alloc(h, &d->d_inertia, static_cast<size_t>(B) * 3))) return rc;
     LAUNCH(h, k_fill, dim3(1, 1), 256, 0, (int64_t)B, d->d_ones, (int64_t)0, 1.0);
     CUDA_OK(h, cudaMallocHost(reinterpret_cast<void**>(&d->h_out), static_cast<size_t>(B) * 32 * sizeof(double)));
-    CUDA_OK(h, cudaStreamSynchronize(d->stream));
+    { int32_t rc_ = sync_stream(h); if (rc_) return rc_; }
     return MADIPM_OK;
 }
 
@@ -783,10 +848,16 @@ void device_destroy(madipm_handle* h) {
     DeviceState* d = h->dev;
     if (!d) return;
     cudaSetDevice(d->device);
-    if (d->stream) cudaStreamSynchronize(d->stream);
+    if (d->stream && !d->wedged) sync_stream(h);
+    if (d->wedged) {                  // a kernel that never returns owns the stream: cudaFree would block for ever -- leak instead
+        delete d;
+        h->dev = nullptr;
+        return;
+    }
     for (void* p : d->allocs) cudaFree(p);
     if (d->h_out) cudaFreeHost(d->h_out);
     if (d->h_fail_pinned) cudaFreeHost(d->h_fail_pinned);
+    if (d->tree_dbg) cudaFreeHost(d->tree_dbg);
     if (d->ev0) cudaEventDestroy(d->ev0);
     if (d->ev1) cudaEventDestroy(d->ev1);
     if (d->ev2) cudaEventDestroy(d->ev2);
@@ -919,7 +990,7 @@ int32_t madipm_load_problem(madipm_handle* h, const double* x0, const double* lv
         LAUNCH(h, k_norm_inf, gm, kVecThreads, 0, (int64_t)m, d->vec[MADIPM_VEC_RHS], (int64_t)m, d->red_scratch, d->red_counter, d->d_out);
         if ((rc = fetch(h, d->d_out, norm_b, B))) return rc;
     } else {
-        CUDA_OK(h, cudaStreamSynchronize(d->stream));       // `os` is read by the copy above
+        { int32_t rc_ = sync_stream(h); if (rc_) return rc_; }       // `os` is read by the copy above
     }
     for (int b = 0; b < B; ++b) obj_scale[b] = os[b];
     return MADIPM_OK;
@@ -968,7 +1039,7 @@ int32_t madipm_vec_get(madipm_handle* h, int32_t vec, double* host) {
     DeviceState* d = h->dev;
     if (vec == MADIPM_VEC_KKT_NZVAL && (rc = refresh_nzval_diag(h))) return rc;
     CUDA_OK(h, cudaMemcpyAsync(host, d->vec[vec], sizeof(double) * d->B * d->veclen[vec], cudaMemcpyDeviceToHost, d->stream));
-    CUDA_OK(h, cudaStreamSynchronize(d->stream));
+    { int32_t rc_ = sync_stream(h); if (rc_) return rc_; }
     return MADIPM_OK;
 }
 
@@ -998,8 +1069,25 @@ int32_t madipm_synchronize(madipm_handle* h) {
     int32_t rc = check(h);
     if (rc) return rc;
     if ((rc = pending_enqueue(h))) return rc;
-    CUDA_OK(h, cudaStreamSynchronize(h->dev->stream));
+    { int32_t rc_ = sync_stream(h); if (rc_) return rc_; }
     pending_collect(h);
+    return MADIPM_OK;
+}
+
+int32_t madipm_debug_barrier_state(madipm_handle* h, int64_t* out8) {
+    if (!h || !out8) return MADIPM_BAD_ARGUMENT;
+    for (int k = 0; k < 8; ++k) out8[k] = 0;
+    if (!h->dev || !h->dev->tree_dbg) return MADIPM_OK;
+    const TreeDebug g = *h->dev->tree_dbg;
+    const int64_t v[8] = {g.aborted, g.kernel, g.op, g.phase, g.block, g.grid, g.seen, g.target};
+    for (int k = 0; k < 8; ++k) out8[k] = v[k];
+    return MADIPM_OK;
+}
+
+int32_t madipm_debug_inject_barrier_fault(madipm_handle* h) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    h->dev->inject_barrier_fault = true;
     return MADIPM_OK;
 }
 
@@ -1144,7 +1232,7 @@ int32_t madipm_factorize(madipm_handle* h, int32_t* n_failed) {
         }
         d->fail_pending = d->prof_pending = d->prof_tree_pending = false;
         CUDA_OK(h, cudaMemcpyAsync(d->h_fail.data(), d->fail, sizeof(int) * B, cudaMemcpyDeviceToHost, d->stream));
-        CUDA_OK(h, cudaStreamSynchronize(d->stream));
+        { int32_t rc_ = sync_stream(h); if (rc_) return rc_; }
         if (light) {
             float ms = 0;
             cudaEventElapsedTime(&ms, d->ev0, d->ev1);
@@ -1168,7 +1256,7 @@ int32_t madipm_is_factorized(madipm_handle* h, int32_t* flags) {
     if (!flags) return MADIPM_BAD_ARGUMENT;
     if (h->dev->fail_pending || h->dev->prof_pending) {
         if ((rc = pending_enqueue(h))) return rc;
-        CUDA_OK(h, cudaStreamSynchronize(h->dev->stream));
+        { int32_t rc_ = sync_stream(h); if (rc_) return rc_; }
         pending_collect(h);
     }
     for (int i = 0; i < h->dev->B; ++i) flags[i] = h->dev->h_fail[i] == 0;
@@ -1184,7 +1272,7 @@ int32_t madipm_inertia(madipm_handle* h, int32_t inst, int64_t* n_pos, int64_t* 
     LAUNCH(h, k_inertia, dim3(vec_blocks(d->N), d->B), kVecThreads, 0, d->N, d->diag_pos, d->Lx, d->lx_stride, d->d_inertia);
     std::vector<unsigned long long> out(3 * d->B);
     CUDA_OK(h, cudaMemcpyAsync(out.data(), d->d_inertia, sizeof(unsigned long long) * 3 * d->B, cudaMemcpyDeviceToHost, d->stream));
-    CUDA_OK(h, cudaStreamSynchronize(d->stream));
+    { int32_t rc_ = sync_stream(h); if (rc_) return rc_; }
     if (n_pos) *n_pos = out[inst * 3];
     if (n_zero) *n_zero = out[inst * 3 + 1];
     if (n_neg) *n_neg = out[inst * 3 + 2];

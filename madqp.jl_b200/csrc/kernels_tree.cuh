@@ -61,6 +61,23 @@ struct __align__(16) ChildRec {
     int32_t pad[2];
 };
 
+// Sync record of one height: tickets of the four task classes, then the grid-barrier counter of the launch that STARTS at
+// this height (32 bytes, so one cudaMemsetAsync over the heights of a launch clears everything the launch synchronises on).
+constexpr int kSyncStride = 8;
+constexpr int kSyncBar = 4;
+
+// Written (once) by the first block whose grid barrier ran out of patience; lives in mapped pinned host memory so that the
+// host can read it even while a kernel is still stuck.
+struct TreeDebug {
+    unsigned aborted;            // 0 = never; else 1 + number of aborts seen
+    unsigned kernel;             // 0 k_tree, 1 k_tree_top
+    unsigned op;                 // 0 factor, 1 forward, 2 backward
+    int phase;                   // height whose end-of-phase barrier gave up
+    unsigned block, grid;
+    unsigned seen, target;       // counter value last read, value waited for
+    unsigned long long waited_ns;
+};
+
 struct TreeView {
     FactorView F;
     const SnMeta* meta;          // [number of tasks], in task order
@@ -74,8 +91,12 @@ struct TreeView {
     int64_t cv_stride;
     double* xw;                  // [batch][xw_stride] permuted right-hand side / solution
     int64_t xw_stride;
-    unsigned* bar;               // grid barrier counter (monotone; the host passes the value it has before a launch)
-    int* tickets;                // [n_levels][4] task tickets of the launch (zeroed by the host before it)
+    unsigned* bar;               // grid barrier counter of THIS launch (slot 4 of its first height's sync record, zeroed
+                                 // by the host together with the tickets: host and device cannot drift apart)
+    int* tickets;                // [n_levels][kSyncStride] per height: 4 task tickets + 1 barrier counter (zeroed by the host before a launch)
+    unsigned* abort_flag;        // device: set when a barrier gave up; every spinner polls it and leaves the kernel
+    TreeDebug* dbg;              // mapped pinned host memory: what the first block that gave up saw
+    long long spin_budget_ns;    // how long one block waits at one barrier before it gives up
     const int* phase_cls;        // [n_levels][5] first task of class 256 / 128 / 64 / 32, end of the phase
     int B;
     int slice[4], cap[4], maxh[4];   // per class: doubles of shared memory per group, of which panel, of which rows
@@ -620,18 +641,53 @@ __device__ __forceinline__ void tree_backward_task(const TreeView& T, const SnMe
 }
 
 // ---- grid barrier (cooperative launch: every block is resident) -------------------------------------------
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
+// A counter in global memory that the host zeroes before every launch; barrier k of a launch waits for k * gridDim.x
+// arrivals.  The spin is BOUNDED: a block that waits longer than T.spin_budget_ns raises T.abort_flag and records what it
+// saw in T.dbg (host-visible); every spinner polls the flag, and an aborted barrier makes the whole grid leave the kernel.
+// The host turns the flag into MADIPM_INTERNAL at its next synchronisation -- a desynchronised grid is an error message,
+// not a GPU pinned at 100 % forever.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ bool grid_barrier(const TreeView& T, unsigned& target, int kernel, int op, int ph) {
+    __shared__ int s_ok;
     __syncthreads();
     if (threadIdx.x == 0) {
         target += gridDim.x;
         __threadfence();
-        atomicAdd(bar, 1u);
-        unsigned v;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-        } while (static_cast<int>(v - target) < 0);
+        atomicAdd(T.bar, 1u);
+        unsigned v, polls = 0;
+        unsigned long long t0 = 0;
+        int ok = 1;
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(T.bar) : "memory");
+            if (static_cast<int>(v - target) >= 0) break;
+            if ((++polls & 1023u) == 0) {
+                unsigned ab;
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(ab) : "l"(T.abort_flag) : "memory");
+                if (ab) { ok = 0; break; }
+                const unsigned long long now = globaltimer_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > static_cast<unsigned long long>(T.spin_budget_ns)) {
+                    if (atomicExch(T.abort_flag, 1u) == 0u) {
+                        TreeDebug* g = T.dbg;
+                        g->kernel = kernel; g->op = op; g->phase = ph; g->block = blockIdx.x; g->grid = gridDim.x;
+                        g->seen = v; g->target = target; g->waited_ns = now - t0;
+                        __threadfence_system();
+                        g->aborted = g->aborted + 1u;
+                        __threadfence_system();
+                    }
+                    ok = 0;
+                    break;
+                }
+            }
+        }
+        s_ok = ok;
     }
     __syncthreads();
+    return s_ok != 0;
 }
 
 template <int OP, int G>
@@ -653,7 +709,7 @@ __device__ __forceinline__ void run_class(const TreeView& T, double* smem, int p
     const int t = threadIdx.x % G;
     for (;;) {
         gsync<G>();                                       // the previous ticket has been read by everyone
-        if (t == 0) *slot = atomicAdd(T.tickets + ph * 4 + CLS, 1);
+        if (t == 0) *slot = atomicAdd(T.tickets + ph * kSyncStride + CLS, 1);
         gsync<G>();
         const int64_t q = *slot;
         if (q >= total) break;
@@ -665,16 +721,16 @@ __device__ __forceinline__ void run_class(const TreeView& T, double* smem, int p
 // OP: 0 factor, 1 forward, 2 backward.  Heights ph_begin, ph_begin + step, ... (ph_end excluded).
 template <int OP>
 __global__ void __launch_bounds__(kTreeThreads, 4)
-k_tree(TreeView T, int ph_begin, int ph_end, int step, unsigned bar_base) {
+k_tree(TreeView T, int ph_begin, int ph_end, int step) {
     extern __shared__ double2 tree_smem2[];
     double* smem = reinterpret_cast<double*>(tree_smem2);
-    unsigned target = bar_base;
+    unsigned target = 0;
     for (int ph = ph_begin; ph != ph_end; ph += step) {
         run_class<OP, 256, 0>(T, smem, ph);
         run_class<OP, 128, 1>(T, smem, ph);
         run_class<OP, 64, 2>(T, smem, ph);
         run_class<OP, 32, 3>(T, smem, ph);
-        if (ph + step != ph_end) grid_barrier(T.bar, target);
+        if (ph + step != ph_end && !grid_barrier(T, target, 0, OP, ph)) return;
     }
 }
 
@@ -682,10 +738,10 @@ k_tree(TreeView T, int ph_begin, int ph_end, int step, unsigned bar_base) {
 constexpr int kTopThreads = 1024;
 template <int OP>
 __global__ void __launch_bounds__(kTopThreads, 1)
-k_tree_top(TreeView T, int ph_begin, int ph_end, int step, unsigned bar_base) {
+k_tree_top(TreeView T, int ph_begin, int ph_end, int step) {
     extern __shared__ double2 tree_smem2[];
     double* smem = reinterpret_cast<double*>(tree_smem2);
-    unsigned target = bar_base;
+    unsigned target = 0;
     for (int ph = ph_begin; ph != ph_end; ph += step) {
         const int first = __ldg(T.phase_cls + ph * 5);
         const int n = __ldg(T.phase_cls + ph * 5 + 4) - first;
@@ -695,7 +751,7 @@ k_tree_top(TreeView T, int ph_begin, int ph_end, int step, unsigned bar_base) {
             tree_task<OP, kTopThreads>(T, ldg_rec(T.meta + first + static_cast<int>(q - static_cast<int64_t>(inst) * n)), inst, smem,
                                        T.cap[0], T.maxh[0]);
         }
-        if (ph + step != ph_end) grid_barrier(T.bar, target);
+        if (ph + step != ph_end && !grid_barrier(T, target, 1, OP, ph)) return;
     }
 }
 

@@ -1,0 +1,75 @@
+"""The persistent tree kernels synchronise their grid by hand; these tests make sure that path can neither drift nor hang
+silently (the driver's benchmark sat at 100 % GPU for 30 minutes without output).
+
+  * a deliberately broken barrier counter surfaces as MADIPM_INTERNAL with the barrier's state in last_error, within the
+    device-side spin budget, and the handle keeps working afterwards;
+  * repeated full-size C3 solves (the headline workload) on one handle converge identically every time.
+"""
+import os
+import time
+
+import numpy as np
+import pytest
+
+from madqp_jl_b200 import _lib
+from madqp_jl_b200 import problems as P
+from madqp_jl_b200.mpc import FixedRegularization, MPCSolver
+
+pytestmark = pytest.mark.gpu
+
+
+def _factor_ready(qp):
+    s = MPCSolver(qp, regularization=FixedRegularization(1e-8, -1e-8))
+    s.initialize()
+    s._update_regularization()
+    s.h.set_aug_diagonal_reg(s.del_w, s.del_c)
+    s.h.build_kkt()
+    return s
+
+
+@pytest.mark.parametrize("where", ["factor", "solve"])
+def test_broken_grid_barrier_is_an_error_not_a_hang(where, monkeypatch):
+    monkeypatch.setenv("MADIPM_BARRIER_TIMEOUT_MS", "300")
+    s = _factor_ready(P.banded_qp(seed=1, n=40000, m=20000))     # several heights -> the launches have barriers
+    h = s.h
+    assert h.info()["n_levels"] > 3
+    assert h.factorize() == 0
+    good = h.inertia()
+    assert h.debug_barrier_state()["aborted"] == 0
+    t0 = time.perf_counter()
+    h.debug_inject_barrier_fault()
+    if where == "factor":
+        with pytest.raises(_lib.MadIPMError) as ei:
+            h.factorize()
+    else:
+        h.set_predictive_rhs()
+        with pytest.raises(_lib.MadIPMError) as ei:
+            h.kkt_solve("P")
+            h.synchronize()
+    dt = time.perf_counter() - t0
+    assert ei.value.code == _lib.INTERNAL
+    assert "grid barrier timed out" in str(ei.value)
+    st = h.debug_barrier_state()
+    assert st["aborted"] == 1 and st["seen"] >= 0x80000000 and st["grid"] > 0
+    assert dt < 30.0, dt                                          # a handful of barriers x 0.3 s, not for ever
+    # the handle is usable again: same factorisation as before the fault
+    h.build_kkt()
+    assert h.factorize() == 0
+    assert h.inertia() == good
+    assert h.debug_barrier_state()["aborted"] == 1
+    s.close()
+
+
+def test_three_full_size_c3_solves_back_to_back():
+    """The driver's benchmark repeats solve() on one handle; every repetition must terminate and agree."""
+    s = MPCSolver(P.banded_qp(), regularization=FixedRegularization(1e-8, -1e-8), max_ncorr=0, tol=1e-8)
+    s.keep_snapshot = True
+    out = []
+    for k in range(3):
+        st = s.solve(resident=(k > 0))
+        assert st.status[0] == "SOLVE_SUCCEEDED"
+        out.append((int(st.iter[0]), float(st.objective[0])))
+    assert s.h.debug_barrier_state()["aborted"] == 0
+    assert len({o[0] for o in out}) == 1, out
+    assert max(abs(o[1] - out[0][1]) for o in out) <= 1e-10 * max(1.0, abs(out[0][1])), out
+    s.close()
