@@ -451,6 +451,9 @@ class Handle:
     def launch_count(self):
         return int(self.lib.madipm_launch_count(self._h))
 
+    def last_error(self):
+        return self.lib.madipm_last_error(self._h).decode()
+
     def debug_barrier_state(self):
         """What the first grid barrier that gave up saw (host-visible memory: readable while a kernel is stuck)."""
         out = np.zeros(8, dtype=np.int64)

@@ -37,12 +37,21 @@ class SolveException(Exception):
     """MadNLP.SolveException (/root/reference/src/linear_solver.jl:41-43)."""
 
 
+# -O3 with AVX2 code generation (x86-64-v3 rather than -march=native: the library is built in one container and runs
+# on another box); no FMA contraction and no -ffast-math, so the arithmetic is the reference's operation by operation.
+C_FLAGS = "gcc -O3 -march=x86-64-v3 -ffp-contract=off"
+
+
 def build(force=False):
     """Compile the C restatement into oracle/liboracle.so (gcc, no FMA contraction)."""
     so = os.path.join(_HERE, "liboracle.so")
     src = os.path.join(_HERE, "madipm_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, src, "-lm"])
+    stamp = so + ".flags"
+    old = open(stamp).read() if os.path.exists(stamp) else ""
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src) or old != C_FLAGS:
+        subprocess.check_call(C_FLAGS.split() + ["-fPIC", "-shared", "-o", so, src, "-lm"])
+        with open(stamp, "w") as f:
+            f.write(C_FLAGS)
     return so
 
 
