@@ -274,6 +274,24 @@ int32_t madipm_vec_axpy(madipm_handle* h, int32_t dst, int64_t off_dst, int32_t 
                         int64_t len, double alpha);
 int32_t madipm_vec_norm_inf(madipm_handle* h, int32_t vec, double* out);
 
+/* ---- sub-range and index-view operations --------------------------------------------------------------------
+ * What the Julia vector type of julia/MadIPMB200.jl (tag + handle + range) maps its methods to, so that the lines of
+ * /root/reference/src/solver.jl that work on solver vectors directly (axpy! at :28 and :332-333, `.=` at :16-18 and :33,
+ * the `.+=` on the zl_r / zu_r index views at :334-335, copyto! of linear_solver.jl:25-29 and solver.jl:236-242,
+ * norm(., Inf) at solver.jl:174-175 and structure.jl:191, adjust_boundary! at :342) run unchanged.  Ranges are 0-based
+ * [off, off + len) inside one instance and apply to every instance of a batch. */
+int32_t madipm_vec_get_range(madipm_handle* h, int32_t vec, int64_t off, int64_t len, double* host);       /* host: [batch][len] */
+int32_t madipm_vec_set_range(madipm_handle* h, int32_t vec, int64_t off, int64_t len, const double* host);
+int32_t madipm_vec_fill_range(madipm_handle* h, int32_t vec, int64_t off, int64_t len, double value);
+int32_t madipm_vec_copy_range(madipm_handle* h, int32_t dst, int64_t off_dst, int32_t src, int64_t off_src, int64_t len);
+int32_t madipm_vec_norm_inf_range(madipm_handle* h, int32_t vec, int64_t off, int64_t len, double* out);   /* out: [batch] */
+/* dst[ind[k]] += alpha * src[off_src + k], k < nlb (which = 0: ind = ind_lb) or k < nub (which = 1: ind = ind_ub);
+ * dst is one of the n_tot-long vectors.  solver.jl:334-335: zl_r .+= alpha_d .* dual_lb(d) */
+int32_t madipm_vec_axpy_at(madipm_handle* h, int32_t dst, int32_t which, int32_t src, int64_t off_src, double alpha);
+/* MadNLP.adjust_boundary!(x_lr, xl_r, x_ur, xu_r, mu), solver.jl:342 ([RECALLED], same arithmetic as inside
+ * madipm_update_iterate); mu: one value per instance */
+int32_t madipm_adjust_boundary(madipm_handle* h, const double* mu);
+
 /* ---- device-resident inputs ------------------------------------------------------------------
  * A solve overwrites x, y and (through adjust_boundary!) xl, xu.  snapshot keeps device copies of the
  * four input vectors as uploaded; restore puts them back without host traffic, so a solve can be

@@ -123,6 +123,13 @@ _SIGNATURES = {
     "madipm_vec_copy": ([C.c_int32, C.c_int32], C.c_int32),
     "madipm_vec_axpy": ([C.c_int32, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_double], C.c_int32),
     "madipm_vec_norm_inf": ([C.c_int32, _PD], C.c_int32),
+    "madipm_vec_get_range": ([C.c_int32, C.c_int64, C.c_int64, _PD], C.c_int32),
+    "madipm_vec_set_range": ([C.c_int32, C.c_int64, C.c_int64, _PD], C.c_int32),
+    "madipm_vec_fill_range": ([C.c_int32, C.c_int64, C.c_int64, C.c_double], C.c_int32),
+    "madipm_vec_copy_range": ([C.c_int32, C.c_int64, C.c_int32, C.c_int64, C.c_int64], C.c_int32),
+    "madipm_vec_norm_inf_range": ([C.c_int32, C.c_int64, C.c_int64, _PD], C.c_int32),
+    "madipm_vec_axpy_at": ([C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_double], C.c_int32),
+    "madipm_adjust_boundary": ([_PD], C.c_int32),
     "madipm_snapshot_inputs": ([], C.c_int32),
     "madipm_restore_inputs": ([], C.c_int32),
     "madipm_launch_count": ([], C.c_int64),
@@ -297,6 +304,34 @@ class Handle:
 
     def vec_axpy(self, dst, off_dst, src, off_src, length, alpha):
         self._check(self.lib.madipm_vec_axpy(self._h, VEC[dst], off_dst, VEC[src], off_src, length, alpha))
+
+    # -- sub-range / index-view operations (what julia/MadIPMB200.jl's vector type calls)
+    def vec_get_range(self, vec, off, length):
+        out = np.zeros(self.batch * length)
+        self._check(self.lib.madipm_vec_get_range(self._h, VEC[vec], off, length, _pd(out)))
+        return out.reshape(self.batch, -1) if self.batch > 1 else out
+
+    def vec_set_range(self, vec, off, host):
+        a = _f64(host)
+        self._check(self.lib.madipm_vec_set_range(self._h, VEC[vec], off, a.size // self.batch, _pd(a)))
+
+    def vec_fill_range(self, vec, off, length, value):
+        self._check(self.lib.madipm_vec_fill_range(self._h, VEC[vec], off, length, value))
+
+    def vec_copy_range(self, dst, off_dst, src, off_src, length):
+        self._check(self.lib.madipm_vec_copy_range(self._h, VEC[dst], off_dst, VEC[src], off_src, length))
+
+    def vec_norm_inf_range(self, vec, off, length):
+        out = np.zeros(self.batch)
+        self._check(self.lib.madipm_vec_norm_inf_range(self._h, VEC[vec], off, length, _pd(out)))
+        return out
+
+    def vec_axpy_at(self, dst, which, src, off_src, alpha):
+        self._check(self.lib.madipm_vec_axpy_at(self._h, VEC[dst], which, VEC[src], off_src, alpha))
+
+    def adjust_boundary(self, mu):
+        m = _f64(np.broadcast_to(mu, (self.batch,)))
+        self._check(self.lib.madipm_adjust_boundary(self._h, _pd(m)))
 
     def vec_norm_inf(self, vec):
         out = np.zeros(self.batch)

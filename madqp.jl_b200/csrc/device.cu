@@ -1125,6 +1125,93 @@ int32_t madipm_vec_norm_inf(madipm_handle* h, int32_t vec, double* out) {
     return fetch(h, d->d_out, out, d->B);
 }
 
+// ---- sub-range and index-view operations (the vector type of julia/MadIPMB200.jl) ---------------------------
+static bool range_ok(const DeviceState* d, int32_t vec, int64_t off, int64_t len) {
+    return vec >= 0 && vec < MADIPM_VEC_COUNT && off >= 0 && len >= 0 && off + len <= d->veclen[vec];
+}
+
+int32_t madipm_vec_get_range(madipm_handle* h, int32_t vec, int64_t off, int64_t len, double* host) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (!host || !range_ok(d, vec, off, len)) return MADIPM_BAD_ARGUMENT;
+    if (vec == MADIPM_VEC_KKT_NZVAL && (rc = refresh_nzval_diag(h))) return rc;
+    if (len > 0)
+        CUDA_OK(h, cudaMemcpy2DAsync(host, sizeof(double) * len, d->vec[vec] + off, sizeof(double) * d->veclen[vec], sizeof(double) * len,
+                                     d->B, cudaMemcpyDeviceToHost, d->stream));
+    return sync_stream(h);
+}
+
+int32_t madipm_vec_set_range(madipm_handle* h, int32_t vec, int64_t off, int64_t len, const double* host) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (!host || !range_ok(d, vec, off, len)) return MADIPM_BAD_ARGUMENT;
+    if (vec == MADIPM_VEC_KKT_NZVAL) { d->image_valid = false; d->nzval_diag_stale = false; }
+    if (len > 0)
+        CUDA_OK(h, cudaMemcpy2DAsync(d->vec[vec] + off, sizeof(double) * d->veclen[vec], host, sizeof(double) * len, sizeof(double) * len,
+                                     d->B, cudaMemcpyHostToDevice, d->stream));
+    return sync_stream(h);                                  // the host array may be reused as soon as the call returns
+}
+
+int32_t madipm_vec_fill_range(madipm_handle* h, int32_t vec, int64_t off, int64_t len, double value) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (!range_ok(d, vec, off, len)) return MADIPM_BAD_ARGUMENT;
+    if (vec == MADIPM_VEC_KKT_NZVAL) { d->image_valid = false; d->nzval_diag_stale = false; }
+    if (len > 0) LAUNCH(h, k_fill, dim3(vec_blocks(len), d->B), kVecThreads, 0, len, d->vec[vec] + off, d->veclen[vec], value);
+    return MADIPM_OK;
+}
+
+int32_t madipm_vec_copy_range(madipm_handle* h, int32_t dst, int64_t off_dst, int32_t src, int64_t off_src, int64_t len) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (!range_ok(d, dst, off_dst, len) || !range_ok(d, src, off_src, len)) return MADIPM_BAD_ARGUMENT;
+    if (src == MADIPM_VEC_KKT_NZVAL && (rc = refresh_nzval_diag(h))) return rc;
+    if (dst == MADIPM_VEC_KKT_NZVAL) { d->image_valid = false; d->nzval_diag_stale = false; }
+    if (len > 0 && !(dst == src && off_dst == off_src))
+        LAUNCH(h, k_copy, dim3(vec_blocks(len), d->B), kVecThreads, 0, len, d->vec[dst] + off_dst, d->veclen[dst], d->vec[src] + off_src,
+               d->veclen[src]);
+    return MADIPM_OK;
+}
+
+int32_t madipm_vec_norm_inf_range(madipm_handle* h, int32_t vec, int64_t off, int64_t len, double* out) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (!out || !range_ok(d, vec, off, len)) return MADIPM_BAD_ARGUMENT;
+    Timer t(h, MADIPM_T_VECTOR);
+    LAUNCH(h, k_norm_inf, dim3(vec_blocks(len), d->B), kVecThreads, 0, len, d->vec[vec] + off, d->veclen[vec], d->red_scratch, d->red_counter, d->d_out);
+    return fetch(h, d->d_out, out, d->B);
+}
+
+int32_t madipm_vec_axpy_at(madipm_handle* h, int32_t dst, int32_t which, int32_t src, int64_t off_src, double alpha) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (which < 0 || which > 1 || dst < 0 || dst >= MADIPM_VEC_COUNT || d->veclen[dst] != d->n) return MADIPM_BAD_ARGUMENT;
+    const int cnt = which == 0 ? d->nlb : d->nub;
+    if (!range_ok(d, src, off_src, cnt)) return MADIPM_BAD_ARGUMENT;
+    Timer t(h, MADIPM_T_VECTOR);
+    if (cnt > 0)
+        LAUNCH(h, k_axpy_at, dim3(vec_blocks(cnt), d->B), kVecThreads, 0, cnt, which == 0 ? d->ind_lb : d->ind_ub, d->vec[dst], (int64_t)d->n,
+               d->vec[src] + off_src, d->veclen[src], alpha);
+    return MADIPM_OK;
+}
+
+int32_t madipm_adjust_boundary(madipm_handle* h, const double* mu) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (!mu) return MADIPM_BAD_ARGUMENT;
+    Timer t(h, MADIPM_T_VECTOR);
+    CUDA_OK(h, cudaMemcpyAsync(d->d_mu, mu, sizeof(double) * d->B, cudaMemcpyHostToDevice, d->stream));
+    LAUNCH(h, k_adjust_boundary, dim3(vec_blocks(d->n), d->B), kVecThreads, 0, make_view(*d), d->d_mu);
+    return MADIPM_OK;
+}
+
 // ---- KKT system ---------------------------------------------------------------------------------
 int32_t madipm_kkt_initialize(madipm_handle* h) {
     int32_t rc = check(h);

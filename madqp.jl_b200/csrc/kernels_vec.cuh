@@ -651,6 +651,34 @@ __global__ void k_update_iterate(VecView V, const double* __restrict__ d, const 
     }
 }
 
+// dst[ind[k]] += alpha * src[k]: the `.+=` on an index view (/root/reference/src/solver.jl:334-335); ind has no repeats
+__global__ void k_axpy_at(int cnt, const int* __restrict__ ind, double* __restrict__ dst, int64_t dstride,
+                          const double* __restrict__ src, int64_t sstride, double alpha) {
+    dst += blockIdx.y * dstride;
+    src += blockIdx.y * sstride;
+    MADIPM_GRID_STRIDE(k, cnt) dst[ind[k]] += alpha * src[k];
+}
+
+// MadNLP.adjust_boundary! alone (/root/reference/src/solver.jl:342): the same arithmetic as the tail of k_update_iterate
+__global__ void k_adjust_boundary(VecView V, const double* __restrict__ mu_dev) {
+    const int inst = blockIdx.y;
+    V = shift(V, inst);
+    const double eps = 2.220446049250313e-16;
+    const double c1 = eps * mu_dev[inst];
+    const double c2 = 1.8189894035458565e-12;   // eps^(3/4)
+    MADIPM_GRID_STRIDE(i, V.n) {
+        const double x = V.x[i];
+        if (V.lb_of[i] >= 0) {
+            const double xl = V.xl[i];
+            if (x - xl < c1) V.xl[i] = xl - c2 * fmax(1.0, fabs(x));
+        }
+        if (V.ub_of[i] >= 0) {
+            const double xu = V.xu[i];
+            if (xu - x < c1) V.xu[i] = xu + c2 * fmax(1.0, fabs(x));
+        }
+    }
+}
+
 // ---- problem loading on the device: MadNLP.initialize!(cb, x, xl, xu, y, rhs, ind_ineq; ...) and set_scaling!
 // (called at /root/reference/src/solver.jl:131-159; un-vendored MadNLP code, restated in mpc.py prepare_host, which
 // is the host reference these kernels are tested against).  Raw inputs are uploaded into the vectors they end up in.
