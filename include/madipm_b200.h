@@ -334,6 +334,14 @@ int32_t madipm_phase_residuals_obj(madipm_handle* h, double c0, double* out4, do
  * affine complementarity + get_correction!.  norms: 3 per instance as madipm_solve_system, out: 4 per instance as
  * madipm_phase_affine.  MADIPM_NONFINITE as madipm_solve_system. */
 int32_t madipm_phase_predictor(madipm_handle* h, double* norms, double* out4);
+/* The same preceded by the first try of factorize_regularized_system! (linear_solver.jl:6-17: set_aug_diagonal_reg! +
+ * build_kkt! + factorize!), one synchronisation for all of it.  When every supernode is factorised by the tree kernels the
+ * predictor's forward sweep is done INSIDE the factor launch (its right-hand side depends on the iterate only,
+ * kernels.jl:21-41; each supernode's forward step runs while its freshly factorised panel is still in shared memory): an
+ * iteration then costs three triangular sweeps instead of four.  Same arithmetic as the separate calls, identical results.
+ * Breakdown flags as after madipm_factorize(h, NULL) (madipm_is_factorized); on a breakdown the caller re-enters the
+ * reference's retry loop with the separate entry points. */
+int32_t madipm_phase_factor_predictor(madipm_handle* h, double del_w, double del_c, double* norms, double* out4);
 /* mpc_direction! without Gondzio corrections, solver.jl:307-311, + the ratio tests of update_step! (kernels.jl:290-305):
  * set_correction_rhs!(mu) + solve_system! + ratio tests at tau.  ratio: 8 per instance as madipm_ratio_test. */
 int32_t madipm_phase_corrector(madipm_handle* h, const double* mu, const double* tau, double* norms, double* ratio8);

@@ -139,6 +139,7 @@ _SIGNATURES = {
     "madipm_debug_inject_barrier_fault": ([], C.c_int32),
     "madipm_phase_residuals_obj": ([C.c_double, _PD, _PD], C.c_int32),
     "madipm_phase_predictor": ([_PD, _PD], C.c_int32),
+    "madipm_phase_factor_predictor": ([C.c_double, C.c_double, _PD, _PD], C.c_int32),
     "madipm_phase_corrector": ([_PD, _PD, _PD, _PD], C.c_int32),
     "madipm_default_scale_options": (None, [C.POINTER(ScaleOptions)], None),
     "madipm_scale_qp": (None, [C.POINTER(ScaleOptions), C.c_int32, C.c_int32, C.c_int64, _P32, _P32, _PD, C.c_int64, _P32, _P32, _PD,
@@ -414,6 +415,13 @@ class Handle:
     def phase_predictor(self):
         norms, out = np.zeros(3 * self.batch), np.zeros(4 * self.batch)
         rc = self._check(self.lib.madipm_phase_predictor(self._h, _pd(norms), _pd(out)), allow=(NONFINITE,))
+        return rc, norms.reshape(self.batch, 3), out.reshape(self.batch, 4)
+
+    def phase_factor_predictor(self, del_w, del_c):
+        """set_aug_diagonal_reg! + build_kkt! + factorize! (asynchronous flags) + phase_predictor, the predictor's forward
+        sweep inside the factor launch."""
+        norms, out = np.zeros(3 * self.batch), np.zeros(4 * self.batch)
+        rc = self._check(self.lib.madipm_phase_factor_predictor(self._h, del_w, del_c, _pd(norms), _pd(out)), allow=(NONFINITE,))
         return rc, norms.reshape(self.batch, 3), out.reshape(self.batch, 4)
 
     def phase_corrector(self, mu, tau):

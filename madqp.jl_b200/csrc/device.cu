@@ -36,11 +36,11 @@ struct DeviceState {
     // small supernodes: persistent height-scheduled kernels (kernels_tree.cuh)
     // heights [ph0, split) in one cooperative launch of k_tree, heights [split, ph1) (at most one task per SM) in one
     // launch of k_tree_top; a height with big supernodes ends a segment
-    struct TreeSeg { int ph0, split, ph1, grid[3], grid_top; };
+    struct TreeSeg { int ph0, split, ph1, grid[4], grid_top; };   // grid[OP], OP 3 = factor + forward (kernels_tree.cuh)
     std::vector<TreeSeg> segs;
     int tree_maxw = 0;
     size_t smem_tree = 0;
-    int tree_occ[3] = {0, 0, 0};
+    int tree_occ[4] = {0, 0, 0, 0};
     int* tickets[3] = {nullptr, nullptr, nullptr};
     int* phase_cls = nullptr;
     int num_sms = 0;
@@ -434,23 +434,24 @@ template <int OP>
 int32_t launch_tree(madipm_handle* h, const DeviceState::TreeSeg& sg) {
     DeviceState* d = h->dev;
     TreeView T = make_tree_view(*d);
-    T.tickets = d->tickets[OP];
-    if (OP == 0 && d->image_valid) { T.image = d->P0; T.dperm = d->dperm; }
+    int* const tickets = d->tickets[OP == 3 ? 0 : OP];     // (the fused factor + forward launch never overlaps a plain factor launch)
+    T.tickets = tickets;
+    if ((OP == 0 || OP == 3) && d->image_valid) { T.image = d->P0; T.dperm = d->dperm; }
     const bool reverse = OP == 2;
     // one memset clears everything the two launches of this segment synchronise on: the tickets of its heights and the
     // barrier counters (slot kSyncBar of the first height each launch walks)
     if (sg.ph1 > sg.ph0)
-        CUDA_OK(h, cudaMemsetAsync(d->tickets[OP] + kSyncStride * sg.ph0, 0, sizeof(int) * kSyncStride * (sg.ph1 - sg.ph0), d->stream));
+        CUDA_OK(h, cudaMemsetAsync(tickets + kSyncStride * sg.ph0, 0, sizeof(int) * kSyncStride * (sg.ph1 - sg.ph0), d->stream));
     if (d->inject_barrier_fault) {     // counters start at 0x80000000: no barrier of this segment can complete
         d->inject_barrier_fault = false;
         for (int ph : {sg.ph0, sg.split})
             if (ph < sg.ph1)
-                CUDA_OK(h, cudaMemsetAsync(reinterpret_cast<char*>(d->tickets[OP] + kSyncStride * ph + kSyncBar) + 3, 0x80, 1, d->stream));
+                CUDA_OK(h, cudaMemsetAsync(reinterpret_cast<char*>(tickets + kSyncStride * ph + kSyncBar) + 3, 0x80, 1, d->stream));
     }
     auto bottom = [&]() -> int32_t {
         if (sg.split <= sg.ph0 || sg.grid[OP] <= 0) return MADIPM_OK;
         int b = reverse ? sg.split - 1 : sg.ph0, e = reverse ? sg.ph0 - 1 : sg.split, step = reverse ? -1 : 1;
-        T.bar = reinterpret_cast<unsigned*>(d->tickets[OP] + kSyncStride * sg.ph0 + kSyncBar);
+        T.bar = reinterpret_cast<unsigned*>(tickets + kSyncStride * sg.ph0 + kSyncBar);
         void* args[] = {&T, &b, &e, &step};
         CUDA_OK(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_tree<OP>), dim3(sg.grid[OP]), dim3(kTreeThreads), args,
                                                d->smem_tree, d->stream));
@@ -460,7 +461,7 @@ int32_t launch_tree(madipm_handle* h, const DeviceState::TreeSeg& sg) {
     auto top = [&]() -> int32_t {
         if (sg.ph1 <= sg.split || sg.grid_top <= 0) return MADIPM_OK;
         int b = reverse ? sg.ph1 - 1 : sg.split, e = reverse ? sg.split - 1 : sg.ph1, step = reverse ? -1 : 1;
-        T.bar = reinterpret_cast<unsigned*>(d->tickets[OP] + kSyncStride * sg.split + kSyncBar);
+        T.bar = reinterpret_cast<unsigned*>(tickets + kSyncStride * sg.split + kSyncBar);
         void* args[] = {&T, &b, &e, &step};
         CUDA_OK(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_tree_top<OP>), dim3(sg.grid_top), dim3(kTopThreads), args,
                                                d->smem_tree, d->stream));
@@ -473,12 +474,14 @@ int32_t launch_tree(madipm_handle* h, const DeviceState::TreeSeg& sg) {
     return top();
 }
 
-int32_t tri_solve(madipm_handle* h) {
+// do_forward = false: the forward sweep of this right-hand side was done by the fused factor + forward launch
+int32_t tri_solve(madipm_handle* h, bool do_forward = true) {
     DeviceState* d = h->dev;
     FactorView F = make_factor_view(*d, 0);
     const int64_t N = d->N;
     int32_t rc;
     for (const DeviceState::TreeSeg& sg : d->segs) {
+        if (!do_forward) break;
         if ((rc = launch_tree<1>(h, sg))) return rc;
         const int l = sg.ph1 - 1;
         const int nbig = d->big_ptr[l + 1] - d->big_ptr[l];
@@ -733,20 +736,24 @@ int32_t device_create(madipm_handle* h) {
         CUDA_OK(h, cudaFuncSetAttribute(k_tree<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_tree));
         CUDA_OK(h, cudaFuncSetAttribute(k_tree<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_tree));
         CUDA_OK(h, cudaFuncSetAttribute(k_tree<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_tree));
+        CUDA_OK(h, cudaFuncSetAttribute(k_tree<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_tree));
+        CUDA_OK(h, cudaFuncSetAttribute(k_tree_top<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_tree));
         CUDA_OK(h, cudaFuncSetAttribute(k_tree_top<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_tree));
         CUDA_OK(h, cudaFuncSetAttribute(k_tree_top<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_tree));
         CUDA_OK(h, cudaFuncSetAttribute(k_tree_top<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_tree));
         CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->tree_occ[0], k_tree<0>, kTreeThreads, d->smem_tree));
         CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->tree_occ[1], k_tree<1>, kTreeThreads, d->smem_tree));
         CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->tree_occ[2], k_tree<2>, kTreeThreads, d->smem_tree));
+        CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->tree_occ[3], k_tree<3>, kTreeThreads, d->smem_tree));
         int top_occ = 1;
         {
             int o = 0;
             CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_tree_top<0>, kTopThreads, d->smem_tree)); top_occ = std::min(top_occ, o);
             CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_tree_top<1>, kTopThreads, d->smem_tree)); top_occ = std::min(top_occ, o);
             CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_tree_top<2>, kTopThreads, d->smem_tree)); top_occ = std::min(top_occ, o);
+            CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_tree_top<3>, kTopThreads, d->smem_tree)); top_occ = std::min(top_occ, o);
         }
-        for (int op = 0; op < 3; ++op)
+        for (int op = 0; op < 4; ++op)
             if (d->tree_occ[op] < 1) { h->error = "tree kernel does not fit on an SM"; return MADIPM_INTERNAL; }
         // launch plan: consecutive heights share one cooperative launch; a height with big supernodes ends it
         // (MADIPM_TREE_SPLIT=1 gives every height its own launch: a per-height launch list for the profiler;
@@ -772,7 +779,7 @@ int32_t device_create(madipm_handle* h) {
                     need = std::max(need, blocks);
                 }
                 for (int q = sg.split; q < sg.ph1; ++q) need_top = std::max(need_top, ntasks(q));
-                for (int op = 0; op < 3; ++op)
+                for (int op = 0; op < 4; ++op)
                     sg.grid[op] = static_cast<int>(std::min<int64_t>(need, static_cast<int64_t>(d->tree_occ[op]) * d->num_sms));
                 sg.grid_top = static_cast<int>(std::min<int64_t>(need_top, d->num_sms));
                 d->segs.push_back(sg);
@@ -1268,53 +1275,67 @@ int32_t madipm_build_kkt(madipm_handle* h) {
     return MADIPM_OK;
 }
 
+// Everything madipm_factorize puts on the stream.  fuse_forward: the tree launches are the factor + forward variant
+// (kernels_tree.cuh OP 3): the right-hand side waiting in xw gets its forward sweep on the way.  Only when every supernode
+// is small (no multi-block fronts); the caller checks.
+static int32_t factorize_enqueue(madipm_handle* h, bool fuse_forward, bool* timed_tree) {
+    int32_t rc;
+    DeviceState* d = h->dev;
+    const int B = d->B;
+    const bool light = d->profiling == 2;
+    bool first_tree = true;
+    if (light) cudaEventRecord(d->ev0, d->stream);
+    CUDA_OK(h, cudaMemsetAsync(d->fail, 0, sizeof(int) * B, d->stream));
+    if (!d->image_valid) {                             // (with a valid panel image the tasks read P0 instead)
+        CUDA_OK(h, cudaMemsetAsync(d->Lx, 0, sizeof(double) * B * d->lx_stride, d->stream));
+        LAUNCH(h, k_assemble_panels, dim3(vec_blocks(d->kkt_nnz) * 4, B), kVecThreads, 0, d->kkt_nnz, d->asm_map,
+               d->vec[MADIPM_VEC_KKT_NZVAL], d->kkt_nnz, d->Lx, d->lx_stride);
+    }
+    for (const DeviceState::TreeSeg& sg : d->segs) {
+        if (light && first_tree) cudaEventRecord(d->ev2, d->stream);
+        if ((rc = fuse_forward ? launch_tree<3>(h, sg) : launch_tree<0>(h, sg))) return rc;
+        if (light && first_tree) { cudaEventRecord(d->ev3, d->stream); first_tree = false; }
+        const int l = sg.ph1 - 1;
+        const int nbig = d->big_ptr[l + 1] - d->big_ptr[l];
+        if (nbig > 0) {
+            const FactorView F = make_factor_view(*d, 0);
+            const int* list = d->big_sn + d->big_ptr[l];
+            const int exclusive = nbig == 1 ? 1 : 0;     // the only writer of its targets during these launches
+            if (d->big_use_panel) {
+                LAUNCH(h, k_big_panel, dim3(std::max(1, d->big_panelblocks[l]), nbig, B), kPanelThreads, d->smem_big_panel, F, list,
+                       d->big_zbuf, d->big_zstride);
+                LAUNCH(h, k_big_store_diag, dim3(nbig, B), 256, 0, F, list, d->big_zbuf, d->big_zstride);
+            } else {
+                LAUNCH(h, k_big_diag, dim3(nbig, B), 256, d->smem_big_diag, F, list, d->big_zbuf, d->big_zstride);
+                if (d->big_rowblocks[l] > 0)
+                    LAUNCH(h, k_big_trsm, dim3(d->big_rowblocks[l], nbig, B), 128, d->smem_big_trsm, F, list, d->big_zbuf, d->big_zstride);
+            }
+            if (d->big_rowblocks[l] > 0) {
+                const int b0 = d->big_ptr[l];
+                LAUNCH(h, k_big_update, dim3(d->big_tiles[l], nbig, B), 128, d->smem_big_update, F, list, d->upd_lim + b0,
+                       d->upd_nsrc + b0, d->upd_src + static_cast<size_t>(b0) * kBigGroup, exclusive);
+            }
+        }
+    }
+    if (light) cudaEventRecord(d->ev1, d->stream);
+    *timed_tree = !first_tree;
+    return MADIPM_OK;
+}
+
 int32_t madipm_factorize(madipm_handle* h, int32_t* n_failed) {
     int32_t rc = check(h, true);
     if (rc) return rc;
     DeviceState* d = h->dev;
     const int B = d->B;
     const bool light = d->profiling == 2;
-    bool first_tree = true;
+    bool timed_tree = false;
     {
         Timer t(h, MADIPM_T_FACTOR);
-        if (light) cudaEventRecord(d->ev0, d->stream);
-        CUDA_OK(h, cudaMemsetAsync(d->fail, 0, sizeof(int) * B, d->stream));
-        if (!d->image_valid) {                             // (with a valid panel image the tasks read P0 instead)
-            CUDA_OK(h, cudaMemsetAsync(d->Lx, 0, sizeof(double) * B * d->lx_stride, d->stream));
-            LAUNCH(h, k_assemble_panels, dim3(vec_blocks(d->kkt_nnz) * 4, B), kVecThreads, 0, d->kkt_nnz, d->asm_map,
-                   d->vec[MADIPM_VEC_KKT_NZVAL], d->kkt_nnz, d->Lx, d->lx_stride);
-        }
-        for (const DeviceState::TreeSeg& sg : d->segs) {
-            if (light && first_tree) cudaEventRecord(d->ev2, d->stream);
-            if ((rc = launch_tree<0>(h, sg))) return rc;
-            if (light && first_tree) { cudaEventRecord(d->ev3, d->stream); first_tree = false; }
-            const int l = sg.ph1 - 1;
-            const int nbig = d->big_ptr[l + 1] - d->big_ptr[l];
-            if (nbig > 0) {
-                const FactorView F = make_factor_view(*d, 0);
-                const int* list = d->big_sn + d->big_ptr[l];
-                const int exclusive = nbig == 1 ? 1 : 0;     // the only writer of its targets during these launches
-                if (d->big_use_panel) {
-                    LAUNCH(h, k_big_panel, dim3(std::max(1, d->big_panelblocks[l]), nbig, B), kPanelThreads, d->smem_big_panel, F, list,
-                           d->big_zbuf, d->big_zstride);
-                    LAUNCH(h, k_big_store_diag, dim3(nbig, B), 256, 0, F, list, d->big_zbuf, d->big_zstride);
-                } else {
-                    LAUNCH(h, k_big_diag, dim3(nbig, B), 256, d->smem_big_diag, F, list, d->big_zbuf, d->big_zstride);
-                    if (d->big_rowblocks[l] > 0)
-                        LAUNCH(h, k_big_trsm, dim3(d->big_rowblocks[l], nbig, B), 128, d->smem_big_trsm, F, list, d->big_zbuf, d->big_zstride);
-                }
-                if (d->big_rowblocks[l] > 0) {
-                    const int b0 = d->big_ptr[l];
-                    LAUNCH(h, k_big_update, dim3(d->big_tiles[l], nbig, B), 128, d->smem_big_update, F, list, d->upd_lim + b0,
-                           d->upd_nsrc + b0, d->upd_src + static_cast<size_t>(b0) * kBigGroup, exclusive);
-                }
-            }
-        }
-        if (light) cudaEventRecord(d->ev1, d->stream);
+        if ((rc = factorize_enqueue(h, false, &timed_tree))) return rc;
         if (!n_failed) {                                   // asynchronous: flags and event times ride on the next synchronisation
             d->fail_pending = true;
             d->prof_pending = light;
-            d->prof_tree_pending = light && !first_tree;
+            d->prof_tree_pending = light && timed_tree;
             return MADIPM_OK;
         }
         d->fail_pending = d->prof_pending = d->prof_tree_pending = false;
@@ -1324,7 +1345,7 @@ int32_t madipm_factorize(madipm_handle* h, int32_t* n_failed) {
             float ms = 0;
             cudaEventElapsedTime(&ms, d->ev0, d->ev1);
             d->t_ms[MADIPM_T_FACTOR] += ms; d->t_calls[MADIPM_T_FACTOR] += 1;
-            if (!first_tree) {
+            if (timed_tree) {
                 cudaEventElapsedTime(&ms, d->ev2, d->ev3);
                 d->t_ms[MADIPM_T_FACTOR_TREE] += ms; d->t_calls[MADIPM_T_FACTOR_TREE] += 1;
             }
@@ -1378,31 +1399,48 @@ int32_t madipm_linear_solve(madipm_handle* h, double* dev_rhs, int64_t stride) {
     return MADIPM_OK;
 }
 
-int32_t madipm_kkt_solve(madipm_handle* h, int32_t vec_w) {
-    int32_t rc = check(h, true);
-    if (rc) return rc;
+// K4 / K4' in stages: 1 = everything before the triangular sweeps (reduce_rhs!, elimination, permutation into xw),
+// 2 = backward sweep + everything after it, 3 = all of it.  Stage 1 needs nothing from the factorisation, which is what lets
+// the predictor's forward sweep ride inside the factor launch (madipm_phase_factor_predictor).
+static int32_t kkt_solve_stages(madipm_handle* h, int32_t vec_w, int stages) {
+    int32_t rc;
     DeviceState* d = h->dev;
     if (vec_w < MADIPM_VEC_D || vec_w > MADIPM_VEC_W2) return MADIPM_BAD_ARGUMENT;
     Timer t(h, MADIPM_T_SOLVE);
     VecView V = make_view(*d);
     double* w = d->vec[vec_w];
     const dim3 gN(vec_blocks(d->N), d->B), gn(vec_blocks(d->n), d->B), gm(vec_blocks(d->m), d->B);
+    const bool pre = stages & 1, post = stages & 2;
     if (d->scaled) {
-        LAUNCH(h, k_k25_presolve, gN, kVecThreads, 0, V, w, d->perm, d->N, d->xw, (int64_t)d->N);
-        if ((rc = tri_solve(h))) return rc;
-        LAUNCH(h, k_k25_postsolve, gN, kVecThreads, 0, V, w, d->iperm, d->N, d->xw, (int64_t)d->N);
+        if (pre) LAUNCH(h, k_k25_presolve, gN, kVecThreads, 0, V, w, d->perm, d->N, d->xw, (int64_t)d->N);
+        if (post) {
+            if ((rc = tri_solve(h, pre))) return rc;
+            LAUNCH(h, k_k25_postsolve, gN, kVecThreads, 0, V, w, d->iperm, d->N, d->xw, (int64_t)d->N);
+        }
     } else if (d->kind == 0) {
-        LAUNCH(h, k_k2_presolve, gN, kVecThreads, 0, V, w, d->perm, d->N, d->xw, (int64_t)d->N);
-        if ((rc = tri_solve(h))) return rc;
-        LAUNCH(h, k_k2_postsolve, gN, kVecThreads, 0, V, w, d->iperm, d->N, d->xw, (int64_t)d->N);
+        if (pre) LAUNCH(h, k_k2_presolve, gN, kVecThreads, 0, V, w, d->perm, d->N, d->xw, (int64_t)d->N);
+        if (post) {
+            if ((rc = tri_solve(h, pre))) return rc;
+            LAUNCH(h, k_k2_postsolve, gN, kVecThreads, 0, V, w, d->iperm, d->N, d->xw, (int64_t)d->N);
+        }
     } else {
-        LAUNCH(h, k_normal_pre, gn, kVecThreads, 0, V, w, d->buffer_n, (int64_t)d->n);
-        LAUNCH(h, k_normal_rhs, gm, kVecThreads, 0, V, d->A_rp, d->A_ci, d->A_val, d->nnzA, w, d->buffer_n, (int64_t)d->n, d->perm, d->xw, (int64_t)d->N);
-        if ((rc = tri_solve(h))) return rc;
-        LAUNCH(h, k_normal_unperm, gm, kVecThreads, 0, V, w, d->iperm, d->xw, (int64_t)d->N);
-        LAUNCH(h, k_normal_post, gn, kVecThreads, 0, V, d->AT_rp, d->AT_ci, d->AT_val, d->nnzA, w);
+        if (pre) {
+            LAUNCH(h, k_normal_pre, gn, kVecThreads, 0, V, w, d->buffer_n, (int64_t)d->n);
+            LAUNCH(h, k_normal_rhs, gm, kVecThreads, 0, V, d->A_rp, d->A_ci, d->A_val, d->nnzA, w, d->buffer_n, (int64_t)d->n, d->perm, d->xw, (int64_t)d->N);
+        }
+        if (post) {
+            if ((rc = tri_solve(h, pre))) return rc;
+            LAUNCH(h, k_normal_unperm, gm, kVecThreads, 0, V, w, d->iperm, d->xw, (int64_t)d->N);
+            LAUNCH(h, k_normal_post, gn, kVecThreads, 0, V, d->AT_rp, d->AT_ci, d->AT_val, d->nnzA, w);
+        }
     }
     return MADIPM_OK;
+}
+
+int32_t madipm_kkt_solve(madipm_handle* h, int32_t vec_w) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    return kkt_solve_stages(h, vec_w, 3);
 }
 
 int32_t madipm_kkt_mul(madipm_handle* h, int32_t vec_w, int32_t vec_v, double alpha, double beta) {
@@ -1426,11 +1464,14 @@ int32_t madipm_kkt_mul(madipm_handle* h, int32_t vec_w, int32_t vec_v, double al
 }
 
 // solve_system! up to the three norms, which stay on the device in `norms_dev` (3 per instance)
-static int32_t solve_system_enqueue(madipm_handle* h, int32_t vec_d, int32_t vec_p, double* norms_dev) {
+// forward_done: d <- p and the solve's stage 1 were enqueued earlier and the forward sweep rode in the factor launch
+static int32_t solve_system_enqueue(madipm_handle* h, int32_t vec_d, int32_t vec_p, double* norms_dev, bool forward_done = false) {
     int32_t rc;
     DeviceState* d = h->dev;
-    if ((rc = madipm_vec_copy(h, vec_d, vec_p))) return rc;                 // linear_solver.jl:25
-    if ((rc = madipm_kkt_solve(h, vec_d))) return rc;                       // :26
+    if (!forward_done) {
+        if ((rc = madipm_vec_copy(h, vec_d, vec_p))) return rc;             // linear_solver.jl:25
+        if ((rc = madipm_kkt_solve(h, vec_d))) return rc;                   // :26
+    } else if ((rc = kkt_solve_stages(h, vec_d, 2))) return rc;
     if ((rc = madipm_vec_copy(h, MADIPM_VEC_W1, vec_p))) return rc;         // :30
     if ((rc = madipm_kkt_mul(h, MADIPM_VEC_W1, vec_d, -1.0, 1.0))) return rc;   // :31
     Timer t(h, MADIPM_T_VECTOR);
@@ -1535,13 +1576,10 @@ static void launch_ratio(madipm_handle* h, const double* tau_dev, double* out_de
 // affine_direction! (solver.jl:294-297) with one synchronisation: set_predictive_rhs!, solve_system!(d, solver, p),
 // ratio tests at tau = 1, affine complementarity, get_correction!.  norms[3] and out[4] per instance as in
 // madipm_solve_system / madipm_phase_affine.
-int32_t madipm_phase_predictor(madipm_handle* h, double* norms, double* out) {
-    int32_t rc = check(h, true);
-    if (rc) return rc;
+static int32_t predictor_tail(madipm_handle* h, double* norms, double* out, bool forward_done) {
+    int32_t rc;
     DeviceState* d = h->dev;
-    if (!norms || !out) return MADIPM_BAD_ARGUMENT;
-    if ((rc = set_rhs(h, 2, nullptr))) return rc;
-    if ((rc = solve_system_enqueue(h, MADIPM_VEC_D, MADIPM_VEC_P, d->d_norms))) return rc;
+    if ((rc = solve_system_enqueue(h, MADIPM_VEC_D, MADIPM_VEC_P, d->d_norms, forward_done))) return rc;
     {
         Timer t(h, MADIPM_T_VECTOR);
         launch_ratio(h, d->d_ones, d->d_out2);                                                   // tau = 1 (solver.jl:295)
@@ -1564,6 +1602,46 @@ int32_t madipm_phase_predictor(madipm_handle* h, double* norms, double* out) {
         out[4 * i + 3] = nb ? (tmp[4 * i + 2] + tmp[4 * i + 3]) / nb : 0.0;
     }
     return norms_status(d, norms);
+}
+
+int32_t madipm_phase_predictor(madipm_handle* h, double* norms, double* out) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    if (!norms || !out) return MADIPM_BAD_ARGUMENT;
+    if ((rc = set_rhs(h, 2, nullptr))) return rc;
+    return predictor_tail(h, norms, out, false);
+}
+
+// First try of factorize_regularized_system! (linear_solver.jl:6-17) + affine_direction! + the scalars of solver.jl:295-297
+// with ONE synchronisation and the predictor's forward sweep inside the factor launch: set_aug_diagonal_reg!, build_kkt!,
+// set_predictive_rhs!, d <- p, the pre-sweep part of solve! (none of which needs the factors), then factorisation with the
+// forward step of every supernode done while its panel is still in shared memory, backward sweep, the rest of solve_system!.
+// Same kernels' arithmetic as the separate calls (the forward step is the same device function): identical results.
+// Breakdown flags as after madipm_factorize(h, NULL): read them with madipm_is_factorized; on a breakdown the caller
+// re-enters the reference's retry (madipm_set_aug_diagonal_reg ... madipm_phase_predictor).
+int32_t madipm_phase_factor_predictor(madipm_handle* h, double del_w, double del_c, double* norms, double* out) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (!norms || !out) return MADIPM_BAD_ARGUMENT;
+    if ((rc = madipm_set_aug_diagonal_reg(h, del_w, del_c))) return rc;
+    if ((rc = madipm_build_kkt(h))) return rc;
+    const bool fuse = d->sym->n_big == 0 && !d->segs.empty();
+    if (fuse) {
+        if ((rc = set_rhs(h, 2, nullptr))) return rc;
+        if ((rc = madipm_vec_copy(h, MADIPM_VEC_D, MADIPM_VEC_P))) return rc;                    // linear_solver.jl:25
+        if ((rc = kkt_solve_stages(h, MADIPM_VEC_D, 1))) return rc;
+    }
+    {
+        Timer t(h, MADIPM_T_FACTOR);
+        bool timed_tree = false;
+        if ((rc = factorize_enqueue(h, fuse, &timed_tree))) return rc;
+        d->fail_pending = true;
+        d->prof_pending = d->profiling == 2;
+        d->prof_tree_pending = d->prof_pending && timed_tree;
+    }
+    if (!fuse && (rc = set_rhs(h, 2, nullptr))) return rc;
+    return predictor_tail(h, norms, out, fuse);
 }
 
 // mpc_direction! without Gondzio corrections (solver.jl:307-311) + the ratio tests of update_step! (solver.jl:329,

@@ -289,6 +289,13 @@ __device__ __forceinline__ void dense_ldl(double* Ps, int h, int w, int* fail, i
 // ---- numeric factorisation of one small supernode ------------------------------------------------------
 // shared: [cap doubles panel][maxh doubles (unused by the blocked LDL')][maxw doubles D][kChildChunk child records]
 template <int G>
+__device__ __forceinline__ void tree_forward_core(const TreeView& T, const SnMeta& m, int inst, const double* Ps, double* su, double* sy,
+                                                  ChildRec* cs, int t);
+
+// FWD: the task also does the forward-sweep step of its supernode for the right-hand side waiting in xw (the predictor's:
+// it depends on the iterate only, /root/reference/src/kernels.jl:21-41), with the freshly factorised panel still in shared
+// memory -- one of the four triangular sweeps of an iteration costs no panel traffic and no extra heights.
+template <int G, bool FWD>
 __device__ __forceinline__ void tree_factor_task(const TreeView& T, const SnMeta& m, int inst, double* sm, int cap, int maxh) {
     const FactorView& F = T.F;
     constexpr int NW = G / 32;
@@ -365,7 +372,10 @@ __device__ __forceinline__ void tree_factor_task(const TreeView& T, const SnMeta
     dense_ldl<G>(Ps, h, w, F.fail + inst, t);            // ends with a barrier of the whole group
     TT(2);
     for (int c = t; c < nchunk; c += G) reinterpret_cast<double2*>(P)[c] = reinterpret_cast<const double2*>(Ps)[c];
-    if (nb == 0) return;
+    if (nb == 0) {
+        if (FWD) tree_forward_core<G>(T, m, inst, Ps, ucol, dk, cs, t);      // (dense_ldl ended with a barrier of the group)
+        return;
+    }
     for (int k = t; k < w; k += G) dk[k] = Ps[k * (h + 1)];
     gsync<G>();
     TT(3);
@@ -451,6 +461,10 @@ __device__ __forceinline__ void tree_factor_task(const TreeView& T, const SnMeta
                 atomicAdd(Lx + cb + target_pos(F, rb, w + a, rows, w + b), __ldcg(col + a));
         }
     }
+    if (FWD) {
+        gsync<G>();                                       // everyone is done with D (dk) and the staged child records
+        tree_forward_core<G>(T, m, inst, Ps, ucol, dk, cs, t);
+    }
 }
 
 // ---- forward sweep: y = L^-1 b, xw <- D^-1 y ---------------------------------------------------------------
@@ -459,24 +473,33 @@ template <int G>
 __device__ __forceinline__ void tree_forward_task(const TreeView& T, const SnMeta& m, int inst, double* sm, int cap, int maxh) {
     const FactorView& F = T.F;
     const int t = threadIdx.x % G;
-    const int lane = t & 31;
-    const int gw = t >> 5;
-    const int c0 = m.c0, c1 = m.c1;
-    const int w = m.w, h = m.h, nb = h - w, fc = m.fc;
     const double* P = F.Lx + inst * F.lx_stride + m.xoff;
-    double* xw = T.xw + inst * T.xw_stride;
-    double* cv = T.cvec + inst * T.cv_stride;
     double* Ps = sm;
     double* su = Ps + cap;
     double* sy = su + maxh;
     ChildRec* cs = reinterpret_cast<ChildRec*>(sy + ((T.maxw + 1) & ~1));
-    const int nchunk = (h * w + 1) >> 1;
+    const int nchunk = (m.h * m.w + 1) >> 1;
+    gsync<G>();
+    for (int c = t; c < nchunk; c += G) cp_async16(Ps + 2 * c, P + 2 * c);
+    tree_forward_core<G>(T, m, inst, Ps, su, sy, cs, t);
+}
+
+// The forward step of one supernode on a panel that is (or is on its way to being, cp.async) in shared memory at Ps.
+// Shared by the forward sweep proper and by the factor task with FWD: same code, same arithmetic, bit for bit.
+template <int G>
+__device__ __forceinline__ void tree_forward_core(const TreeView& T, const SnMeta& m, int inst, const double* Ps, double* su, double* sy,
+                                                  ChildRec* cs, int t) {
+    const FactorView& F = T.F;
+    const int lane = t & 31;
+    const int gw = t >> 5;
+    const int c0 = m.c0, c1 = m.c1;
+    const int w = m.w, h = m.h, nb = h - w, fc = m.fc;
+    double* xw = T.xw + inst * T.xw_stride;
+    double* cv = T.cvec + inst * T.cv_stride;
 #ifdef MADIPM_TREE_TIMING
     long long tt[6];
 #endif
     TT(0);
-    gsync<G>();
-    for (int c = t; c < nchunk; c += G) cp_async16(Ps + 2 * c, P + 2 * c);
     for (int j = t; j < w; j += G) sy[j] = __ldcg(xw + fc + j);
     for (int i = t; i < nb; i += G) su[i] = 0.0;
     for (int base = 0; base < c1 - c0; base += kChildChunk) {
@@ -692,7 +715,8 @@ __device__ __forceinline__ bool grid_barrier(const TreeView& T, unsigned& target
 
 template <int OP, int G>
 __device__ __forceinline__ void tree_task(const TreeView& T, const SnMeta& m, int inst, double* sm, int cap, int maxh) {
-    if (OP == 0) tree_factor_task<G>(T, m, inst, sm, cap, maxh);
+    if (OP == 0) tree_factor_task<G, false>(T, m, inst, sm, cap, maxh);
+    else if (OP == 3) tree_factor_task<G, true>(T, m, inst, sm, cap, maxh);
     else if (OP == 1) tree_forward_task<G>(T, m, inst, sm, cap, maxh);
     else tree_backward_task<G>(T, m, inst, sm, cap, maxh);
 }
@@ -718,7 +742,7 @@ __device__ __forceinline__ void run_class(const TreeView& T, double* smem, int p
     }
 }
 
-// OP: 0 factor, 1 forward, 2 backward.  Heights ph_begin, ph_begin + step, ... (ph_end excluded).
+// OP: 0 factor, 1 forward, 2 backward, 3 factor + forward step of the right-hand side in xw.  Heights ph_begin, ph_begin + step, ... (ph_end excluded).
 template <int OP>
 __global__ void __launch_bounds__(kTreeThreads, 4)
 k_tree(TreeView T, int ph_begin, int ph_end, int step) {

@@ -93,6 +93,7 @@ class IPMOptions:
     max_width: int = 64
     block_panel: int = 0            # 0 = library default (csrc/symbolic.hpp)
     fused_phases: bool = True       # 3 host synchronisations per iteration (madipm_phase_*) instead of 7; same arithmetic
+    fused_factor_forward: bool = True   # ... and the predictor's forward sweep inside the factor launch (madipm_phase_factor_predictor)
     device_prepare: bool = True     # initialize! / set_scaling! on the device (madipm_load_problem) instead of numpy
     relax_small: int = 0            # relaxed amalgamation (0 / None = library defaults)
     relax_zeros: tuple = None
@@ -512,10 +513,14 @@ class MPCSolver:
             if fused:
                 # first try of factorize_regularized_system without a synchronisation: the breakdown flags come back with
                 # the scalars of the predictor phase; a failure (rare) re-enters the reference's retry loop
-                h.set_aug_diagonal_reg(self.del_w, self.del_c)
-                self.kkt.build_kkt()
-                h.factorize_async()
-                rc, norms, aff = h.phase_predictor()                    # l.294-297 affine_direction!
+                if opt.fused_factor_forward:
+                    # ... and with the predictor's forward sweep inside the factor launch (three sweeps per iteration)
+                    rc, norms, aff = h.phase_factor_predictor(self.del_w, self.del_c)
+                else:
+                    h.set_aug_diagonal_reg(self.del_w, self.del_c)
+                    self.kkt.build_kkt()
+                    h.factorize_async()
+                    rc, norms, aff = h.phase_predictor()                # l.294-297 affine_direction!
                 if not np.all(self.kkt.is_factorized()[self.active.astype(bool)]):
                     self.del_w *= 100.0
                     self.del_c *= 100.0

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _solver(batch=1):
-    qps = [P.inequality_qp(seed=3 + i, n=60, m=40, n_ineq=15) for i in range(batch)]
+    qps = [P.small_qp(instance=i) for i in range(batch)] if batch > 1 else [P.inequality_qp(seed=3, n=60, m=40, n_ineq=15)]
     s = MPCSolver(qps if batch > 1 else qps[0], regularization=FixedRegularization(1e-8, -1e-8))
     s.initialize()
     return s
