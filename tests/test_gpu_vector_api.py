@@ -49,7 +49,7 @@ def test_unfused_iterate_update_equals_the_fused_entry_point():
     rng = np.random.default_rng(1)
     L = a.h.vec_len("D")
     d = rng.standard_normal(L) * 1e-3
-    ap, ad, mu = 0.7, 0.4, 1e3          # a huge mu makes adjust_boundary! move bounds, so that branch is exercised
+    ap, ad, mu = 0.7, 0.4, 1e16         # a huge mu (eps * mu ~ 2) makes adjust_boundary! move bounds, so that branch is exercised
     for s in (a, b):
         s.h.vec_set("D", d)
     n, m, nlb = a.n, a.m, a.nlb
