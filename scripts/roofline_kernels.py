@@ -69,6 +69,59 @@ def timed(fn, cold, reps=20):
     return max(full - base, 1e-9) / reps
 
 
+def cusparse_baselines():
+    """cusparseSpMV (CSR, Int32 indices, FP64, CUSPARSE_SPMV_ALG_DEFAULT) on the same three operators: what the reference's GPU
+    path calls for every product (/root/reference/scripts/cuda_wrapper.jl:60-87, which also rebuilds the descriptors per call --
+    not timed here).  A stated baseline for k_spmv; library code, never on the product path."""
+    import ctypes as C
+    import scipy.sparse as sp
+    try:
+        cs = C.CDLL("libcusparse.so.12")
+    except OSError:
+        return {}
+    hdl = C.c_void_p()
+    assert cs.cusparseCreate(C.byref(hdl)) == 0
+    assert cs.cusparseSetStream(hdl, C.c_void_p(h.stream())) == 0
+    A = sp.csr_matrix((qp.A_vals, (qp.A_rows, qp.A_cols)), shape=(qp.ncon, qp.nvar))
+    ops = {"A": A, "AT": A.T.tocsr()}
+    if qp.nnzh:
+        Hl = sp.coo_matrix((qp.H_vals, (qp.H_rows, qp.H_cols)), shape=(qp.nvar, qp.nvar))
+        ops["Q"] = (Hl + sp.tril(Hl, -1).T).tocsr()
+    out, keep = {}, []
+    one, zero = C.c_double(1.0), C.c_double(0.0)
+    for name, M in ops.items():
+        M.sort_indices()
+        rp = torch.as_tensor(M.indptr.astype(np.int32), device="cuda")
+        ci = torch.as_tensor(M.indices.astype(np.int32), device="cuda")
+        va = torch.as_tensor(M.data.astype(np.float64), device="cuda")
+        x = torch.ones(M.shape[1], dtype=torch.float64, device="cuda")
+        y = torch.zeros(M.shape[0], dtype=torch.float64, device="cuda")
+        mat, vx, vy = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        assert cs.cusparseCreateCsr(C.byref(mat), C.c_int64(M.shape[0]), C.c_int64(M.shape[1]), C.c_int64(M.nnz), C.c_void_p(rp.data_ptr()),
+                                    C.c_void_p(ci.data_ptr()), C.c_void_p(va.data_ptr()), 2, 2, 0, 1) == 0      # 32I, 32I, base 0, CUDA_R_64F
+        assert cs.cusparseCreateDnVec(C.byref(vx), C.c_int64(M.shape[1]), C.c_void_p(x.data_ptr()), 1) == 0
+        assert cs.cusparseCreateDnVec(C.byref(vy), C.c_int64(M.shape[0]), C.c_void_p(y.data_ptr()), 1) == 0
+        bs = C.c_size_t(0)
+        assert cs.cusparseSpMV_bufferSize(hdl, 0, C.byref(one), mat, vx, C.byref(zero), vy, 1, 0, C.byref(bs)) == 0
+        buf = torch.empty(max(bs.value, 8), dtype=torch.uint8, device="cuda")
+        keep += [rp, ci, va, x, y, buf]
+
+        def fn(mat=mat, vx=vx, vy=vy, buf=buf):
+            rc = cs.cusparseSpMV(hdl, 0, C.byref(one), mat, vx, C.byref(zero), vy, 1, 0, C.c_void_p(buf.data_ptr()))
+            assert rc == 0, rc
+        # check against scipy once
+        fn(); torch.cuda.synchronize()
+        assert np.allclose(y.cpu().numpy(), M @ np.ones(M.shape[1]), rtol=1e-12, atol=1e-12)
+        out[f"cusparseSpMV {name:2s} (CSR, f64, ALG_DEFAULT; baseline)"] = (fn, spmv_bytes(M.nnz, M.shape[0], M.shape[1]))
+    out["_keep"] = keep
+    return out
+
+
+if scale == 1.0 or True:
+    base = cusparse_baselines()
+    _keep = base.pop("_keep", None)
+    KERNELS.update(base)
+
 for kname, spec in KERNELS.items():
     if spec is None:
         continue
