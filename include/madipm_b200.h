@@ -209,6 +209,12 @@ int32_t madipm_factorize(madipm_handle* h, int32_t* n_failed);
  *  then read with madipm_is_factorized.  The retry of linear_solver.jl:8-16 still sees every failure, one call later.) */
 /* is_factorized per instance (0/1), /root/reference/src/utils.jl:54-62 */
 int32_t madipm_is_factorized(madipm_handle* h, int32_t* flags);
+/* The LDL' does not pivot (neither does the reference's default CPU solver, LDLFactorizations).  A pivot of roundoff size --
+ * linearly dependent constraint rows with delta_c = 0 -- is not exactly zero, passes the zero / non-finite test and yields a
+ * garbage factor.  Its symptom is element growth, so a factor entry |L_ik| above `limit` counts as a breakdown as well
+ * (default 1e13: regularisation 1e-8 against entries of order one explains 1e8); 0 switches the test off (the reference's
+ * exact semantics). */
+int32_t madipm_set_growth_limit(madipm_handle* h, double limit);
 /* inertia of the last factorisation of instance `inst`: signs of D */
 int32_t madipm_inertia(madipm_handle* h, int32_t inst, int64_t* n_pos, int64_t* n_zero, int64_t* n_neg);
 /* solve!(linear_solver, rhs): in-place solve with the current factors on a device vector of

@@ -99,6 +99,7 @@ _SIGNATURES = {
     "madipm_build_kkt": ([], C.c_int32),
     "madipm_factorize": ([_P32], C.c_int32),
     "madipm_is_factorized": ([_P32], C.c_int32),
+    "madipm_set_growth_limit": ([C.c_double], C.c_int32),
     "madipm_inertia": ([C.c_int32, _P64, _P64, _P64], C.c_int32),
     "madipm_linear_solve": ([C.c_void_p, C.c_int64], C.c_int32),
     "madipm_kkt_solve": ([C.c_int32], C.c_int32),
@@ -368,6 +369,9 @@ class Handle:
         """madipm_factorize(h, NULL): no synchronisation; read the outcome with is_factorized() after the next call that
         returns scalars."""
         self._check(self.lib.madipm_factorize(self._h, None))
+
+    def set_growth_limit(self, limit):
+        self._check(self.lib.madipm_set_growth_limit(self._h, float(limit)))
 
     def is_factorized(self):
         f = np.zeros(self.batch, dtype=np.int32)

@@ -118,6 +118,7 @@ struct DeviceState {
 
     const Symbolic* sym = nullptr;
     bool values_set = false;
+    double growth_limit = 1.0e13;      // see madipm_set_growth_limit
     bool inject_barrier_fault = false; // test hook: see madipm_debug_inject_barrier_fault
     bool wedged = false;               // a synchronisation timed out: the stream still holds a kernel that never returns
     int profiling = 0;
@@ -190,7 +191,7 @@ FactorView make_factor_view(const DeviceState& d, int = 0) {
     FactorView F;
     F.sn_first = d.sn_first; F.sn_rowptr = d.sn_rowptr; F.sn_rows = d.sn_rows; F.sn_xoff = d.sn_xoff;
     F.sn_of = d.sn_of; F.row_colbase = d.row_colbase; F.row_relbase = d.row_relbase; F.rel = d.rel;
-    F.Lx = d.Lx; F.lx_stride = d.lx_stride; F.fail = d.fail;
+    F.Lx = d.Lx; F.lx_stride = d.lx_stride; F.fail = d.fail; F.growth = d.growth_limit;
     return F;
 }
 
@@ -1356,6 +1357,14 @@ int32_t madipm_factorize(madipm_handle* h, int32_t* n_failed) {
     for (int i = 0; i < B; ++i) bad += d->h_fail[i] != 0;
     if (n_failed) *n_failed = bad;
     return bad ? MADIPM_FACTOR_BREAKDOWN : MADIPM_OK;
+}
+
+int32_t madipm_set_growth_limit(madipm_handle* h, double limit) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    if (!(limit >= 0.0)) return MADIPM_BAD_ARGUMENT;
+    h->dev->growth_limit = limit;
+    return MADIPM_OK;
 }
 
 int32_t madipm_is_factorized(madipm_handle* h, int32_t* flags) {

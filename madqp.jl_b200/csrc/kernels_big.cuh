@@ -183,7 +183,7 @@ k_big_panel(FactorView F, const int* __restrict__ big_sn, double* __restrict__ z
         Ps[idx] = ldcg(&P[(i < w ? i : r0 + i - w) + j * ld]);
     }
     __syncthreads();
-    dense_ldl<kPanelThreads>(Ps, hp, w, F.fail + inst, t);
+    dense_ldl<kPanelThreads>(Ps, hp, w, F.fail + inst, t, F.growth);
     __syncthreads();
     for (int idx = t; idx < nr * w; idx += kPanelThreads) {
         const int i = idx % nr, j = idx / nr;

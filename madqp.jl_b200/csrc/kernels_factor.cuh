@@ -27,6 +27,7 @@ struct FactorView {
     double* Lx;                // [batch][lx_stride]
     int64_t lx_stride;
     int* fail;                 // [batch]
+    double growth;             // element-growth limit of the unpivoted LDL': |L_ik| above it is a breakdown (0 = no check)
 };
 
 constexpr int64_t kRelShift = int64_t(1) << 40;

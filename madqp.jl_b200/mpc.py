@@ -93,6 +93,11 @@ class IPMOptions:
     max_width: int = 64
     block_panel: int = 0            # 0 = library default (csrc/symbolic.hpp)
     fused_phases: bool = True       # 3 host synchronisations per iteration (madipm_phase_*) instead of 7; same arithmetic
+    # Deviation from linear_solver.jl:14-15, acts only after a breakdown (where the reference's unpivoted LDLSolver path fails
+    # as well): the retry multiplies (del_w, del_c) by 100, which leaves del_c = 0 (the reference's default delta_d) at 0 for
+    # ever; with the kick the first retry starts del_c at -del_w, so dependent constraint rows get a usable pivot.
+    dual_regularization_kick: bool = True
+    growth_limit: float = 1e13      # element-growth breakdown test of the unpivoted LDL' (madipm_set_growth_limit); 0 = off
     fused_factor_forward: bool = True   # ... and the predictor's forward sweep inside the factor launch (madipm_phase_factor_predictor)
     device_prepare: bool = True     # initialize! / set_scaling! on the device (madipm_load_problem) instead of numpy
     relax_small: int = 0            # relaxed amalgamation (0 / None = library defaults)
@@ -340,6 +345,8 @@ class MPCSolver:
     def start(self):
         """Device-side part of initialize! (solver.jl:144, 162-179); inputs already resident in HBM."""
         opt, h, B = self.opt, self.h, self.B
+        if opt.growth_limit != 1e13:                     # (the library's default)
+            h.set_growth_limit(opt.growth_limit)
         self.k = 0
         self.iters[:] = 0
         self.status = [INITIAL] * B
@@ -387,6 +394,13 @@ class MPCSolver:
         self.kkt.build_kkt()
         return self.kkt.factorize()
 
+    def _bump_regularization(self):
+        """linear_solver.jl:14-15 (+ the dual kick described at IPMOptions.dual_regularization_kick)."""
+        if self.opt.dual_regularization_kick and self.del_c == 0.0 and self.del_w > 0.0 and self.opt.kkt_system != "NORMAL":
+            self.del_c = -self.del_w / 100.0
+        self.del_w *= 100.0
+        self.del_c *= 100.0
+
     def factorize_regularized_system(self, tries=3):
         """/root/reference/src/linear_solver.jl:6-17."""
         for _ in range(tries):
@@ -394,8 +408,7 @@ class MPCSolver:
             self.factorize_wrapper()
             if np.all(self.kkt.is_factorized()[self.active.astype(bool)]):
                 break
-            self.del_w *= 100.0
-            self.del_c *= 100.0
+            self._bump_regularization()
 
     def solve_system(self):
         """/root/reference/src/linear_solver.jl:19-45 on (d, p)."""
@@ -522,8 +535,7 @@ class MPCSolver:
                     h.factorize_async()
                     rc, norms, aff = h.phase_predictor()                # l.294-297 affine_direction!
                 if not np.all(self.kkt.is_factorized()[self.active.astype(bool)]):
-                    self.del_w *= 100.0
-                    self.del_c *= 100.0
+                    self._bump_regularization()
                     self.factorize_regularized_system(tries=2)
                     rc, norms, aff = h.phase_predictor()
                 self._check_solve_norms(norms)
