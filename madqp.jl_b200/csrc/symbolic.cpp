@@ -682,6 +682,8 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
         // (default 1e9 entries = 4 GB of the 180 GB): the alternative is a binary search per updated entry.
         const char* benv = std::getenv("MADIPM_REL_BUDGET");
         const double rel_budget = benv ? std::atof(benv) : 1.0e9;
+        const char* cenv = std::getenv("MADIPM_CHECK_TABLES");
+        const bool check_tables = cenv && cenv[0] == '1';
         std::vector<int32_t> pos;
         for (int32_t s = 0; s < ns; ++s) {
             const int64_t r0 = S.sn_rowptr[s];
@@ -689,6 +691,8 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
             const int32_t ws = S.sn_first[s + 1] - S.sn_first[s];
             const int32_t* rows = S.sn_rows.data() + r0;
             int32_t jb = ws;
+            int32_t prev_t = -1, prev_ht = 0, prev_w = 0, prev_jb = 0;
+            bool prev_full = false;       // `pos` holds the positions in prev_t of rows[prev_jb .. hs)
             while (jb < hs) {
                 const int32_t t = S.sn_of[rows[jb]];
                 const int32_t fct = S.sn_first[t], lct = S.sn_first[t + 1];
@@ -696,20 +700,54 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
                 const int32_t ht = static_cast<int32_t>(S.sn_rowptr[t + 1] - S.sn_rowptr[t]);
                 int32_t je = jb;
                 while (je < hs && rows[je] < lct) ++je;
-                // positions of rows[jb..hs) in trows (both ascending)
-                pos.resize(hs - jb);
-                const int32_t* from = trows;
+                // positions of rows[jb..hs) in trows (both ascending).  Fast path: the rows are a subset of the ancestor's
+                // (a property of the symbolic factorisation), so when the ancestor has exactly as many rows from the position
+                // of rows[jb] on, the two lists coincide there and every position is i + c -- the whole dense trailing chain
+                // of a front-dominated problem (C4: 10^10 binary-search steps otherwise).
                 bool shift = true;
-                for (int32_t i = jb; i < hs; ++i) {
-                    const int32_t* it = std::lower_bound(from, trows + ht, rows[i]);
-                    if (it == trows + ht || *it != rows[i]) throw std::runtime_error("analyze: update row missing in ancestor");
-                    pos[i - jb] = static_cast<int32_t>(it - trows);
-                    if (pos[i - jb] - pos[0] != i - jb) shift = false;
-                    from = it + 1;
+                int32_t pos0 = 0;
+                {
+                    const int32_t* it0 = std::lower_bound(trows, trows + ht, rows[jb]);
+                    if (it0 == trows + ht || *it0 != rows[jb]) throw std::runtime_error("analyze: update row missing in ancestor");
+                    pos0 = static_cast<int32_t>(it0 - trows);
+                }
+                if (ht - pos0 != hs - jb || trows[ht - 1] != rows[hs - 1]) {
+                    if (prev_t != -1 && S.sn_parent[prev_t] == t && ht == prev_ht - prev_w && prev_full) {
+                        // t's row list is exactly the below-part of the previous target's (parent with as many rows as the
+                        // child has below its columns): positions shift by the previous target's width
+                        const int32_t skip = jb - prev_jb;
+                        for (int32_t i = jb; i < hs; ++i) pos[i - jb] = pos[i - jb + skip] - prev_w;
+                        pos.resize(hs - jb);
+                        for (int32_t i = jb; i < hs && shift; ++i)
+                            if (pos[i - jb] - pos[0] != i - jb) shift = false;
+                    } else {
+                        pos.resize(hs - jb);
+                        const int32_t* from = trows;
+                        for (int32_t i = jb; i < hs; ++i) {
+                            const int32_t* it = std::lower_bound(from, trows + ht, rows[i]);
+                            if (it == trows + ht || *it != rows[i]) throw std::runtime_error("analyze: update row missing in ancestor");
+                            pos[i - jb] = static_cast<int32_t>(it - trows);
+                            if (pos[i - jb] - pos[0] != i - jb) shift = false;
+                            from = it + 1;
+                        }
+                    }
+                    prev_full = true;
+                } else {
+                    prev_full = false;
+                }
+                prev_t = t; prev_ht = ht; prev_w = lct - fct; prev_jb = jb;
+                if (check_tables) {                       // MADIPM_CHECK_TABLES=1: every shortcut above against the plain search
+                    for (int32_t i = jb; i < hs; ++i) {
+                        const int32_t* it = std::lower_bound(trows, trows + ht, rows[i]);
+                        const int32_t want = static_cast<int32_t>(it - trows);
+                        const int32_t got = prev_full ? pos[i - jb] : pos0 + (i - jb);
+                        if (it == trows + ht || *it != rows[i] || got != want || (shift && want - pos0 != i - jb))
+                            throw std::runtime_error("analyze: scatter-table shortcut disagrees with the search");
+                    }
                 }
                 int64_t relbase;
                 if (shift) {
-                    const int64_t c = static_cast<int64_t>(pos[0]) - jb;     // position = i + c
+                    const int64_t c = static_cast<int64_t>(pos0) - jb;       // position = i + c
                     relbase = -(c + Symbolic::kRelShift) - 1;
                 } else if (hs <= 4096 || static_cast<double>(S.rel.size()) + (hs - jb) <= rel_budget) {
                     relbase = static_cast<int64_t>(S.rel.size()) - jb;      // rel[relbase + i]

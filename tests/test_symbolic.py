@@ -315,3 +315,19 @@ int main(void) {
                            "-L", lib_dir, "-l:libmadipm_b200.so", "-Wl,-rpath," + lib_dir])
     out = subprocess.check_output([str(exe)], text=True)
     assert "kind=2 order=3 nlb=2 sweeps=10" in out, out
+
+
+@pytest.mark.parametrize("maker,kw,kkt,cfg", [
+    (P.transportation_lp, dict(seed=0, n_src=300, n_dst=300, n_arcs=12000), "NORMAL", dict(block_panel=2048)),
+    (P.sparse_lp, dict(seed=1, n=6000, m=3000), "NORMAL", dict(block_panel=1024)),
+    (P.banded_qp, dict(seed=0, n=8000, m=4000), "K2", dict(block_panel=512)),
+])
+def test_scatter_table_shortcuts_agree_with_the_plain_search(maker, kw, kkt, cfg, monkeypatch):
+    """The scatter tables of the right-looking update (symbolic.cpp step 7b) take two shortcuts for nested row structures
+    (whole-list coincidence; parent = child's below rows): MADIPM_CHECK_TABLES=1 re-derives every position by binary search
+    inside analyze and throws on any difference.  Small block_panel forces multi-block supernodes, where the tables matter."""
+    monkeypatch.setenv("MADIPM_CHECK_TABLES", "1")
+    h, _ = analyze_handle(maker(**kw), kkt, **cfg)
+    info = h.info()
+    assert info["n_big"] > 0
+    h.close()
