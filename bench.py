@@ -436,6 +436,7 @@ def run_ours(args):
                         algorithmic_bytes_per_launch=alg_bytes, avg_launch_ms=sub_avg_s * 1e3, launches=sub_calls,
                         share_of_step=sub_ms / 1e3 / res["sec"] if res["sec"] > 0 else None,
                         factor_phase_ms_avg=fac_ms / max(fac_calls, 1),
+                        top_of_tree_ms_avg=prof["factor_top"][0] / max(prof["factor_top"][1], 1),
                         factor_tflops=info["factor_flops"] * B / ((fac_ms / max(fac_calls, 1)) / 1e3) / 1e12 if fac_ms > 0 else None)
         traffic = {}
         try:

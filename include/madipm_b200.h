@@ -311,7 +311,8 @@ int64_t madipm_launch_count(const madipm_handle* h);
 /* accumulated device milliseconds per kernel class since the last reset (CUDA events on the
  * handle's stream; enabled by madipm_profile(h, 1)) */
 enum { MADIPM_T_ASSEMBLY = 0, MADIPM_T_FACTOR, MADIPM_T_SOLVE, MADIPM_T_SPMV, MADIPM_T_VECTOR,
-       MADIPM_T_FACTOR_TREE /* the k_tree_factor launches alone */, MADIPM_T_COUNT };
+       MADIPM_T_FACTOR_TREE /* the tree launches of the first segment alone */,
+       MADIPM_T_FACTOR_TOP /* ... of which the launch for the heights near the root (k_front / k_tree_top) */, MADIPM_T_COUNT };
 /* enable = 1: every class, with a stream synchronisation per call (diagnostic runs only);
  * enable = 2: only the factorisation (classes FACTOR and FACTOR_TREE), read at the synchronisation
  *             madipm_factorize performs anyway -- cheap enough to leave on inside a timed region. */

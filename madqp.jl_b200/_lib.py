@@ -33,7 +33,7 @@ SYM = dict(PERM=0, ETREE_PARENT=1, COLCOUNT=2, SUPER_FIRST=3, SUPER_PARENT=4, SU
            A_CSR_MAP=14, SUPER_LEVEL=15, PROD_PTR=16, PROD_A=17, PROD_B=18, PROD_K=19, CHILD_PTR=20, CHILD_IDX=21,
            SUPER_KIND=22, PAR_POS=23, SUPER_COFF=24, TASK_SN=25, PHASE_PTR=26, PHASE_NBLOCK=27, PHASE_CLS=28)
 
-T_CLASSES = ["assembly", "factor", "solve", "spmv", "vector", "factor_tree"]
+T_CLASSES = ["assembly", "factor", "solve", "spmv", "vector", "factor_tree", "factor_top"]
 
 
 class MadIPMError(RuntimeError):

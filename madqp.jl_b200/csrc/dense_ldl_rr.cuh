@@ -2,15 +2,20 @@
 //
 // Why: a front near the root of the elimination tree is one task on one SM and nothing else can run until it is done
 // (the height is a phase), so what counts is the length of the dependent chain per column, not flops.  Thread t owns row t
-// of the panel and keeps its w entries in registers (compile-time bound WMAX, fully unrolled).  Column j:
-//   * everybody reads the published column  u_k = a_kj (k > j, the entries of the pivot block below the diagonal, before
-//     scaling) and d_j from a small shared buffer (broadcast loads),
-//   * l_ij = a_ij / d_j, then FIRST the entry of the next column, a_i,j+1 -= l_ij u_j+1, which is published at once for
-//     step j + 1 (look-ahead), then the rest of the row, a_ik -= l_ij u_k,
+// of the panel and keeps the part of it that is still to be eliminated in registers.  Column j:
+//   * everybody reads the published pivot column (d_j and u_r = a_{j+r,j}, r >= 1: the entries of the pivot block below the
+//     diagonal, before scaling) from a small shared buffer, indexed RELATIVE to the pivot (broadcast 16-byte loads at
+//     compile-time offsets),
+//   * l_ij = a_ij / d_j goes to the panel, then FIRST the entry of the next column, a_i,j+1 -= l_ij u_1, which is
+//     published at once for step j + 1 (look-ahead), then the rest of the row, a_i,j+k -= l_ij u_k,
+//   * the register row SHIFTS by one (the FMA for a_k writes register k - 1), so the loop body has compile-time register
+//     indices while j is a run-time loop variable: the code is one compact loop per register width (W, W - 8, ..., 8: the
+//     width follows the shrinking trailing row), a few hundred instructions in all.  (A fully unrolled j loop is 50 KB of
+//     straight-line code per width that is executed once per front: measured 14 k cycles with a warm instruction cache and
+//     30 k inside the factorisation kernel, where it never is.)
 //   * one barrier (the buffer is double-buffered by column parity).
-// The chain per column is LDS -> rcp -> mul -> fma -> STS -> barrier, about 150 cycles; the blocked left-looking routine
-// (dense_ldl in kernels_tree.cuh) needs about 900 per column on the same fronts because its inner loops run over
-// shared-memory operands.
+// The blocked left-looking routine (dense_ldl in kernels_tree.cuh) keeps the row in shared memory and needs ~600 cycles per
+// column on the same fronts (~1100 inside k_tree_top with its 32 warps per barrier).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -31,67 +36,77 @@ __device__ __forceinline__ void rr_bar(int id, int n) {
     else asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
 
-// Column steps j = J .. WMAX-1 as a compile-time recursion: every index into the register row is a constant (a runtime
-// loop, or an unroll the compiler declines, would send the row to local memory).  Columns w .. WMAX-1 are zero padding
-// (a_k = 0 and u_k = 0 there), so the row update runs unpredicated over the compile-time width.
-template <int WMAX, int J>
-struct rr_steps {
-    static __device__ __forceinline__ void run(double (&a)[WMAX], double* __restrict__ buf, int w, int t, int nact, int bar_id) {
-        constexpr int LD = WMAX + 2;
-        if (J >= w) return;
-        const double* u = buf + (J & 1) * LD;
-        double* un = buf + ((J + 1) & 1) * LD;
-        const double l = a[J] * rr_rcp(u[J]);
-        constexpr int J1 = (J + 1 < WMAX) ? J + 1 : J;
-        if (J + 1 < WMAX) {
-            a[J1] = fma(-l, u[J1], a[J1]);
-            if (t > J && t < w) un[t] = a[J1];                            // rows J+1 .. w-1 publish column J+1
-        }
-        // the rest of the row: u in aligned pairs (one 16-byte broadcast load per two columns)
-        constexpr int K0 = J + 2;
-        constexpr int KA = (K0 + 1) & ~1;                                 // first even index >= K0
-        if (K0 < KA && K0 < WMAX) a[K0 < WMAX ? K0 : 0] = fma(-l, u[K0 < WMAX ? K0 : 0], a[K0 < WMAX ? K0 : 0]);
-#pragma unroll
-        for (int k = KA; k + 1 < WMAX; k += 2) {
-            const double2 uu = *reinterpret_cast<const double2*>(u + k);
-            a[k] = fma(-l, uu.x, a[k]);
-            a[k + 1] = fma(-l, uu.y, a[k + 1]);
-        }
-        if (t > J) a[J] = l;                                              // unit-lower factor; row J keeps d_J
-        rr_bar(bar_id, nact);
-        rr_steps<WMAX, J + 1>::run(a, buf, w, t, nact, bar_id);
-    }
-};
-template <int WMAX>
-struct rr_steps<WMAX, WMAX> {
-    static __device__ __forceinline__ void run(double (&)[WMAX], double*, int, int, int, int) {}
+constexpr int kRrLd = 64 + 2;           // leading dimension of the two column buffers (doubles)
+
+struct RrState {
+    double* Ps;
+    double* buf;
+    int h, w, t, nact, bar_id;
+    double growth;
+    bool bad;
 };
 
-// Ps: panel, column-major, leading dimension h; on return D on the diagonal, unit-lower L below (strict upper triangle of
-// the pivot block: untouched).  buf: 2 * (WMAX + 2) doubles of shared memory, 16-byte aligned.  t: index of the thread in
-// its group; the group has at least ((h + 31) & ~31) threads; threads with t >= that return at once.  bar_id: a named
-// barrier reserved for this group.  Requires w <= WMAX (even), h >= w.  Pivots are not checked here (the caller looks at D).
+// columns J, J + 1, ... with a register row of width W (a[k] = entry (t, J + k)), while more than W - 8 columns remain
+template <int WMAX, int W>
+struct rr_phase {
+    static __device__ __forceinline__ void run(double (&a)[WMAX], RrState& S, int& J) {
+        const int w = S.w, h = S.h, t = S.t;
+#pragma unroll 1
+        while (J < w && (W == 8 || w - J > W - 8)) {
+            const double* u = S.buf + (J & 1) * kRrLd;
+            double* un = S.buf + ((J + 1) & 1) * kRrLd;
+            const double2 u01 = *reinterpret_cast<const double2*>(u);
+            const double d = u01.x;
+            S.bad |= !(fabs(d) > 0.0 && fabs(d) < 1.0e300);
+            const double l = a[0] * rr_rcp(d);
+            const double a1 = fma(-l, u01.y, a[1]);
+            if (t == J) S.Ps[J * (h + 1)] = d;                       // D stays on the diagonal
+            if (t > J) {
+                if (t < w) un[t - J - 1] = a1;                       // rows J+1 .. w-1 publish column J+1 (row J+1: its pivot)
+                if (t < h) {
+                    S.Ps[t + J * h] = l;                             // unit-lower factor
+                    S.bad |= S.growth > 0.0 && !(fabs(l) <= S.growth);
+                }
+            }
+            a[0] = a1;
+#pragma unroll
+            for (int k = 2; k + 1 < W; k += 2) {
+                const double2 uu = *reinterpret_cast<const double2*>(u + k);
+                a[k - 1] = fma(-l, uu.x, a[k]);
+                a[k] = fma(-l, uu.y, a[k + 1]);
+            }
+            a[W - 1] = 0.0;
+            ++J;
+            rr_bar(S.bar_id, S.nact);
+        }
+        if constexpr (W > 8) rr_phase<WMAX, W - 8>::run(a, S, J);
+    }
+};
+
+// Ps: panel, column-major, leading dimension h; on return D on the diagonal, unit-lower L below (the strict upper triangle
+// of the pivot block is left alone).  buf: 2 * kRrLd doubles of shared memory, 16-byte aligned.  t: index of the thread in
+// its group; the group has at least ((h + 31) & ~31) threads; threads with t >= that return at once (false).  bar_id: a named
+// barrier reserved for this group.  Requires w <= WMAX <= 64 (WMAX a multiple of 8), h >= w.  Returns true where this
+// thread saw a zero / non-finite pivot or (growth > 0) a factor entry of its row above `growth` in magnitude.
 template <int WMAX>
-__device__ __forceinline__ void dense_ldl_rr(double* __restrict__ Ps, int h, int w, double* __restrict__ buf, int t, int bar_id) {
-    static_assert(WMAX % 2 == 0, "WMAX must be even");
-    constexpr int LD = WMAX + 2;
+__device__ __forceinline__ bool dense_ldl_rr(double* __restrict__ Ps, int h, int w, double* __restrict__ buf, int t, int bar_id,
+                                             double growth = 0.0) {
+    static_assert(WMAX % 8 == 0 && WMAX <= 64, "WMAX: multiple of 8, at most 64");
     const int nact = (h + 31) & ~31;
-    if (t >= nact) return;
+    if (t >= nact) return false;
     const bool live = t < h;
     double a[WMAX];
 #pragma unroll
     for (int k = 0; k < WMAX; ++k) a[k] = (live && k < w && k <= t) ? Ps[t + k * h] : 0.0;
-    // zero padding of both column buffers beyond w, then column 0
-    for (int k = w + t; k < 2 * LD; k += nact)
-        if (k < LD || k >= LD + w) buf[k] = 0.0;
+    // column 0, relative to its pivot; the rest of both buffers is zero (entries past the pivot block multiply padding only)
+    for (int k = t; k < 2 * kRrLd; k += nact) buf[k] = 0.0;
+    rr_bar(bar_id, nact);
     if (live && t < w) buf[t] = a[0];
     rr_bar(bar_id, nact);
-    rr_steps<WMAX, 0>::run(a, buf, w, t, nact, bar_id);
-    if (live) {
-#pragma unroll
-        for (int k = 0; k < WMAX; ++k)
-            if (k < w && k <= t) Ps[t + k * h] = a[k];
-    }
+    RrState S{Ps, buf, h, w, t, nact, bar_id, growth, false};
+    int J = 0;
+    rr_phase<WMAX, WMAX>::run(a, S, J);
+    return S.bad;
 }
 
 }  // namespace madipm

@@ -15,6 +15,7 @@
 #include "handle.hpp"
 #include "kernels_factor.cuh"
 #include "kernels_tree.cuh"
+#include "kernels_front.cuh"
 #include "kernels_big.cuh"
 #include "kernels_vec.cuh"
 
@@ -42,6 +43,9 @@ struct DeviceState {
     size_t smem_tree = 0;
     int tree_occ[4] = {0, 0, 0, 0};
     int* tickets[3] = {nullptr, nullptr, nullptr};
+    bool use_front = false;            // the heights near the root are factorised by k_front (kernels_front.cuh) instead of k_tree_top
+    FrontLayout front_lo = {};
+    size_t smem_front = 0;
     int* phase_cls = nullptr;
     int num_sms = 0;
     unsigned* abort_flag = nullptr;    // device: a grid barrier gave up (kernels_tree.cuh grid_barrier)
@@ -122,7 +126,7 @@ struct DeviceState {
     bool inject_barrier_fault = false; // test hook: see madipm_debug_inject_barrier_fault
     bool wedged = false;               // a synchronisation timed out: the stream still holds a kernel that never returns
     int profiling = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr;   // ev4: before the top launch of the first segment
     double t_ms[MADIPM_T_COUNT] = {};
     int64_t t_calls[MADIPM_T_COUNT] = {};
 };
@@ -245,11 +249,11 @@ struct Timer {
 std::string describe_tree_debug(const DeviceState* d) {
     const TreeDebug g = d->tree_dbg ? *d->tree_dbg : TreeDebug{};
     if (!g.aborted) return "no grid barrier reported a timeout";
-    static const char* kn[] = {"k_tree", "k_tree_top"};
+    static const char* kn[] = {"k_tree", "k_tree_top", "k_front", "?"};
     static const char* on[] = {"factor", "forward", "backward"};
     char buf[320];
     std::snprintf(buf, sizeof(buf), "grid barrier timed out: %s<%s> after height %d, block %u of %u saw %u arrivals, waited for %u, for %.0f ms",
-                  kn[g.kernel & 1], on[g.op % 3], g.phase, g.block, g.grid, g.seen, g.target, g.waited_ns / 1e6);
+                  kn[g.kernel & 3], on[g.op == 3 ? 0 : g.op % 3], g.phase, g.block, g.grid, g.seen, g.target, g.waited_ns / 1e6);
     return buf;
 }
 
@@ -303,6 +307,7 @@ void pending_collect(madipm_handle* h) {
         if (cudaEventElapsedTime(&ms, d->ev0, d->ev1) == cudaSuccess) { d->t_ms[MADIPM_T_FACTOR] += ms; d->t_calls[MADIPM_T_FACTOR] += 1; }
         if (d->prof_tree_pending && cudaEventElapsedTime(&ms, d->ev2, d->ev3) == cudaSuccess) {
             d->t_ms[MADIPM_T_FACTOR_TREE] += ms; d->t_calls[MADIPM_T_FACTOR_TREE] += 1;
+            if (cudaEventElapsedTime(&ms, d->ev4, d->ev3) == cudaSuccess) { d->t_ms[MADIPM_T_FACTOR_TOP] += ms; d->t_calls[MADIPM_T_FACTOR_TOP] += 1; }
         }
         d->prof_pending = d->prof_tree_pending = false;
     }
@@ -463,6 +468,14 @@ int32_t launch_tree(madipm_handle* h, const DeviceState::TreeSeg& sg) {
         if (sg.ph1 <= sg.split || sg.grid_top <= 0) return MADIPM_OK;
         int b = reverse ? sg.ph1 - 1 : sg.split, e = reverse ? sg.split - 1 : sg.ph1, step = reverse ? -1 : 1;
         T.bar = reinterpret_cast<unsigned*>(tickets + kSyncStride * sg.split + kSyncBar);
+        if ((OP == 0 || OP == 3) && d->use_front) {
+            FrontLayout lo = d->front_lo;
+            void* fargs[] = {&T, &lo, &b, &e};
+            CUDA_OK(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_front<OP == 3 ? 3 : 0>), dim3(sg.grid_top), dim3(kFrontThreads),
+                                                   fargs, d->smem_front, d->stream));
+            ++h->launches;
+            return MADIPM_OK;
+        }
         void* args[] = {&T, &b, &e, &step};
         CUDA_OK(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_tree_top<OP>), dim3(sg.grid_top), dim3(kTopThreads), args,
                                                d->smem_tree, d->stream));
@@ -472,6 +485,7 @@ int32_t launch_tree(madipm_handle* h, const DeviceState::TreeSeg& sg) {
     int32_t rc;
     if (reverse) { if ((rc = top())) return rc; return bottom(); }
     if ((rc = bottom())) return rc;
+    if ((OP == 0 || OP == 3) && d->profiling == 2 && &sg == &d->segs.front()) cudaEventRecord(d->ev4, d->stream);
     return top();
 }
 
@@ -530,6 +544,7 @@ int32_t device_create(madipm_handle* h) {
     CUDA_OK(h, cudaEventCreate(&d->ev1));
     CUDA_OK(h, cudaEventCreate(&d->ev2));
     CUDA_OK(h, cudaEventCreate(&d->ev3));
+    CUDA_OK(h, cudaEventCreate(&d->ev4));
     const KktPattern& p = h->pat;
     const Symbolic& s = h->sym;
     if (p.A_rowptr.back() > INT32_MAX || p.kkt_colptr.back() > INT32_MAX || (int64_t)s.sn_rows.size() > INT32_MAX ||
@@ -754,6 +769,32 @@ int32_t device_create(madipm_handle* h) {
             CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_tree_top<2>, kTopThreads, d->smem_tree)); top_occ = std::min(top_occ, o);
             CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_tree_top<3>, kTopThreads, d->smem_tree)); top_occ = std::min(top_occ, o);
         }
+        {   // k_front for the factorisation of the heights near the root: needs every front to fit its layout
+            auto even = [](int64_t v) { return static_cast<int>((v + 1) & ~int64_t(1)); };
+            int64_t nbmax = 0;
+            for (int sn = 0; sn < s.nsuper; ++sn)
+                if (s.sn_kind[sn] != 2)
+                    nbmax = std::max<int64_t>(nbmax, (s.sn_rowptr[sn + 1] - s.sn_rowptr[sn]) - (s.sn_first[sn + 1] - s.sn_first[sn]));
+            FrontLayout lo;
+            lo.cap = even(std::max(s.small_max_panel, 2)) + 2;
+            lo.ctri = even(nbmax * (nbmax + 1) / 2 + 2);
+            lo.maxh = even(std::max(s.small_max_h, 2));
+            lo.maxw = even(std::max(s.max_w, 1));
+            lo.total = lo.cap + lo.ctri + lo.maxh + lo.maxw + 2 * 66 + kChildChunk * 4 + kFrontPosCap / 2;
+            const char* nf = std::getenv("MADIPM_NO_FRONT");
+            d->front_lo = lo;
+            d->smem_front = static_cast<size_t>(lo.total) * sizeof(double);
+            d->use_front = s.n_big == 0 && s.small_max_h <= kFrontThreads && s.max_w <= 64 && d->smem_front <= 200 * 1024 &&
+                           !(nf && nf[0] == '1');
+            if (d->use_front) {
+                CUDA_OK(h, cudaFuncSetAttribute(k_front<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_front));
+                CUDA_OK(h, cudaFuncSetAttribute(k_front<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_front));
+                int o0 = 0, o3 = 0;
+                CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o0, k_front<0>, kFrontThreads, d->smem_front));
+                CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, k_front<3>, kFrontThreads, d->smem_front));
+                if (o0 < 1 || o3 < 1) d->use_front = false;
+            }
+        }
         for (int op = 0; op < 4; ++op)
             if (d->tree_occ[op] < 1) { h->error = "tree kernel does not fit on an SM"; return MADIPM_INTERNAL; }
         // launch plan: consecutive heights share one cooperative launch; a height with big supernodes ends it
@@ -870,6 +911,7 @@ void device_destroy(madipm_handle* h) {
     if (d->ev1) cudaEventDestroy(d->ev1);
     if (d->ev2) cudaEventDestroy(d->ev2);
     if (d->ev3) cudaEventDestroy(d->ev3);
+    if (d->ev4) cudaEventDestroy(d->ev4);
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d;
     h->dev = nullptr;
@@ -1349,6 +1391,7 @@ int32_t madipm_factorize(madipm_handle* h, int32_t* n_failed) {
             if (timed_tree) {
                 cudaEventElapsedTime(&ms, d->ev2, d->ev3);
                 d->t_ms[MADIPM_T_FACTOR_TREE] += ms; d->t_calls[MADIPM_T_FACTOR_TREE] += 1;
+                if (cudaEventElapsedTime(&ms, d->ev4, d->ev3) == cudaSuccess) { d->t_ms[MADIPM_T_FACTOR_TOP] += ms; d->t_calls[MADIPM_T_FACTOR_TOP] += 1; }
             }
         }
     }

@@ -8,7 +8,7 @@
 using namespace madipm;
 
 template <int WMAX>
-__global__ void __launch_bounds__(128, 1) kb_rr(double* P, int h, int w, long long* cyc, int reps) {
+__global__ void __launch_bounds__(256, 1) kb_rr(double* P, int h, int w, long long* cyc, int reps) {
     extern __shared__ double2 sm2[];
     double* Ps = reinterpret_cast<double*>(sm2);
     double* buf = Ps + ((h * w + 1) & ~1);
@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(128, 1) kb_rr(double* P, int h, int w, long lo
         for (int i = t; i < h * w; i += blockDim.x) Ps[i] = P[i];
         __syncthreads();
         long long t0 = clock64();
-        dense_ldl_rr<WMAX>(Ps, h, w, buf, t, 1);
+        bad |= dense_ldl_rr<WMAX>(Ps, h, w, buf, t, 1, 1e13);
         __syncthreads();
         long long t1 = clock64();
         if (t1 - t0 < best) best = t1 - t0;
@@ -58,7 +58,7 @@ static double check(const std::vector<double>& A0, const std::vector<double>& L,
 }
 
 int main() {
-    int shapes[][2] = {{109, 47}, {73, 47}, {113, 64}, {72, 64}, {65, 25}, {37, 16}, {24, 8}, {16, 4}, {128, 32}};
+    int shapes[][2] = {{109, 47}, {73, 47}, {113, 64}, {72, 64}, {104, 44}, {76, 56}, {65, 25}, {37, 16}, {24, 8}, {16, 4}, {128, 32}, {200, 40}};
     for (auto& sh : shapes) {
         int h = sh[0], w = sh[1];
         std::vector<double> A(h * w), A0;
@@ -78,9 +78,10 @@ int main() {
         printf("h %3d w %2d old<256>   : %7lld cycles (%5.0f per column) err %.2e %s\n", h, w, c[0], c[0] / (double)w, check(A0, L, h, w), cudaGetErrorString(e));
         // new
         cudaMemcpy(dP, A0.data(), A.size() * 8, cudaMemcpyHostToDevice);
-#define RUN(WM) do { cudaFuncSetAttribute(kb_rr<WM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); kb_rr<WM><<<1, 128, smem>>>(dP, h, w, cyc, 5); } while (0)
-        int wm = w <= 16 ? 16 : w <= 32 ? 32 : w <= 48 ? 48 : 64;
-        if (wm == 16) RUN(16); else if (wm == 32) RUN(32); else if (wm == 48) RUN(48); else RUN(64);
+#define RUN(WM) do { cudaFuncSetAttribute(kb_rr<WM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); kb_rr<WM><<<1, 256, smem>>>(dP, h, w, cyc, 5); } while (0)
+        int wm = (w + 7) / 8 * 8;
+        switch (wm) { case 8: RUN(8); break; case 16: RUN(16); break; case 24: RUN(24); break; case 32: RUN(32); break; case 40: RUN(40); break;
+                      case 48: RUN(48); break; case 56: RUN(56); break; default: RUN(64); }
         e = cudaDeviceSynchronize();
         cudaMemcpy(c, cyc, 16, cudaMemcpyDeviceToHost); cudaMemcpy(L.data(), dP, A.size() * 8, cudaMemcpyDeviceToHost);
         printf("h %3d w %2d rr<%2d>      : %7lld cycles (%5.0f per column) err %.2e bad %lld %s\n", h, w, wm, c[0], c[0] / (double)w, check(A0, L, h, w), c[1], cudaGetErrorString(e));
