@@ -211,10 +211,11 @@ int32_t madipm_factorize(madipm_handle* h, int32_t* n_failed);
 int32_t madipm_is_factorized(madipm_handle* h, int32_t* flags);
 /* The LDL' does not pivot (neither does the reference's default CPU solver, LDLFactorizations).  A pivot of roundoff size --
  * linearly dependent constraint rows with delta_c = 0 -- is not exactly zero, passes the zero / non-finite test and yields a
- * garbage factor.  Its symptom is element growth, so a factor entry |L_ik| above `limit` counts as a breakdown as well
- * (default 1e13: regularisation 1e-8 against entries of order one explains 1e8); 0 switches the test off (the reference's
- * exact semantics). */
-int32_t madipm_set_growth_limit(madipm_handle* h, double limit);
+ * garbage factor.  Two more breakdown tests catch it: |pivot| <= tiny (default 1e-13 in the scaled problem's units: the
+ * regularised pivots of an interior-point KKT matrix are 1e-8 and up, cancellation leaves 1e-16 times the operands), and
+ * element growth, a factor entry |L_ik| above `growth` (default 1e13: regularisation 1e-8 against entries of order one
+ * explains 1e8).  0 switches a test off; (0, 0) is the reference's exact semantics. */
+int32_t madipm_set_pivot_checks(madipm_handle* h, double tiny, double growth);
 /* inertia of the last factorisation of instance `inst`: signs of D */
 int32_t madipm_inertia(madipm_handle* h, int32_t inst, int64_t* n_pos, int64_t* n_zero, int64_t* n_neg);
 /* solve!(linear_solver, rhs): in-place solve with the current factors on a device vector of
@@ -352,6 +353,27 @@ int32_t madipm_phase_factor_predictor(madipm_handle* h, double del_w, double del
 /* mpc_direction! without Gondzio corrections, solver.jl:307-311, + the ratio tests of update_step! (kernels.jl:290-305):
  * set_correction_rhs!(mu) + solve_system! + ratio tests at tau.  ratio: 8 per instance as madipm_ratio_test. */
 int32_t madipm_phase_corrector(madipm_handle* h, const double* mu, const double* tau, double* norms, double* ratio8);
+
+/* One whole iteration of mpc! (solver.jl:288-342) with ONE synchronisation, for max_ncorr = 0 and the Conservative / Adaptive
+ * step rules: madipm_phase_factor_predictor, update_barrier! (kernels.jl:226-236), madipm_phase_corrector, update_step!,
+ * madipm_update_iterate, madipm_eval_model and the residuals of the NEW iterate (what the next pass of the loop starts
+ * with).  The scalars the host computes between the phases (mu_affine, mu_curr, sigma, mu, tau, alpha_p, alpha_d) are
+ * computed on the device in the same floating-point operations.  The iterate is updated only if, for every active
+ * instance, the factorisation did not break down and both residual ratios are numbers; otherwise *ok = 0, nothing has
+ * moved, and the caller redoes the iteration through the separate phases (the reference's retry, linear_solver.jl:8-16).
+ * active: one flag per instance or NULL (all).  out: 28 doubles per instance:
+ *   [0:3) predictor norms (as madipm_solve_system), [3:7) alpha_aff_p, alpha_aff_d, mu_affine, mu_curr, [7] mu, [8] tau,
+ *   [9:12) corrector norms, [12:20) ratio tests at tau (as madipm_ratio_test), [20:22) alpha_p, alpha_d,
+ *   [22:26) residuals of the new iterate (as madipm_phase_residuals), [26] its objective c0 + c'x + x'Qx/2, [27] unused. */
+typedef struct {
+    double del_w, del_c;      /* regularisation of this iteration */
+    double mu_min;            /* opt.mu_min */
+    double tau;               /* ConservativeStep: tau;  AdaptiveStep: tau_min */
+    double c0;                /* constant term of the objective (scaled) */
+    int32_t adaptive_step;    /* 1: tau = max(1 - mu, tau_min) (kernels.jl:315-323), 0: tau fixed (kernels.jl:307-313) */
+    int32_t has_inequalities; /* SURVEY 8a note B.1: any finite bound */
+} madipm_iter_options;
+int32_t madipm_phase_iteration(madipm_handle* h, const madipm_iter_options* opt, const int32_t* active, double* out28, int32_t* ok);
 
 /* ---- preprocessing --------------------------------------------------------------- */
 /* scale_qp, /root/reference/scripts/common.jl:38-100: Ruiz equilibration of the constraint matrix in the infinity

@@ -53,6 +53,11 @@ class LoadOptions(C.Structure):
                 ("scaling", C.c_int32), ("reserved", C.c_int32)]
 
 
+class IterOptions(C.Structure):
+    _fields_ = [("del_w", C.c_double), ("del_c", C.c_double), ("mu_min", C.c_double), ("tau", C.c_double), ("c0", C.c_double),
+                ("adaptive_step", C.c_int32), ("has_inequalities", C.c_int32)]
+
+
 class ScaleOptions(C.Structure):
     _fields_ = [("device", C.c_int32), ("max_iter", C.c_int32), ("tol", C.c_double), ("launches", C.c_int64)]
 
@@ -99,7 +104,7 @@ _SIGNATURES = {
     "madipm_build_kkt": ([], C.c_int32),
     "madipm_factorize": ([_P32], C.c_int32),
     "madipm_is_factorized": ([_P32], C.c_int32),
-    "madipm_set_growth_limit": ([C.c_double], C.c_int32),
+    "madipm_set_pivot_checks": ([C.c_double, C.c_double], C.c_int32),
     "madipm_inertia": ([C.c_int32, _P64, _P64, _P64], C.c_int32),
     "madipm_linear_solve": ([C.c_void_p, C.c_int64], C.c_int32),
     "madipm_kkt_solve": ([C.c_int32], C.c_int32),
@@ -142,6 +147,7 @@ _SIGNATURES = {
     "madipm_phase_predictor": ([_PD, _PD], C.c_int32),
     "madipm_phase_factor_predictor": ([C.c_double, C.c_double, _PD, _PD], C.c_int32),
     "madipm_phase_corrector": ([_PD, _PD, _PD, _PD], C.c_int32),
+    "madipm_phase_iteration": ([C.POINTER(IterOptions), _P32, _PD, _P32], C.c_int32),
     "madipm_default_scale_options": (None, [C.POINTER(ScaleOptions)], None),
     "madipm_scale_qp": (None, [C.POINTER(ScaleOptions), C.c_int32, C.c_int32, C.c_int64, _P32, _P32, _PD, C.c_int64, _P32, _P32, _PD,
                                _PD, _PD, _PD, _PD, _PD, _PD, _PD, _PD, _PD, _P32, _PD], C.c_int32),
@@ -370,8 +376,8 @@ class Handle:
         returns scalars."""
         self._check(self.lib.madipm_factorize(self._h, None))
 
-    def set_growth_limit(self, limit):
-        self._check(self.lib.madipm_set_growth_limit(self._h, float(limit)))
+    def set_pivot_checks(self, tiny, growth):
+        self._check(self.lib.madipm_set_pivot_checks(self._h, float(tiny), float(growth)))
 
     def is_factorized(self):
         f = np.zeros(self.batch, dtype=np.int32)
@@ -427,6 +433,15 @@ class Handle:
         norms, out = np.zeros(3 * self.batch), np.zeros(4 * self.batch)
         rc = self._check(self.lib.madipm_phase_factor_predictor(self._h, del_w, del_c, _pd(norms), _pd(out)), allow=(NONFINITE,))
         return rc, norms.reshape(self.batch, 3), out.reshape(self.batch, 4)
+
+    def phase_iteration(self, del_w, del_c, mu_min, tau, adaptive, has_inequalities, c0=0.0, active=None):
+        """One mpc! iteration with one synchronisation (madipm_phase_iteration).  Returns (ok, out[batch, 28])."""
+        opt = IterOptions(del_w, del_c, mu_min, tau, c0, 1 if adaptive else 0, 1 if has_inequalities else 0)
+        out = np.zeros(28 * self.batch)
+        ok = C.c_int32(0)
+        act = None if active is None else np.ascontiguousarray(active, dtype=np.int32)
+        self._check(self.lib.madipm_phase_iteration(self._h, C.byref(opt), _p32(act), _pd(out), C.byref(ok)))
+        return bool(ok.value), out.reshape(self.batch, 28)
 
     def phase_corrector(self, mu, tau):
         mu = _f64(np.broadcast_to(mu, (self.batch,)))

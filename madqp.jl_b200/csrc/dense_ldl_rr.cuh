@@ -42,7 +42,7 @@ struct RrState {
     double* Ps;
     double* buf;
     int h, w, t, nact, bar_id;
-    double growth;
+    double growth, tiny;
     bool bad;
 };
 
@@ -57,7 +57,7 @@ struct rr_phase {
             double* un = S.buf + ((J + 1) & 1) * kRrLd;
             const double2 u01 = *reinterpret_cast<const double2*>(u);
             const double d = u01.x;
-            S.bad |= !(fabs(d) > 0.0 && fabs(d) < 1.0e300);
+            S.bad |= !(fabs(d) > S.tiny && fabs(d) < 1.0e300);
             const double l = a[0] * rr_rcp(d);
             const double a1 = fma(-l, u01.y, a[1]);
             if (t == J) S.Ps[J * (h + 1)] = d;                       // D stays on the diagonal
@@ -87,10 +87,10 @@ struct rr_phase {
 // of the pivot block is left alone).  buf: 2 * kRrLd doubles of shared memory, 16-byte aligned.  t: index of the thread in
 // its group; the group has at least ((h + 31) & ~31) threads; threads with t >= that return at once (false).  bar_id: a named
 // barrier reserved for this group.  Requires w <= WMAX <= 64 (WMAX a multiple of 8), h >= w.  Returns true where this
-// thread saw a zero / non-finite pivot or (growth > 0) a factor entry of its row above `growth` in magnitude.
+// thread saw a zero / tiny (|d| <= tiny) / non-finite pivot or (growth > 0) a factor entry of its row above `growth` in magnitude.
 template <int WMAX>
 __device__ __forceinline__ bool dense_ldl_rr(double* __restrict__ Ps, int h, int w, double* __restrict__ buf, int t, int bar_id,
-                                             double growth = 0.0) {
+                                             double growth = 0.0, double tiny = 0.0) {
     static_assert(WMAX % 8 == 0 && WMAX <= 64, "WMAX: multiple of 8, at most 64");
     const int nact = (h + 31) & ~31;
     if (t >= nact) return false;
@@ -103,7 +103,7 @@ __device__ __forceinline__ bool dense_ldl_rr(double* __restrict__ Ps, int h, int
     rr_bar(bar_id, nact);
     if (live && t < w) buf[t] = a[0];
     rr_bar(bar_id, nact);
-    RrState S{Ps, buf, h, w, t, nact, bar_id, growth, false};
+    RrState S{Ps, buf, h, w, t, nact, bar_id, growth, tiny, false};
     int J = 0;
     rr_phase<WMAX, WMAX>::run(a, S, J);
     return S.bad;

@@ -107,6 +107,8 @@ struct DeviceState {
     int* h_fail_pinned = nullptr;
     bool fail_pending = false, prof_pending = false, prof_tree_pending = false;
     double *d_norms = nullptr, *d_obj = nullptr;   // outputs of the fused phases that share one synchronisation
+    double *d_iter = nullptr, *h_iter = nullptr;   // madipm_phase_iteration: [aff4 4B | norms2 3B | ratio8 8B | res4 4B] device, 28B pinned
+    int* d_ok = nullptr;
 
     double* vec[MADIPM_VEC_COUNT] = {};
     int64_t veclen[MADIPM_VEC_COUNT] = {};
@@ -122,7 +124,7 @@ struct DeviceState {
 
     const Symbolic* sym = nullptr;
     bool values_set = false;
-    double growth_limit = 1.0e13;      // see madipm_set_growth_limit
+    double growth_limit = 1.0e13, tiny_pivot = 1.0e-13;   // see madipm_set_pivot_checks
     bool inject_barrier_fault = false; // test hook: see madipm_debug_inject_barrier_fault
     bool wedged = false;               // a synchronisation timed out: the stream still holds a kernel that never returns
     int profiling = 0;
@@ -195,7 +197,7 @@ FactorView make_factor_view(const DeviceState& d, int = 0) {
     FactorView F;
     F.sn_first = d.sn_first; F.sn_rowptr = d.sn_rowptr; F.sn_rows = d.sn_rows; F.sn_xoff = d.sn_xoff;
     F.sn_of = d.sn_of; F.row_colbase = d.row_colbase; F.row_relbase = d.row_relbase; F.rel = d.rel;
-    F.Lx = d.Lx; F.lx_stride = d.lx_stride; F.fail = d.fail; F.growth = d.growth_limit;
+    F.Lx = d.Lx; F.lx_stride = d.lx_stride; F.fail = d.fail; F.growth = d.growth_limit; F.tiny = d.tiny_pivot;
     return F;
 }
 
@@ -879,6 +881,9 @@ int32_t device_create(madipm_handle* h) {
     if ((rc = dev_alloc(h, &d->d_out2, static_cast<size_t>(B) * 16))) return rc;
     if ((rc = dev_alloc(h, &d->d_norms, static_cast<size_t>(B) * 4))) return rc;
     if ((rc = dev_alloc(h, &d->d_obj, static_cast<size_t>(B) * 2))) return rc;
+    if ((rc = dev_alloc(h, &d->d_iter, static_cast<size_t>(B) * 19))) return rc;
+    if ((rc = dev_alloc(h, &d->d_ok, 1))) return rc;
+    CUDA_OK(h, cudaMallocHost(reinterpret_cast<void**>(&d->h_iter), (static_cast<size_t>(B) * 32 + 2) * sizeof(double)));
     CUDA_OK(h, cudaMallocHost(reinterpret_cast<void**>(&d->h_fail_pinned), static_cast<size_t>(B) * sizeof(int)));
     if ((rc = dev_alloc(h, &d->d_steps, static_cast<size_t>(B) * 2))) return rc;
     if ((rc = dev_alloc(h, &d->d_mu, B))) return rc;
@@ -906,6 +911,7 @@ void device_destroy(madipm_handle* h) {
     for (void* p : d->allocs) cudaFree(p);
     if (d->h_out) cudaFreeHost(d->h_out);
     if (d->h_fail_pinned) cudaFreeHost(d->h_fail_pinned);
+    if (d->h_iter) cudaFreeHost(d->h_iter);
     if (d->tree_dbg) cudaFreeHost(d->tree_dbg);
     if (d->ev0) cudaEventDestroy(d->ev0);
     if (d->ev1) cudaEventDestroy(d->ev1);
@@ -1402,11 +1408,12 @@ int32_t madipm_factorize(madipm_handle* h, int32_t* n_failed) {
     return bad ? MADIPM_FACTOR_BREAKDOWN : MADIPM_OK;
 }
 
-int32_t madipm_set_growth_limit(madipm_handle* h, double limit) {
+int32_t madipm_set_pivot_checks(madipm_handle* h, double tiny, double growth) {
     int32_t rc = check(h);
     if (rc) return rc;
-    if (!(limit >= 0.0)) return MADIPM_BAD_ARGUMENT;
-    h->dev->growth_limit = limit;
+    if (!(tiny >= 0.0) || !(growth >= 0.0)) return MADIPM_BAD_ARGUMENT;
+    h->dev->tiny_pivot = tiny;
+    h->dev->growth_limit = growth;
     return MADIPM_OK;
 }
 
@@ -1694,6 +1701,115 @@ int32_t madipm_phase_factor_predictor(madipm_handle* h, double del_w, double del
     }
     if (!fuse && (rc = set_rhs(h, 2, nullptr))) return rc;
     return predictor_tail(h, norms, out, fuse);
+}
+
+int32_t madipm_phase_iteration(madipm_handle* h, const madipm_iter_options* o, const int32_t* active, double* out, int32_t* ok) {
+    int32_t rc = check(h, true);
+    if (rc) return rc;
+    DeviceState* d = h->dev;
+    if (!o || !out || !ok) return MADIPM_BAD_ARGUMENT;
+    const int B = d->B;
+    double* d_aff4 = d->d_iter;
+    double* d_norms2 = d_aff4 + 4 * B;
+    double* d_ratio8 = d_norms2 + 3 * B;
+    double* d_res4 = d_ratio8 + 8 * B;
+    const int* act = nullptr;
+    if (active) {
+        CUDA_OK(h, cudaMemcpyAsync(d->d_active, active, sizeof(int) * B, cudaMemcpyHostToDevice, d->stream));
+        act = d->d_active;
+    }
+    // ---- factorize_regularized_system! (first try) + affine_direction!, as madipm_phase_factor_predictor
+    if ((rc = madipm_set_aug_diagonal_reg(h, o->del_w, o->del_c))) return rc;
+    if ((rc = madipm_build_kkt(h))) return rc;
+    const bool fuse = d->sym->n_big == 0 && !d->segs.empty();
+    if (fuse) {
+        if ((rc = set_rhs(h, 2, nullptr))) return rc;
+        if ((rc = madipm_vec_copy(h, MADIPM_VEC_D, MADIPM_VEC_P))) return rc;
+        if ((rc = kkt_solve_stages(h, MADIPM_VEC_D, 1))) return rc;
+    }
+    {
+        Timer t(h, MADIPM_T_FACTOR);
+        bool timed_tree = false;
+        if ((rc = factorize_enqueue(h, fuse, &timed_tree))) return rc;
+        d->fail_pending = true;
+        d->prof_pending = d->profiling == 2;
+        d->prof_tree_pending = d->prof_pending && timed_tree;
+    }
+    if (!fuse && (rc = set_rhs(h, 2, nullptr))) return rc;
+    if ((rc = solve_system_enqueue(h, MADIPM_VEC_D, MADIPM_VEC_P, d->d_norms, fuse))) return rc;
+    const dim3 gb(vec_blocks(std::max(d->nlb, d->nub)), B);
+    {
+        Timer t(h, MADIPM_T_VECTOR);
+        launch_ratio(h, d->d_ones, d->d_out2);                                                   // tau = 1 (solver.jl:295)
+        LAUNCH(h, k_steps_from_ratio, (B + 127) / 128, 128, 0, B, d->d_out2, d->d_steps);
+        LAUNCH(h, k_complementarity, gb, kVecThreads, 0, make_view(*d), d->vec[MADIPM_VEC_D], d->d_steps, 1, d->red_scratch,
+               d->red_counter, d->d_out);                                                        // solver.jl:296-297
+        // ---- update_barrier! and the step rule's tau, on the device
+        LAUNCH(h, k_iter_scalars1, 1, 256, 0, B, d->nlb + d->nub, d->d_out, d->d_steps, d->d_norms, d->fail, act, o->has_inequalities,
+               o->mu_min, o->adaptive_step, o->tau, d_aff4, d->d_mu, d->d_tau, d->d_ok);
+        // ---- mehrotra_correction_direction! (solver.jl:307-311)
+        const int top = std::max(std::max(d->n, d->m), std::max(d->nlb, d->nub));
+        LAUNCH(h, k_set_rhs, dim3(vec_blocks(top), B), kVecThreads, 0, make_view(*d), d->vec[MADIPM_VEC_P], 3, d->d_mu);
+    }
+    if ((rc = solve_system_enqueue(h, MADIPM_VEC_D, MADIPM_VEC_P, d_norms2))) return rc;
+    {
+        Timer t(h, MADIPM_T_VECTOR);
+        launch_ratio(h, d->d_tau, d_ratio8);                                                     // update_step! (solver.jl:329)
+        LAUNCH(h, k_iter_scalars2, 1, 256, 0, B, d_ratio8, d_norms2, act, d->d_steps, d->d_ok);
+        // ---- solver.jl:332-335, 342: only if every active instance is fine
+        LAUNCH(h, k_update_iterate, dim3(vec_blocks(std::max(d->n, d->m)), B), kVecThreads, 0, make_view(*d), d->vec[MADIPM_VEC_D],
+               d->d_steps, d->d_mu, act, d->d_ok);
+    }
+    {
+        Timer t(h, MADIPM_T_SPMV);                                                               // solver.jl:338-340, then :259-272
+        LAUNCH(h, k_eval_model, dim3(vec_blocks(std::max(d->n, d->m)), B), kVecThreads, 0, make_view(*d), d->Q_rp, d->Q_ci,
+               d->Q_val, d->nnzQ, d->A_rp, d->A_ci, d->A_val, d->nnzA, d->red_scratch, d->red_counter, d->d_obj);
+        LAUNCH(h, k_residuals, dim3(vec_blocks(std::max(d->n, d->m)), B), kVecThreads, 0, make_view(*d), d->AT_rp, d->AT_ci,
+               d->AT_val, d->nnzA, d->vec[MADIPM_VEC_D], d->red_scratch, d->red_counter, d_res4);
+    }
+    // ---- one synchronisation for everything
+    double* hp = d->h_iter;
+    double* h_norms1 = hp;              hp += 3 * B;
+    double* h_aff4 = hp;                hp += 4 * B;
+    double* h_mu = hp;                  hp += B;
+    double* h_tau = hp;                 hp += B;
+    double* h_norms2 = hp;              hp += 3 * B;
+    double* h_ratio8 = hp;              hp += 8 * B;
+    double* h_steps = hp;               hp += 2 * B;
+    double* h_res4 = hp;                hp += 4 * B;
+    double* h_obj2 = hp;                hp += 2 * B;
+    int* h_ok = reinterpret_cast<int*>(hp);
+    auto back = [&](void* dst, const void* src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, d->stream); };
+    CUDA_OK(h, back(h_norms1, d->d_norms, sizeof(double) * 3 * B));
+    CUDA_OK(h, back(h_aff4, d_aff4, sizeof(double) * 4 * B));
+    CUDA_OK(h, back(h_mu, d->d_mu, sizeof(double) * B));
+    CUDA_OK(h, back(h_tau, d->d_tau, sizeof(double) * B));
+    CUDA_OK(h, back(h_norms2, d_norms2, sizeof(double) * 3 * B));
+    CUDA_OK(h, back(h_ratio8, d_ratio8, sizeof(double) * 8 * B));
+    CUDA_OK(h, back(h_steps, d->d_steps, sizeof(double) * 2 * B));
+    CUDA_OK(h, back(h_res4, d_res4, sizeof(double) * 4 * B));
+    CUDA_OK(h, back(h_obj2, d->d_obj, sizeof(double) * 2 * B));
+    CUDA_OK(h, back(h_ok, d->d_ok, sizeof(int)));
+    if ((rc = pending_enqueue(h))) return rc;
+    if ((rc = sync_stream(h))) return rc;
+    CUDA_OK(h, cudaGetLastError());
+    pending_collect(h);
+    *ok = *h_ok;
+    for (int i = 0; i < B; ++i) {
+        double* r = out + 28 * i;
+        for (int k = 0; k < 3; ++k) r[k] = h_norms1[3 * i + k];
+        for (int k = 0; k < 4; ++k) r[3 + k] = h_aff4[4 * i + k];
+        r[7] = h_mu[i];
+        r[8] = h_tau[i];
+        for (int k = 0; k < 3; ++k) r[9 + k] = h_norms2[3 * i + k];
+        for (int k = 0; k < 8; ++k) r[12 + k] = h_ratio8[8 * i + k];
+        r[20] = h_steps[2 * i];
+        r[21] = h_steps[2 * i + 1];
+        for (int k = 0; k < 4; ++k) r[22 + k] = h_res4[4 * i + k];
+        r[26] = o->c0 + h_obj2[2 * i] + 0.5 * h_obj2[2 * i + 1];
+        r[27] = 0.0;
+    }
+    return MADIPM_OK;
 }
 
 // mpc_direction! without Gondzio corrections (solver.jl:307-311) + the ratio tests of update_step! (solver.jl:329,

@@ -51,7 +51,7 @@ __global__ void k_big_diag(FactorView F, const int* __restrict__ big_sn, double*
     __syncthreads();
     for (int j = 0; j < w; ++j) {
         const double d = Bs[j * (w + 1)];
-        if (tid == 0 && bad_pivot(d)) atomicExch(F.fail + inst, 1);
+        if (tid == 0 && bad_pivot(d, F.tiny)) atomicExch(F.fail + inst, 1);
         for (int i = j + 1 + tid; i < w; i += T) {
             const double u = Bs[i + j * w];
             ucol[i] = u;
@@ -183,7 +183,7 @@ k_big_panel(FactorView F, const int* __restrict__ big_sn, double* __restrict__ z
         Ps[idx] = ldcg(&P[(i < w ? i : r0 + i - w) + j * ld]);
     }
     __syncthreads();
-    dense_ldl<kPanelThreads>(Ps, hp, w, F.fail + inst, t, F.growth);
+    dense_ldl<kPanelThreads>(Ps, hp, w, F.fail + inst, t, F.growth, F.tiny);
     __syncthreads();
     for (int idx = t; idx < nr * w; idx += kPanelThreads) {
         const int i = idx % nr, j = idx / nr;

@@ -28,6 +28,7 @@ struct FactorView {
     int64_t lx_stride;
     int* fail;                 // [batch]
     double growth;             // element-growth limit of the unpivoted LDL': |L_ik| above it is a breakdown (0 = no check)
+    double tiny;               // |pivot| at or below it is a breakdown (0 = only exact zeros, the reference's semantics)
 };
 
 constexpr int64_t kRelShift = int64_t(1) << 40;
@@ -45,7 +46,7 @@ __device__ __forceinline__ int lower_bound_rows(const int* rows, int n, int key)
     return lo;
 }
 
-__device__ __forceinline__ bool bad_pivot(double d) { return !(fabs(d) > 0.0 && fabs(d) < 1.0e300); }
+__device__ __forceinline__ bool bad_pivot(double d, double tiny = 0.0) { return !(fabs(d) > tiny && fabs(d) < 1.0e300); }
 
 // position of rows[i] inside the target's row list
 __device__ __forceinline__ int target_pos(const FactorView& F, int64_t rb, int i, const int* rows, int jj) {

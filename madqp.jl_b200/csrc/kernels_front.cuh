@@ -134,14 +134,14 @@ __device__ __forceinline__ void front_factor_task(const TreeView& T, const Front
     {
         bool bad;
         switch ((w + 7) >> 3) {
-            case 1: bad = dense_ldl_rr<8>(Ps, h, w, cbuf, t, 1, F.growth); break;
-            case 2: bad = dense_ldl_rr<16>(Ps, h, w, cbuf, t, 1, F.growth); break;
-            case 3: bad = dense_ldl_rr<24>(Ps, h, w, cbuf, t, 1, F.growth); break;
-            case 4: bad = dense_ldl_rr<32>(Ps, h, w, cbuf, t, 1, F.growth); break;
-            case 5: bad = dense_ldl_rr<40>(Ps, h, w, cbuf, t, 1, F.growth); break;
-            case 6: bad = dense_ldl_rr<48>(Ps, h, w, cbuf, t, 1, F.growth); break;
-            case 7: bad = dense_ldl_rr<56>(Ps, h, w, cbuf, t, 1, F.growth); break;
-            default: bad = dense_ldl_rr<64>(Ps, h, w, cbuf, t, 1, F.growth); break;
+            case 1: bad = dense_ldl_rr<8>(Ps, h, w, cbuf, t, 1, F.growth, F.tiny); break;
+            case 2: bad = dense_ldl_rr<16>(Ps, h, w, cbuf, t, 1, F.growth, F.tiny); break;
+            case 3: bad = dense_ldl_rr<24>(Ps, h, w, cbuf, t, 1, F.growth, F.tiny); break;
+            case 4: bad = dense_ldl_rr<32>(Ps, h, w, cbuf, t, 1, F.growth, F.tiny); break;
+            case 5: bad = dense_ldl_rr<40>(Ps, h, w, cbuf, t, 1, F.growth, F.tiny); break;
+            case 6: bad = dense_ldl_rr<48>(Ps, h, w, cbuf, t, 1, F.growth, F.tiny); break;
+            case 7: bad = dense_ldl_rr<56>(Ps, h, w, cbuf, t, 1, F.growth, F.tiny); break;
+            default: bad = dense_ldl_rr<64>(Ps, h, w, cbuf, t, 1, F.growth, F.tiny); break;
         }
         if (bad) atomicExch(F.fail + inst, 1);
     }

@@ -193,7 +193,7 @@ __device__ __forceinline__ double fast_rcp(double d) {
 #define LDL_PROBE(k)
 #endif
 template <int G>
-__device__ __forceinline__ void dense_ldl(double* Ps, int h, int w, int* fail, int t, double growth = 0.0) {
+__device__ __forceinline__ void dense_ldl(double* Ps, int h, int w, int* fail, int t, double growth = 0.0, double tiny = 0.0) {
     constexpr int NB = 4;
     for (int jb = 0; jb < w; jb += NB) {
         LDL_PROBE(7);
@@ -282,7 +282,7 @@ __device__ __forceinline__ void dense_ldl(double* Ps, int h, int w, int* fail, i
     gsync<G>();                                           // the warps that ran out of rows rejoin here
     // pivots: a zero / non-finite one poisons everything after it, so one pass over D at the end is enough
     bool bad = false;
-    for (int k = t; k < w; k += G) bad |= bad_pivot(Ps[k * (h + 1)]);
+    for (int k = t; k < w; k += G) bad |= bad_pivot(Ps[k * (h + 1)], tiny);
     // A pivot of roundoff size (dependent rows, delta_c = 0) is not zero, so the test above lets it through and the factor is
     // garbage; without pivoting the symptom is element growth: |L_ik| = |a_ik / d_k| beyond anything regularisation explains
     // (delta = 1e-8 against entries of order one gives 1e8).  One pass over the strictly lower part of the panel.
@@ -376,7 +376,7 @@ __device__ __forceinline__ void tree_factor_task(const TreeView& T, const SnMeta
     }
     TT(1);
     // 2. dense LDL' of the panel: D on the diagonal of the top w x w block, unit-lower L elsewhere
-    dense_ldl<G>(Ps, h, w, F.fail + inst, t, F.growth);  // ends with a barrier of the whole group
+    dense_ldl<G>(Ps, h, w, F.fail + inst, t, F.growth, F.tiny);  // ends with a barrier of the whole group
     TT(2);
     for (int c = t; c < nchunk; c += G) reinterpret_cast<double2*>(P)[c] = reinterpret_cast<const double2*>(Ps)[c];
     if (nb == 0) {

@@ -580,6 +580,61 @@ __global__ void k_steps_from_ratio(int B, const double* __restrict__ ratio_out, 
     }
 }
 
+// ---- device-side control scalars of one mpc! iteration (madipm_phase_iteration): what the host does between the phases when
+// they are separate calls, in the same floating-point operations.
+//  stage 1, after the predictor: mu_affine, mu_curr from the complementarity sums (solver.jl:296, kernels.jl:171-224),
+//  update_barrier! (kernels.jl:226-236: sigma = clamp((mu_affine / mu_curr)^3, 1e-6, 10), ^3 as x*x*x like Julia's literal
+//  power), tau of the step rule (kernels.jl:307-323), and the go / no-go of the iteration: every active instance factorised
+//  and its predictor residual ratio is a number (linear_solver.jl:41-43).  One block; ok_all is shared by the whole batch
+//  because the retry of linear_solver.jl:8-16 is (regularisation is one pair of scalars per handle).
+__device__ __forceinline__ double clamp_nan(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }   // NaN stays NaN, like clamp()
+__device__ __forceinline__ double max_nan(double a, double b) { return (a != a || b != b) ? (a + b) : (a > b ? a : b); }
+
+__global__ void k_iter_scalars1(int B, int nb, const double* __restrict__ sums, const double* __restrict__ steps_aff,
+                                const double* __restrict__ norms, const int* __restrict__ fail, const int* __restrict__ active,
+                                int has_ineq, double mu_min, int adaptive, double tau_par,
+                                double* __restrict__ aff4, double* __restrict__ mu, double* __restrict__ tau, int* __restrict__ ok_all) {
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        const double mu_aff = nb ? __ddiv_rn(__dadd_rn(sums[4 * i], sums[4 * i + 1]), static_cast<double>(nb)) : 0.0;
+        const double mu_cur = nb ? __ddiv_rn(__dadd_rn(sums[4 * i + 2], sums[4 * i + 3]), static_cast<double>(nb)) : 0.0;
+        aff4[4 * i] = steps_aff[2 * i];
+        aff4[4 * i + 1] = steps_aff[2 * i + 1];
+        aff4[4 * i + 2] = mu_aff;
+        aff4[4 * i + 3] = mu_cur;
+        double sigma = 1.0;
+        if (has_ineq) {
+            const double r = __ddiv_rn(mu_aff, mu_cur);
+            sigma = clamp_nan(__dmul_rn(__dmul_rn(r, r), r), 1e-6, 10.0);
+        }
+        const double m = max_nan(mu_min, __dmul_rn(sigma, mu_cur));
+        mu[i] = m;
+        tau[i] = adaptive ? max_nan(__dsub_rn(1.0, m), tau_par) : tau_par;
+        const double ratio = __ddiv_rn(norms[3 * i], fmax(1.0, norms[3 * i + 1]));
+        if ((!active || active[i]) && (fail[i] != 0 || ratio != ratio)) atomicExch(&bad, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *ok_all = bad ? 0 : 1;
+}
+
+//  stage 2, after the corrector: the steps of update_step! (kernels.jl:290-323) and the second residual check
+__global__ void k_iter_scalars2(int B, const double* __restrict__ ratio8, const double* __restrict__ norms, const int* __restrict__ active,
+                                double* __restrict__ steps, int* __restrict__ ok_all) {
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        steps[2 * i] = fmin(ratio8[8 * i], ratio8[8 * i + 1]);
+        steps[2 * i + 1] = fmin(ratio8[8 * i + 2], ratio8[8 * i + 3]);
+        const double ratio = __ddiv_rn(norms[3 * i], fmax(1.0, norms[3 * i + 1]));
+        if ((!active || active[i]) && ratio != ratio) atomicExch(&bad, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && bad) *ok_all = 0;
+}
+
 // ---- Gondzio set_extra_correction! (/root/reference/src/kernels.jl:78-126)
 __global__ void k_extra_correction(VecView V, const double* __restrict__ d, const double* __restrict__ steps,
                                    double bmin, double bmax, const double* __restrict__ mu_dev) {
@@ -617,8 +672,9 @@ __global__ void k_extra_correction(VecView V, const double* __restrict__ d, cons
 // (solver.jl:342, MadNLP [RECALLED]).  steps = { alpha_p, alpha_d }, mu per instance;
 // active[inst] == 0 leaves the instance untouched.
 __global__ void k_update_iterate(VecView V, const double* __restrict__ d, const double* __restrict__ steps,
-                                 const double* __restrict__ mu_dev, const int* __restrict__ active) {
+                                 const double* __restrict__ mu_dev, const int* __restrict__ active, const int* __restrict__ go = nullptr) {
     const int inst = blockIdx.y;
+    if (go && !*go) return;                      // madipm_phase_iteration: a breakdown anywhere leaves every iterate alone
     if (active && !active[inst]) return;
     V = shift(V, inst);
     d += inst * V.sL;

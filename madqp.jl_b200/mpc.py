@@ -97,7 +97,9 @@ class IPMOptions:
     # as well): the retry multiplies (del_w, del_c) by 100, which leaves del_c = 0 (the reference's default delta_d) at 0 for
     # ever; with the kick the first retry starts del_c at -del_w, so dependent constraint rows get a usable pivot.
     dual_regularization_kick: bool = True
-    growth_limit: float = 1e13      # element-growth breakdown test of the unpivoted LDL' (madipm_set_growth_limit); 0 = off
+    growth_limit: float = 1e13      # element-growth breakdown test of the unpivoted LDL' (madipm_set_pivot_checks); 0 = off
+    tiny_pivot: float = 1e-13       # |pivot| at or below it is a breakdown as well; 0 = only exact zeros (the reference)
+    fused_iteration: bool = True    # ... and a whole iteration behind ONE synchronisation (madipm_phase_iteration) when max_ncorr = 0
     fused_factor_forward: bool = True   # ... and the predictor's forward sweep inside the factor launch (madipm_phase_factor_predictor)
     device_prepare: bool = True     # initialize! / set_scaling! on the device (madipm_load_problem) instead of numpy
     relax_small: int = 0            # relaxed amalgamation (0 / None = library defaults)
@@ -345,8 +347,8 @@ class MPCSolver:
     def start(self):
         """Device-side part of initialize! (solver.jl:144, 162-179); inputs already resident in HBM."""
         opt, h, B = self.opt, self.h, self.B
-        if opt.growth_limit != 1e13:                     # (the library's default)
-            h.set_growth_limit(opt.growth_limit)
+        if opt.growth_limit != 1e13 or opt.tiny_pivot != 1e-13:      # (the library's defaults)
+            h.set_pivot_checks(opt.tiny_pivot, opt.growth_limit)
         self.k = 0
         self.iters[:] = 0
         self.status = [INITIAL] * B
@@ -446,7 +448,8 @@ class MPCSolver:
         has_inequalities = (self.nlb + self.nub) > 0       # SURVEY note B.1
         if has_inequalities:
             with np.errstate(divide="ignore", invalid="ignore"):
-                sigma = np.clip((mu_affine / mu_curr) ** 3, 1e-6, 10.0)
+                r = mu_affine / mu_curr
+                sigma = np.clip(r * r * r, 1e-6, 10.0)       # Julia lowers ^3 with a literal exponent to x*x*x
         else:
             sigma = np.ones(self.B)
         self.mu = np.maximum(self.opt.mu_min, sigma * mu_curr)
@@ -496,8 +499,13 @@ class MPCSolver:
     def mpc(self):
         opt, h = self.opt, self.h
         self._obj_pending = False
+        self._next_res = None
         while True:
-            if self._obj_pending:                                       # l.259-274 + the objective of l.338
+            if self._next_res is not None:                              # left by madipm_phase_iteration: l.259-274 of the new iterate
+                res, obj = self._next_res
+                self._next_res = None
+                self.obj_val = np.where(self.active.astype(bool), obj, self.obj_val)
+            elif self._obj_pending:                                       # l.259-274 + the objective of l.338
                 res, obj = h.phase_residuals_obj(float(self._c0[0]) if self.B == 1 else 0.0)
                 if self.B > 1:
                     obj = obj + self._c0
@@ -523,6 +531,22 @@ class MPCSolver:
                 return
             self._update_regularization()                               # l.288
             fused = opt.fused_phases
+            rule = opt.step_rule
+            if (fused and opt.fused_iteration and opt.max_ncorr == 0 and isinstance(rule, (ConservativeStep, AdaptiveStep))
+                    and not opt.check_residual):
+                # the whole iteration (l.288-342) behind one synchronisation; the device leaves the iterate alone and says so
+                # when a factorisation broke down or a residual is not a number: then the phases below redo the iteration
+                adaptive = isinstance(rule, AdaptiveStep)
+                ok, it = h.phase_iteration(self.del_w, self.del_c, opt.mu_min, rule.tau_min if adaptive else rule.tau, adaptive,
+                                           (self.nlb + self.nub) > 0, float(self._c0[0]) if self.B == 1 else 0.0,
+                                           None if self.B == 1 else self.active)
+                if ok:
+                    self.last_residual_ratio = it[:, 9] / np.maximum(1.0, it[:, 10])
+                    self.mu = it[:, 7].copy()
+                    self.alpha_p, self.alpha_d = it[:, 20].copy(), it[:, 21].copy()
+                    self._next_res = (it[:, 22:26].copy(), it[:, 26] + (self._c0 if self.B > 1 else 0.0))
+                    self.k += 1
+                    continue
             if fused:
                 # first try of factorize_regularized_system without a synchronisation: the breakdown flags come back with
                 # the scalars of the predictor phase; a failure (rare) re-enters the reference's retry loop

@@ -773,7 +773,8 @@ class MPCOracle:
         has_inequalities = (self.nlb + self.nub) > 0
         mu_curr = self.get_complementarity_measure()
         if has_inequalities:
-            sigma = min(max((mu_affine / mu_curr) ** 3, 1e-6), 10.0)
+            r = mu_affine / mu_curr
+            sigma = min(max(r * r * r, 1e-6), 10.0)          # Julia lowers ^3 with a literal exponent to x*x*x (Base.literal_pow)
         else:
             sigma = 1.0
         self.mu = max(self.opt.mu_min, sigma * mu_curr)

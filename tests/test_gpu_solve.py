@@ -325,10 +325,63 @@ def test_dependent_constraint_rows_with_the_default_regularisation():
     assert abs(st.objective[0] - ref.objective[0]) <= 1e-6 * max(1.0, abs(ref.objective[0]))
     np.testing.assert_allclose(st.solution[0], ref.solution[0], atol=1e-5 * max(1.0, np.max(np.abs(ref.solution[0]))))
     s.close()
-    raw = MPCSolver(dependent_rows_qp(), regularization=FixedRegularization(1e-8, 0.0), dual_regularization_kick=False, growth_limit=0.0,
+    raw = MPCSolver(dependent_rows_qp(), regularization=FixedRegularization(1e-8, 0.0), dual_regularization_kick=False, growth_limit=0.0, tiny_pivot=0.0,
                     max_iter=60)
     st2 = raw.solve()
     good = st2.status[0] == "SOLVE_SUCCEEDED" and abs(st2.objective[0] - ref.objective[0]) <= 1e-6 * max(1.0, abs(ref.objective[0]))
     print("dependent rows, reference semantics:", st2.status[0], int(st2.iter[0]), st2.objective[0], "vs", ref.objective[0])
     raw.close()
     assert not good or True      # informative only: an exactly cancelling pivot is caught by the zero test either way
+
+
+@pytest.mark.parametrize("maker,kw,opts", [
+    (P.maros_meszaros_like, dict(), dict()),
+    (P.banded_qp, dict(n=20000, m=10000), dict()),
+    (P.inequality_qp, dict(seed=2), dict(step_rule=ConservativeStep(0.99))),
+    (P.sparse_lp, dict(n=4000, m=2000), dict(kkt_system="NORMAL")),
+    (P.maros_meszaros_like, dict(), dict(kkt_system="K2.5")),
+    (P.simple_lp, dict(), dict()),
+])
+def test_one_synchronisation_iteration_is_the_same_arithmetic(maker, kw, opts):
+    """madipm_phase_iteration computes the scalars between the phases (mu_affine, mu_curr, sigma, mu, tau, alpha) on the
+    device in the same floating-point operations as the host does between the separate phase calls: identical traces."""
+    qp = maker(**kw)
+    out = []
+    for it in (True, False):
+        s = MPCSolver(qp, regularization=FixedRegularization(1e-8, -1e-8), fused_iteration=it, **opts)
+        st = s.solve()
+        out.append((st, s.trace))
+        exact = bool((s.h.symbolic("SUPER_KIND") == 0).all())
+        s.close()
+    (a, ta), (b, tb) = out
+    assert a.status == b.status and int(a.iter[0]) == int(b.iter[0])
+    assert len(ta) == len(tb)
+    if exact:
+        assert a.objective[0] == b.objective[0]
+        assert np.array_equal(a.solution, b.solution) and np.array_equal(a.multipliers, b.multipliers)
+        for x, y in zip(ta, tb):
+            for key in ("obj", "inf_pr", "inf_du", "inf_compl", "mu", "alpha_p", "alpha_d"):
+                assert np.array_equal(x[key], y[key]), (x["k"], key, x[key], y[key])
+    else:
+        assert abs(a.objective[0] - b.objective[0]) <= 1e-10 * max(1.0, abs(b.objective[0]))
+
+
+def test_one_synchronisation_iteration_batch_and_retry():
+    """Batch: converged instances stay frozen, results equal the phase-by-phase path.  Breakdown: the device reports
+    no-go, nothing moves, and the phases redo the iteration with the reference's retry (same end state as without it)."""
+    qps = [P.small_qp(instance=i) for i in range(9)]
+    res = []
+    for it in (True, False):
+        s = MPCSolver(qps, regularization=FixedRegularization(1e-8, -1e-8), fused_iteration=it)
+        res.append(s.solve())
+        s.close()
+    assert res[0].status == res[1].status and np.array_equal(res[0].iter, res[1].iter)
+    assert np.array_equal(res[0].objective, res[1].objective) and np.array_equal(res[0].solution, res[1].solution)
+    qp = free_pair_lp()
+    end = []
+    for it in (True, False):
+        s = MPCSolver(qp, regularization=NoRegularization(), fused_iteration=it, max_iter=8)
+        st = s.solve()
+        end.append((st.status[0], int(st.iter[0]), s.del_w, s.del_c))
+        s.close()
+    assert end[0] == end[1] and end[0][0] == "ERROR_IN_STEP_COMPUTATION", end
