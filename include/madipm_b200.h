@@ -214,7 +214,8 @@ int32_t madipm_is_factorized(madipm_handle* h, int32_t* flags);
  * garbage factor.  Two more breakdown tests catch it: |pivot| <= tiny (default 1e-13 in the scaled problem's units: the
  * regularised pivots of an interior-point KKT matrix are 1e-8 and up, cancellation leaves 1e-16 times the operands), and
  * element growth, a factor entry |L_ik| above `growth` (default 1e13: regularisation 1e-8 against entries of order one
- * explains 1e8).  0 switches a test off; (0, 0) is the reference's exact semantics. */
+ * explains 1e8).  0 switches a test off; (0, 0) is the reference's exact semantics and the default for the normal
+ * equations, whose pivots and factor entries legitimately span many orders of magnitude (Sigma does). */
 int32_t madipm_set_pivot_checks(madipm_handle* h, double tiny, double growth);
 /* inertia of the last factorisation of instance `inst`: signs of D */
 int32_t madipm_inertia(madipm_handle* h, int32_t inst, int64_t* n_pos, int64_t* n_zero, int64_t* n_neg);

@@ -742,6 +742,7 @@ int32_t device_create(madipm_handle* h) {
     CUDA_OK(h, cudaMemsetAsync(d->abort_flag, 0, sizeof(unsigned), d->stream));
     CUDA_OK(h, cudaHostAlloc(reinterpret_cast<void**>(&d->tree_dbg), sizeof(TreeDebug), cudaHostAllocMapped | cudaHostAllocPortable));
     std::memset(d->tree_dbg, 0, sizeof(TreeDebug));
+    if (d->kind != 0) d->tiny_pivot = d->growth_limit = 0.0;   // normal equations: pivots and factor entries legitimately span 1e-12 .. 1e12 (Sigma does)
     if (const char* e = std::getenv("MADIPM_SYNC_TIMEOUT_S")) d->sync_timeout_s = std::max(0.0, std::atof(e));
     if (const char* e = std::getenv("MADIPM_BARRIER_TIMEOUT_MS")) d->spin_budget_ns = std::max(1ll, std::atoll(e)) * 1000000ll;
     d->num_sms = prop.multiProcessorCount;

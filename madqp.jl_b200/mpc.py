@@ -347,7 +347,7 @@ class MPCSolver:
     def start(self):
         """Device-side part of initialize! (solver.jl:144, 162-179); inputs already resident in HBM."""
         opt, h, B = self.opt, self.h, self.B
-        if opt.growth_limit != 1e13 or opt.tiny_pivot != 1e-13:      # (the library's defaults)
+        if (opt.growth_limit != 1e13 or opt.tiny_pivot != 1e-13) and opt.kkt_system != "NORMAL":   # (the library's defaults)
             h.set_pivot_checks(opt.tiny_pivot, opt.growth_limit)
         self.k = 0
         self.iters[:] = 0
