@@ -40,6 +40,7 @@ METRIC, UNIT = "ipm_iters_per_sec", "iter/s"
 
 _T0 = time.perf_counter()
 _PHASE = ["start"]
+_HANDLES = []          # handles of the live solvers: the guard asks them what the device was doing
 
 
 def progress(phase):
@@ -58,9 +59,17 @@ def start_guard(limit_s, args):
     faulthandler.dump_traceback_later(max(1.0, limit_s - 2.0), exit=False, file=sys.stderr)
 
     def fire():
+        device = []
+        for hd in _HANDLES:
+            try:
+                device.append(hd.debug_describe())
+            except Exception as e:  # noqa: BLE001
+                device.append(repr(e))
         line = dict(metric=METRIC, value=None, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                     error=f"bench.py guard: still in phase '{_PHASE[0]}' after {limit_s:.0f} s", phase=_PHASE[0],
-                    impl=args.impl)
+                    impl=args.impl, device_state=device, rank=int(os.environ.get("RANK", "0")))
+        sys.stderr.write(json.dumps(line) + "\n")
+        sys.stderr.flush()
         try:
             emit(line)
         finally:
@@ -303,6 +312,7 @@ def run_c5(args, world, rank, local, barrier, anomalies):
     progress(f"C5: generate instances [{lo}, {hi}) of {n_items}")
     qps = [problems.small_qp(instance=i) for i in range(lo, hi)]
     solver = MPCSolver(qps, kkt_system="K2", device=local, **solver_options())
+    _HANDLES.append(solver.h)
     solver.keep_snapshot = True
     for k in range(2):
         progress(f"C5: warm-up solve {k + 1}")
@@ -322,6 +332,7 @@ def run_c5(args, world, rank, local, barrier, anomalies):
                max_iterations=float(np.max(table[:, 1])), mean_iterations=float(np.mean(table[:, 1])), converged=ok,
                gathered=int(table.shape[0]), collective="one all_gather of the status records" if world > 1 else "none (1 rank)",
                gpu_launches=int(res["launches"]))
+    _HANDLES.remove(solver.h)
     solver.close()
     return out
 
@@ -358,6 +369,7 @@ def run_ours(args):
     solver = MPCSolver(qps if len(qps) > 1 else qps[0], kkt_system=kkt, device=local, **solver_options())
     solver.keep_snapshot = True
     h = solver.h
+    _HANDLES.append(h)
     info = solver.info
     c_doubles = int(solver.h.symbolic("SUPER_COFF")[-1])     # packed contribution blocks of the small supernodes
     cv_doubles = int(len(solver.h.symbolic("SUPER_ROWS")))   # contribution vectors of the forward sweep (one entry per row-list entry)
@@ -406,6 +418,7 @@ def run_ours(args):
         gpu_solution = dict(status=st.status[0], iterations=int(st.iter[0]), objective=float(st.objective[0]))
     solver_h2d, solver_d2h, analysis_s = int(solver.h2d_bytes), int(solver.d2h_bytes), solver.analysis_time
     first_qp = qps[0]
+    _HANDLES.remove(h)
     solver.close()
 
     # ---- the north star's sharded workload (C5) beside the headline, at every N
@@ -528,8 +541,11 @@ def main():
     ap.add_argument("--c5-steps", type=int, default=3)
     ap.add_argument("--cpu-iters", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--guard-s", type=float, default=1500.0, help="wall-clock limit after which an error line is printed (0 = off)")
+    ap.add_argument("--guard-s", type=float, default=None,
+                    help="wall-clock limit after which an error line is printed (0 = off; default 480 s for the GPU arm, 1500 s for --impl reference)")
     args = ap.parse_args()
+    if args.guard_s is None:
+        args.guard_s = 1500.0 if args.impl == "reference" else 480.0
     start_guard(args.guard_s, args)
     if args.impl == "reference":
         run_reference(args)

@@ -333,6 +333,9 @@ int32_t madipm_profile_read(madipm_handle* h, double* ms, int64_t* calls, int32_
  * reach its target, so the guards above can be exercised on purpose (tests/test_gpu_guards.py). */
 int32_t madipm_debug_barrier_state(madipm_handle* h, int64_t* out8);
 int32_t madipm_debug_inject_barrier_fault(madipm_handle* h);
+/* One line of text: the barrier record, the kernel launched last, the launch count and the last height a tree kernel
+ * started.  Makes no CUDA call and takes no lock, so a watchdog thread may call it while the owning thread is blocked. */
+const char* madipm_debug_describe(madipm_handle* h);
 
 /* ---- fused iteration phases: one host synchronisation each ------------------------------------------ */
 /* The reference synchronises once per reduction (~22 per iteration); the separate entry points above once per returned

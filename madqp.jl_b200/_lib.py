@@ -143,6 +143,7 @@ _SIGNATURES = {
     "madipm_profile_read": ([_PD, _P64, C.c_int32], C.c_int32),
     "madipm_debug_barrier_state": ([_P64], C.c_int32),
     "madipm_debug_inject_barrier_fault": ([], C.c_int32),
+    "madipm_debug_describe": ([], C.c_char_p),
     "madipm_phase_residuals_obj": ([C.c_double, _PD, _PD], C.c_int32),
     "madipm_phase_predictor": ([_PD, _PD], C.c_int32),
     "madipm_phase_factor_predictor": ([C.c_double, C.c_double, _PD, _PD], C.c_int32),
@@ -521,6 +522,10 @@ class Handle:
         out = np.zeros(8, dtype=np.int64)
         self._check(self.lib.madipm_debug_barrier_state(self._h, _p64(out)))
         return dict(zip("aborted kernel op height block grid seen target".split(), (int(v) for v in out)))
+
+    def debug_describe(self):
+        """Host-only snapshot (no CUDA call): safe from a watchdog thread while the owning thread is blocked."""
+        return self.lib.madipm_debug_describe(self._h).decode()
 
     def debug_inject_barrier_fault(self):
         self._check(self.lib.madipm_debug_inject_barrier_fault(self._h))

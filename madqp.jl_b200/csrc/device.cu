@@ -148,6 +148,7 @@ namespace {
     do {                                                                                   \
         kernel<<<grid, block, smem, (h)->dev->stream>>>(__VA_ARGS__);                      \
         ++(h)->launches;                                                                   \
+        (h)->last_launch = #kernel;                                                        \
     } while (0)
 
 template <class T>
@@ -273,7 +274,11 @@ int32_t sync_stream(madipm_handle* h) {
                 std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > d->sync_timeout_s) {
                 char buf[128];
                 std::snprintf(buf, sizeof(buf), "stream still busy after %.0f s (MADIPM_SYNC_TIMEOUT_S); ", d->sync_timeout_s);
-                h->error = std::string(buf) + describe_tree_debug(d);
+                char prog[160];
+                const unsigned pg = d->tree_dbg ? d->tree_dbg->progress : 0u;
+                std::snprintf(prog, sizeof(prog), "; last kernel launched: %s (launch %lld); last tree progress mark: kernel %u op %u height %u",
+                              h->last_launch, static_cast<long long>(h->launches), pg >> 24, (pg >> 16) & 0xffu, pg & 0xffffu);
+                h->error = std::string(buf) + describe_tree_debug(d) + prog;
                 d->wedged = true;
                 return MADIPM_INTERNAL;
             }
@@ -464,6 +469,7 @@ int32_t launch_tree(madipm_handle* h, const DeviceState::TreeSeg& sg) {
         CUDA_OK(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_tree<OP>), dim3(sg.grid[OP]), dim3(kTreeThreads), args,
                                                d->smem_tree, d->stream));
         ++h->launches;
+        h->last_launch = "k_tree (cooperative)";
         return MADIPM_OK;
     };
     auto top = [&]() -> int32_t {
@@ -476,12 +482,14 @@ int32_t launch_tree(madipm_handle* h, const DeviceState::TreeSeg& sg) {
             CUDA_OK(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_front<OP == 3 ? 3 : 0>), dim3(sg.grid_top), dim3(kFrontThreads),
                                                    fargs, d->smem_front, d->stream));
             ++h->launches;
+            h->last_launch = "k_front (cooperative)";
             return MADIPM_OK;
         }
         void* args[] = {&T, &b, &e, &step};
         CUDA_OK(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_tree_top<OP>), dim3(sg.grid_top), dim3(kTopThreads), args,
                                                d->smem_tree, d->stream));
         ++h->launches;
+        h->last_launch = "k_tree_top (cooperative)";
         return MADIPM_OK;
     };
     int32_t rc;
@@ -936,6 +944,7 @@ static int32_t upload_values(madipm_handle* h, const double* hess_V, const doubl
     DeviceState* d = h->dev;
     const int B = d->B;
     if ((d->nnzh > 0 && !hess_V) || (d->nnzj > 0 && !jac_V)) return MADIPM_BAD_ARGUMENT;
+    { int32_t rc_ = sync_stream(h); if (rc_) return rc_; }      // pageable sources below: wait for the stream under the guard
     if (d->nnzh) CUDA_OK(h, cudaMemcpyAsync(d->hessV, hess_V, sizeof(double) * B * d->nnzh, cudaMemcpyHostToDevice, d->stream));
     if (d->nnzJfull > d->nnzj)
         LAUNCH(h, k_fill, dim3(vec_blocks(d->nnzJfull), B), kVecThreads, 0, d->nnzJfull, d->jacV, d->nnzJfull, -1.0);
@@ -996,6 +1005,7 @@ int32_t madipm_load_problem(madipm_handle* h, const double* x0, const double* lv
     if (!opt || !obj_scale || !norm_b || (nx > 0 && (!x0 || !lvar || !uvar || !c)) || (m > 0 && (!y0 || !lcon || !ucon)))
         return MADIPM_BAD_ARGUMENT;
     Timer t(h, MADIPM_T_ASSEMBLY);
+    if ((rc = sync_stream(h))) return rc;                   // pageable sources below: wait for the stream under the guard
     auto up_n = [&](int vec, const double* src) {           // [B][nx] host -> the first nx entries of an n_tot vector
         return nx == 0 ? cudaSuccess
                        : cudaMemcpy2DAsync(d->vec[vec], sizeof(double) * n, src, sizeof(double) * nx, sizeof(double) * nx, B,
@@ -1085,6 +1095,7 @@ int32_t madipm_vec_set(madipm_handle* h, int32_t vec, const double* host) {
     if (vec < 0 || vec >= MADIPM_VEC_COUNT || !host) return MADIPM_BAD_ARGUMENT;
     DeviceState* d = h->dev;
     if (vec == MADIPM_VEC_KKT_NZVAL) { d->image_valid = false; d->nzval_diag_stale = false; }   // the caller owns the KKT values now: assemble from nzval
+    if ((rc = sync_stream(h))) return rc;      // (a copy from pageable memory synchronises the stream in the driver: do it under the guard)
     CUDA_OK(h, cudaMemcpyAsync(d->vec[vec], host, sizeof(double) * d->B * d->veclen[vec], cudaMemcpyHostToDevice, d->stream));
     return MADIPM_OK;
 }
@@ -1095,6 +1106,7 @@ int32_t madipm_vec_get(madipm_handle* h, int32_t vec, double* host) {
     if (vec < 0 || vec >= MADIPM_VEC_COUNT || !host) return MADIPM_BAD_ARGUMENT;
     DeviceState* d = h->dev;
     if (vec == MADIPM_VEC_KKT_NZVAL && (rc = refresh_nzval_diag(h))) return rc;
+    if ((rc = sync_stream(h))) return rc;      // a copy to pageable memory blocks in the driver: wait for the stream under the guard first
     CUDA_OK(h, cudaMemcpyAsync(host, d->vec[vec], sizeof(double) * d->B * d->veclen[vec], cudaMemcpyDeviceToHost, d->stream));
     { int32_t rc_ = sync_stream(h); if (rc_) return rc_; }
     return MADIPM_OK;
@@ -1139,6 +1151,16 @@ int32_t madipm_debug_barrier_state(madipm_handle* h, int64_t* out8) {
     const int64_t v[8] = {g.aborted, g.kernel, g.op, g.phase, g.block, g.grid, g.seen, g.target};
     for (int k = 0; k < 8; ++k) out8[k] = v[k];
     return MADIPM_OK;
+}
+
+const char* madipm_debug_describe(madipm_handle* h) {
+    if (!h) return "";
+    char buf[256];
+    const unsigned pg = (h->dev && h->dev->tree_dbg) ? h->dev->tree_dbg->progress : 0u;
+    std::snprintf(buf, sizeof(buf), "last kernel launched: %s (launch %lld); last tree progress mark: kernel %u op %u height %u; wedged %d; ",
+                  h->last_launch, static_cast<long long>(h->launches), pg >> 24, (pg >> 16) & 0xffu, pg & 0xffffu, (h->dev && h->dev->wedged) ? 1 : 0);
+    h->describe = std::string(buf) + (h->dev ? describe_tree_debug(h->dev) : std::string("no device state"));
+    return h->describe.c_str();
 }
 
 int32_t madipm_debug_inject_barrier_fault(madipm_handle* h) {
@@ -1193,6 +1215,7 @@ int32_t madipm_vec_get_range(madipm_handle* h, int32_t vec, int64_t off, int64_t
     DeviceState* d = h->dev;
     if (!host || !range_ok(d, vec, off, len)) return MADIPM_BAD_ARGUMENT;
     if (vec == MADIPM_VEC_KKT_NZVAL && (rc = refresh_nzval_diag(h))) return rc;
+    if ((rc = sync_stream(h))) return rc;
     if (len > 0)
         CUDA_OK(h, cudaMemcpy2DAsync(host, sizeof(double) * len, d->vec[vec] + off, sizeof(double) * d->veclen[vec], sizeof(double) * len,
                                      d->B, cudaMemcpyDeviceToHost, d->stream));
@@ -1205,6 +1228,7 @@ int32_t madipm_vec_set_range(madipm_handle* h, int32_t vec, int64_t off, int64_t
     DeviceState* d = h->dev;
     if (!host || !range_ok(d, vec, off, len)) return MADIPM_BAD_ARGUMENT;
     if (vec == MADIPM_VEC_KKT_NZVAL) { d->image_valid = false; d->nzval_diag_stale = false; }
+    if ((rc = sync_stream(h))) return rc;
     if (len > 0)
         CUDA_OK(h, cudaMemcpy2DAsync(d->vec[vec] + off, sizeof(double) * d->veclen[vec], host, sizeof(double) * len, sizeof(double) * len,
                                      d->B, cudaMemcpyHostToDevice, d->stream));
@@ -1389,6 +1413,7 @@ int32_t madipm_factorize(madipm_handle* h, int32_t* n_failed) {
             return MADIPM_OK;
         }
         d->fail_pending = d->prof_pending = d->prof_tree_pending = false;
+        { int32_t rc_ = sync_stream(h); if (rc_) return rc_; }      // (pageable destination: guard first)
         CUDA_OK(h, cudaMemcpyAsync(d->h_fail.data(), d->fail, sizeof(int) * B, cudaMemcpyDeviceToHost, d->stream));
         { int32_t rc_ = sync_stream(h); if (rc_) return rc_; }
         if (light) {
@@ -1439,6 +1464,7 @@ int32_t madipm_inertia(madipm_handle* h, int32_t inst, int64_t* n_pos, int64_t* 
     CUDA_OK(h, cudaMemsetAsync(d->d_inertia, 0, sizeof(unsigned long long) * 3 * d->B, d->stream));
     LAUNCH(h, k_inertia, dim3(vec_blocks(d->N), d->B), kVecThreads, 0, d->N, d->diag_pos, d->Lx, d->lx_stride, d->d_inertia);
     std::vector<unsigned long long> out(3 * d->B);
+    { int32_t rc_ = sync_stream(h); if (rc_) return rc_; }
     CUDA_OK(h, cudaMemcpyAsync(out.data(), d->d_inertia, sizeof(unsigned long long) * 3 * d->B, cudaMemcpyDeviceToHost, d->stream));
     { int32_t rc_ = sync_stream(h); if (rc_) return rc_; }
     if (n_pos) *n_pos = out[inst * 3];

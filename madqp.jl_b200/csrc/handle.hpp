@@ -22,6 +22,8 @@ struct madipm_handle {
     std::vector<int32_t> ind_lb, ind_ub;   // 0-based
     madipm::DeviceState* dev = nullptr;
     int64_t launches = 0;
+    const char* last_launch = "";
+    std::string describe;                  // buffer of madipm_debug_describe          // name of the kernel launched last (diagnostics of a synchronisation timeout)
 };
 
 namespace madipm {

@@ -214,6 +214,7 @@ k_front(TreeView T, FrontLayout Lo, int ph_begin, int ph_end) {
     double* smem = reinterpret_cast<double*>(tree_smem2);
     unsigned target = 0;
     for (int ph = ph_begin; ph < ph_end; ++ph) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<volatile unsigned*>(&T.dbg->progress) = (2u << 24) | (OP << 16) | ph;
         const int first = __ldg(T.phase_cls + ph * 5);
         const int n = __ldg(T.phase_cls + ph * 5 + 4) - first;
         const int64_t total = static_cast<int64_t>(n) * T.B;

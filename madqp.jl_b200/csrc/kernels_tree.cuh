@@ -76,6 +76,7 @@ struct TreeDebug {
     unsigned block, grid;
     unsigned seen, target;       // counter value last read, value waited for
     unsigned long long waited_ns;
+    unsigned progress;           // (kernel << 24) | (op << 16) | height: written by block 0 at the start of every height
 };
 
 struct TreeView {
@@ -757,6 +758,7 @@ k_tree(TreeView T, int ph_begin, int ph_end, int step) {
     double* smem = reinterpret_cast<double*>(tree_smem2);
     unsigned target = 0;
     for (int ph = ph_begin; ph != ph_end; ph += step) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<volatile unsigned*>(&T.dbg->progress) = (0u << 24) | (OP << 16) | ph;
         run_class<OP, 256, 0>(T, smem, ph);
         run_class<OP, 128, 1>(T, smem, ph);
         run_class<OP, 64, 2>(T, smem, ph);
@@ -774,6 +776,7 @@ k_tree_top(TreeView T, int ph_begin, int ph_end, int step) {
     double* smem = reinterpret_cast<double*>(tree_smem2);
     unsigned target = 0;
     for (int ph = ph_begin; ph != ph_end; ph += step) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<volatile unsigned*>(&T.dbg->progress) = (1u << 24) | (OP << 16) | ph;
         const int first = __ldg(T.phase_cls + ph * 5);
         const int n = __ldg(T.phase_cls + ph * 5 + 4) - first;
         const int64_t total = static_cast<int64_t>(n) * T.B;
