@@ -543,14 +543,68 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--guard-s", type=float, default=None,
                     help="wall-clock limit after which an error line is printed (0 = off; default 480 s for the GPU arm, 1500 s for --impl reference)")
+    ap.add_argument("--child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.guard_s is None:
-        args.guard_s = 1500.0 if args.impl == "reference" else 480.0
+        args.guard_s = 1500.0 if args.impl == "reference" else (300.0 if args.workload in ("C3", "C3-K2.5", "C1", "C5") else 900.0)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "ours" and world == 1 and not args.child:
+        return supervise(args)
     start_guard(args.guard_s, args)
+    if os.environ.get("BENCH_TEST_HANG_ATTEMPT") and os.environ.get("BENCH_TEST_HANG_ATTEMPT") == os.environ.get("BENCH_ATTEMPT"):
+        progress("test hook: this attempt pretends to hang")          # exercises the supervisor (tests/test_gpu_guards.py)
+        signal_free_sleep()
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+
+
+def signal_free_sleep():
+    import faulthandler
+    faulthandler.cancel_dump_traceback_later()
+    while True:
+        time.sleep(3600)
+
+
+def supervise(args):
+    """Single-GPU runs go through a supervisor: the benchmark proper runs in a child process under a wall-clock limit, and an
+    attempt that hangs or fails is killed (which tears its CUDA context down) and repeated ONCE.  The line of the successful
+    attempt carries `attempts` and what the failed one reported.  Why: twice (round 1's driver run, one 2-GPU run of round 2)
+    a process sat in its first solves with the GPU busy and never came back; 60+ other processes on the same builds did not,
+    and the cause has not been found.  A retry is a workaround and is reported as such -- it is not a fix."""
+    failed = []
+    for attempt in (1, 2):
+        cmd = [sys.executable, os.path.abspath(__file__)] + [a for a in sys.argv[1:] if a != "--child"] + ["--child"]
+        progress(f"supervisor: attempt {attempt}")
+        proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=None, text=True, start_new_session=True,
+                                env=dict(os.environ, BENCH_ATTEMPT=str(attempt)))
+        try:
+            out, _ = proc.communicate(timeout=args.guard_s + 30.0)
+        except subprocess.TimeoutExpired:
+            try:
+                os.killpg(proc.pid, 9)
+            except OSError:
+                proc.kill()
+            out, _ = proc.communicate()
+            out = (out or "") + json.dumps(dict(error=f"attempt {attempt}: no result after {args.guard_s + 30.0:.0f} s, killed")) + "\n"
+        line = None
+        for l in (out or "").splitlines():
+            if l.startswith("{"):
+                try:
+                    line = json.loads(l)
+                except ValueError:
+                    pass
+        if line is not None and "error" not in line and proc.returncode == 0:
+            line["attempts"] = attempt
+            line["failed_attempts"] = failed
+            emit(line)
+            return
+        failed.append(dict(attempt=attempt, returncode=proc.returncode, line=line))
+        progress(f"supervisor: attempt {attempt} failed: rc={proc.returncode} {json.dumps(line)[:400] if line else 'no line'}")
+    emit(dict(metric=METRIC, value=None, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+              error="both attempts failed", failed_attempts=failed))
+    sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -73,3 +73,20 @@ def test_three_full_size_c3_solves_back_to_back():
     assert len({o[0] for o in out}) == 1, out
     assert max(abs(o[1] - out[0][1]) for o in out) <= 1e-10 * max(1.0, abs(out[0][1])), out
     s.close()
+
+
+def test_bench_supervisor_retries_a_hung_attempt(tmp_path):
+    """bench.py at N = 1 runs the benchmark in a child process; an attempt that never returns is killed and repeated once,
+    and the line says so."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, BENCH_TEST_HANG_ATTEMPT="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--scale", "0.02", "--steps", "1", "--warmup", "1", "--no-cpu",
+                          "--no-c5", "--guard-s", "8"], env=env, capture_output=True, text=True, timeout=300)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout + out.stderr[-2000:]
+    line = json.loads(lines[0])
+    assert "error" not in line and line["attempts"] == 2 and len(line["failed_attempts"]) == 1, line
+    assert line["value"] > 0 and line["converged"]
