@@ -307,6 +307,14 @@ int32_t madipm_adjust_boundary(madipm_handle* h, const double* mu);
 int32_t madipm_snapshot_inputs(madipm_handle* h);
 int32_t madipm_restore_inputs(madipm_handle* h);
 
+/* ---- page-locked host memory -------------------------------------------------------------------------------
+ * Host arrays stay the caller's (header, "Ownership"), and any host memory works.  Copies from / to PAGE-LOCKED memory are
+ * the fast and truly asynchronous ones (a copy from pageable memory synchronises the stream and goes through a staging
+ * buffer at a fraction of the PCIe rate), so a caller that re-sends inputs every solve keeps them in memory from this
+ * allocator (the Julia side: the buffers behind the model's x0, lvar, ..., the Jacobian / Hessian values).  Needs no handle. */
+int32_t madipm_pinned_alloc(int64_t bytes, void** ptr);
+int32_t madipm_pinned_free(void* ptr);
+
 /* ---- measurement hooks -------------------------------------------------------------------- */
 /* number of kernel launches issued by this handle since creation */
 int64_t madipm_launch_count(const madipm_handle* h);

@@ -136,6 +136,8 @@ _SIGNATURES = {
     "madipm_vec_norm_inf_range": ([C.c_int32, C.c_int64, C.c_int64, _PD], C.c_int32),
     "madipm_vec_axpy_at": ([C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_double], C.c_int32),
     "madipm_adjust_boundary": ([_PD], C.c_int32),
+    "madipm_pinned_alloc": (None, [C.c_int64, C.POINTER(C.c_void_p)], C.c_int32),
+    "madipm_pinned_free": (None, [C.c_void_p], C.c_int32),
     "madipm_snapshot_inputs": ([], C.c_int32),
     "madipm_restore_inputs": ([], C.c_int32),
     "madipm_launch_count": ([], C.c_int64),
@@ -178,6 +180,30 @@ def load():
             fn.argtypes, fn.restype = [_H] + sig[0], sig[1]
     _lib = lib
     return lib
+
+
+class PinnedArray:
+    """A float64 numpy array over page-locked host memory (madipm_pinned_alloc).  `.a` is the array; freed with the object.
+    Falls back to ordinary memory when no CUDA device is present (host-only use of the package)."""
+
+    def __init__(self, shape):
+        lib = load()
+        n = int(np.prod(shape))
+        self._ptr = C.c_void_p()
+        self.pinned = lib.madipm_pinned_alloc(8 * n, C.byref(self._ptr)) == OK and bool(self._ptr.value)
+        if self.pinned:
+            buf = (C.c_double * max(n, 1)).from_address(self._ptr.value)
+            self.a = np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape)
+        else:
+            self.a = np.zeros(shape)
+
+    def __del__(self):
+        try:
+            if getattr(self, "pinned", False) and self._ptr.value:
+                load().madipm_pinned_free(self._ptr)
+                self._ptr = C.c_void_p()
+        except Exception:  # noqa: BLE001
+            pass
 
 
 def _pd(a):
@@ -295,9 +321,14 @@ class Handle:
         assert a.size == self.batch * self.vec_len(vec), (vec, a.size)
         self._check(self.lib.madipm_vec_set(self._h, VEC[vec], _pd(a)))
 
-    def vec_get(self, vec):
-        out = np.zeros(self.batch * self.vec_len(vec))
+    def vec_get(self, vec, out=None):
+        """out: a preallocated (ideally page-locked, PinnedArray) array of the right size to read into."""
+        if out is None:
+            out = np.zeros(self.batch * self.vec_len(vec))
+        else:
+            assert out.size == self.batch * self.vec_len(vec) and out.flags.c_contiguous and out.dtype == np.float64
         self._check(self.lib.madipm_vec_get(self._h, VEC[vec], _pd(out)))
+        out = out.reshape(-1)
         return out.reshape(self.batch, -1) if self.batch > 1 else out
 
     def vec_fill(self, vec, value):

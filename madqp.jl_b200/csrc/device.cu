@@ -1170,6 +1170,17 @@ int32_t madipm_debug_inject_barrier_fault(madipm_handle* h) {
     return MADIPM_OK;
 }
 
+int32_t madipm_pinned_alloc(int64_t bytes, void** ptr) {
+    if (!ptr || bytes < 0) return MADIPM_BAD_ARGUMENT;
+    *ptr = nullptr;
+    return cudaHostAlloc(ptr, static_cast<size_t>(std::max<int64_t>(bytes, 8)), cudaHostAllocPortable) == cudaSuccess ? MADIPM_OK : MADIPM_CUDA_ERROR;
+}
+
+int32_t madipm_pinned_free(void* ptr) {
+    if (!ptr) return MADIPM_OK;
+    return cudaFreeHost(ptr) == cudaSuccess ? MADIPM_OK : MADIPM_CUDA_ERROR;
+}
+
 void* madipm_stream(madipm_handle* h) { return (h && h->dev) ? h->dev->stream : nullptr; }
 
 int32_t madipm_vec_copy(madipm_handle* h, int32_t dst, int32_t src) {

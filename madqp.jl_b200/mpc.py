@@ -318,12 +318,18 @@ class MPCSolver:
         """prepare_host + upload in one device-side call (madipm_load_problem): the raw model arrays go to the GPU and
         MadNLP.initialize! / set_scaling! / the value compression run there.  prepare_host stays as the host reference."""
         opt, h = self.opt, self.h
-        cat = (lambda f: np.ascontiguousarray(f(self.qps[0]), dtype=np.float64)) if self.B == 1 else \
-            (lambda f: np.stack([np.asarray(f(qp), dtype=np.float64) for qp in self.qps]))
-        os_, nb, nbytes = h.load_problem(cat(lambda q: q.x0), cat(lambda q: q.lvar), cat(lambda q: q.uvar), cat(lambda q: q.y0),
-                                         cat(lambda q: q.lcon), cat(lambda q: q.ucon), cat(lambda q: q.c),
-                                         cat(lambda q: q.H_vals), cat(lambda q: q.A_vals),
-                                         opt.bound_relax_factor, opt.bound_push, opt.bound_fac, opt.scaling)
+        if getattr(self, "_raw", None) is None:
+            # the model's arrays, batch-major, in page-locked host memory: marshalled once (they are the caller's inputs and
+            # do not change between solves), sent to the device every solve
+            self._raw = []
+            for f in (lambda q: q.x0, lambda q: q.lvar, lambda q: q.uvar, lambda q: q.y0, lambda q: q.lcon, lambda q: q.ucon,
+                      lambda q: q.c, lambda q: q.H_vals, lambda q: q.A_vals):
+                first = np.asarray(f(self.qps[0]), dtype=np.float64)
+                buf = _lib.PinnedArray((self.B, first.size))
+                for b, qp in enumerate(self.qps):
+                    buf.a[b, :] = f(qp)
+                self._raw.append(buf)
+        os_, nb, nbytes = h.load_problem(*[r.a for r in self._raw], opt.bound_relax_factor, opt.bound_push, opt.bound_fac, opt.scaling)
         self.obj_scale[:] = os_
         self.norm_b = nb
         self._c0 = np.array([qp.c0 for qp in self.qps]) * self.obj_scale
@@ -618,11 +624,13 @@ class MPCSolver:
             if e.code == _lib.CUDA_ERROR:
                 raise
             self._fail(ERROR_IN_STEP_COMPUTATION if e.code in (_lib.NONFINITE, _lib.FACTOR_BREAKDOWN) else INTERNAL_ERROR)
-        x = self.h.vec_get("X").reshape(self.B, -1)
-        y = self.h.vec_get("Y").reshape(self.B, -1)
+        if getattr(self, "_res", None) is None:              # page-locked landing buffers for the results
+            self._res = {v: _lib.PinnedArray((self.B, self.h.vec_len(v))) for v in ("X", "Y", "CON_SCALE")}
+        x = self.h.vec_get("X", out=self._res["X"].a).reshape(self.B, -1)
+        y = self.h.vec_get("Y", out=self._res["Y"].a).reshape(self.B, -1)
         self.d2h_bytes = x.nbytes + y.nbytes
         if getattr(self, "_con_scale_on_device", False):
-            self.con_scale = self.h.vec_get("CON_SCALE").reshape(self.B, -1)
+            self.con_scale = self.h.vec_get("CON_SCALE", out=self._res["CON_SCALE"].a).reshape(self.B, -1).copy()
             self.d2h_bytes += self.con_scale.nbytes
         self.total_time = time.perf_counter() - t0
         return ExecutionStats(
