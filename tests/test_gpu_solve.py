@@ -231,7 +231,9 @@ def test_fused_phases_are_the_same_arithmetic(maker, kw, opts):
         for x, y in list(zip(ta, tb))[:4]:
             for key in ("obj", "inf_pr", "inf_du", "mu", "alpha_p", "alpha_d"):
                 np.testing.assert_allclose(x[key], y[key], rtol=1e-6, atol=1e-12)
-    assert la <= lb                # same kernels (the predictor's forward sweep rides in the factor launch), fewer synchronisations
+    # same kernels up to the two scalar kernels of madipm_phase_iteration per iteration (and the forward sweep that rides in the
+    # factor launch), far fewer synchronisations
+    assert la <= 1.05 * lb
 
 
 def free_pair_lp():
