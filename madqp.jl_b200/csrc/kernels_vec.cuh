@@ -21,6 +21,8 @@ __device__ __forceinline__ double nanmax(double a, double b) {
     return (a > b || a != a) ? a : b;
 }
 
+__device__ __forceinline__ double nanmin(double a, double b) { return (b < a || b != b) ? b : a; }
+
 struct ArgMin {
     double v;
     int i;
@@ -47,7 +49,7 @@ template <int OP>
 __device__ __forceinline__ double red_op(double a, double b) {
     if (OP == RED_SUM) return a + b;
     if (OP == RED_MAX) return nanmax(a, b);
-    return (b < a) ? b : a;
+    return (b < a || b != b) ? b : a;           // min that propagates NaN (Julia's minimum does; the asserts of solver.jl:119-122 must see it)
 }
 
 template <int OP>
@@ -929,8 +931,8 @@ k_start_a(VecView V, double* scratch, unsigned int* counter, double* out) {
         else if (fu) zu = -res;
         V.zl[i] = zl; V.zu[i] = zu;
         const double x = V.x[i];
-        if (V.lb_of[i] >= 0) { r.v[0] = fmin(r.v[0], x - l); r.v[2] = fmin(r.v[2], zl); }
-        if (V.ub_of[i] >= 0) { r.v[1] = fmin(r.v[1], u - x); r.v[3] = fmin(r.v[3], zu); }
+        if (V.lb_of[i] >= 0) { r.v[0] = nanmin(r.v[0], x - l); r.v[2] = nanmin(r.v[2], zl); }
+        if (V.ub_of[i] >= 0) { r.v[1] = nanmin(r.v[1], u - x); r.v[3] = nanmin(r.v[3], zu); }
     }
     grid_reduce<4, RED_MIN, RED_MIN, RED_MIN, RED_MIN>(r, scratch, counter, out);
 }
@@ -991,8 +993,8 @@ k_start_c(VecView V, const double* __restrict__ deltas, double kappa, double* sc
         if (x < l) x = l + fmin(kappa * fmax(1.0, l), kappa * (u - l));
         else if (u < x) x = u - fmin(kappa * fmax(1.0, u), kappa * (u - l));
         V.x[i] = x;
-        if (hl) { r.v[0] = fmin(r.v[0], V.zl[i]); r.v[2] = fmin(r.v[2], x - l); }
-        if (hu) { r.v[1] = fmin(r.v[1], V.zu[i]); r.v[3] = fmin(r.v[3], u - x); }
+        if (hl) { r.v[0] = nanmin(r.v[0], V.zl[i]); r.v[2] = nanmin(r.v[2], x - l); }
+        if (hu) { r.v[1] = nanmin(r.v[1], V.zu[i]); r.v[3] = nanmin(r.v[3], u - x); }
     }
     grid_reduce<4, RED_MIN, RED_MIN, RED_MIN, RED_MIN>(r, scratch, counter, out);
 }

@@ -387,3 +387,16 @@ def test_one_synchronisation_iteration_batch_and_retry():
         end.append((st.status[0], int(st.iter[0]), s.del_w, s.del_c))
         s.close()
     assert end[0] == end[1] and end[0][0] == "ERROR_IN_STEP_COMPUTATION", end
+
+
+def test_nan_in_the_starting_point_fails_the_reference_asserts():
+    """Julia's minimum / all(...) propagate NaN, so a NaN iterate trips the @asserts of
+    solver.jl:119-122 and solve! ends in INTERNAL_ERROR; the device reductions now propagate NaN as well."""
+    qp = P.inequality_qp(seed=2)
+    qp.c = qp.c.copy()
+    qp.c[0] = np.nan
+    s = MPCSolver(qp, regularization=FixedRegularization(1e-8, -1e-8))
+    st = s.solve()
+    assert st.status[0] in ("INTERNAL_ERROR", "ERROR_IN_STEP_COMPUTATION")
+    assert int(st.iter[0]) == 0
+    s.close()
