@@ -382,6 +382,8 @@ typedef struct {
     double mu_min;            /* opt.mu_min */
     double tau;               /* ConservativeStep: tau;  AdaptiveStep: tau_min */
     double c0;                /* constant term of the objective (scaled) */
+    double res_tol;           /* > 0: a predictor residual ratio above it is a no-go as well (a garbage factor that the pivot tests
+                                 cannot see: exactly dependent rows); 0: only NaN is, as in linear_solver.jl:41-43 */
     int32_t adaptive_step;    /* 1: tau = max(1 - mu, tau_min) (kernels.jl:315-323), 0: tau fixed (kernels.jl:307-313) */
     int32_t has_inequalities; /* SURVEY 8a note B.1: any finite bound */
 } madipm_iter_options;

@@ -55,7 +55,7 @@ class LoadOptions(C.Structure):
 
 class IterOptions(C.Structure):
     _fields_ = [("del_w", C.c_double), ("del_c", C.c_double), ("mu_min", C.c_double), ("tau", C.c_double), ("c0", C.c_double),
-                ("adaptive_step", C.c_int32), ("has_inequalities", C.c_int32)]
+                ("res_tol", C.c_double), ("adaptive_step", C.c_int32), ("has_inequalities", C.c_int32)]
 
 
 class ScaleOptions(C.Structure):
@@ -466,9 +466,9 @@ class Handle:
         rc = self._check(self.lib.madipm_phase_factor_predictor(self._h, del_w, del_c, _pd(norms), _pd(out)), allow=(NONFINITE,))
         return rc, norms.reshape(self.batch, 3), out.reshape(self.batch, 4)
 
-    def phase_iteration(self, del_w, del_c, mu_min, tau, adaptive, has_inequalities, c0=0.0, active=None):
+    def phase_iteration(self, del_w, del_c, mu_min, tau, adaptive, has_inequalities, c0=0.0, active=None, res_tol=0.0):
         """One mpc! iteration with one synchronisation (madipm_phase_iteration).  Returns (ok, out[batch, 28])."""
-        opt = IterOptions(del_w, del_c, mu_min, tau, c0, 1 if adaptive else 0, 1 if has_inequalities else 0)
+        opt = IterOptions(del_w, del_c, mu_min, tau, c0, res_tol, 1 if adaptive else 0, 1 if has_inequalities else 0)
         out = np.zeros(28 * self.batch)
         ok = C.c_int32(0)
         act = None if active is None else np.ascontiguousarray(active, dtype=np.int32)

@@ -1784,7 +1784,7 @@ int32_t madipm_phase_iteration(madipm_handle* h, const madipm_iter_options* o, c
                d->red_counter, d->d_out);                                                        // solver.jl:296-297
         // ---- update_barrier! and the step rule's tau, on the device
         LAUNCH(h, k_iter_scalars1, 1, 256, 0, B, d->nlb + d->nub, d->d_out, d->d_steps, d->d_norms, d->fail, act, o->has_inequalities,
-               o->mu_min, o->adaptive_step, o->tau, d_aff4, d->d_mu, d->d_tau, d->d_ok);
+               o->mu_min, o->adaptive_step, o->tau, o->res_tol, d_aff4, d->d_mu, d->d_tau, d->d_ok);
         // ---- mehrotra_correction_direction! (solver.jl:307-311)
         const int top = std::max(std::max(d->n, d->m), std::max(d->nlb, d->nub));
         LAUNCH(h, k_set_rhs, dim3(vec_blocks(top), B), kVecThreads, 0, make_view(*d), d->vec[MADIPM_VEC_P], 3, d->d_mu);

@@ -594,7 +594,7 @@ __device__ __forceinline__ double max_nan(double a, double b) { return (a != a |
 
 __global__ void k_iter_scalars1(int B, int nb, const double* __restrict__ sums, const double* __restrict__ steps_aff,
                                 const double* __restrict__ norms, const int* __restrict__ fail, const int* __restrict__ active,
-                                int has_ineq, double mu_min, int adaptive, double tau_par,
+                                int has_ineq, double mu_min, int adaptive, double tau_par, double res_tol,
                                 double* __restrict__ aff4, double* __restrict__ mu, double* __restrict__ tau, int* __restrict__ ok_all) {
     __shared__ int bad;
     if (threadIdx.x == 0) bad = 0;
@@ -615,7 +615,7 @@ __global__ void k_iter_scalars1(int B, int nb, const double* __restrict__ sums, 
         mu[i] = m;
         tau[i] = adaptive ? max_nan(__dsub_rn(1.0, m), tau_par) : tau_par;
         const double ratio = __ddiv_rn(norms[3 * i], fmax(1.0, norms[3 * i + 1]));
-        if ((!active || active[i]) && (fail[i] != 0 || ratio != ratio)) atomicExch(&bad, 1);
+        if ((!active || active[i]) && (fail[i] != 0 || ratio != ratio || (res_tol > 0.0 && ratio > res_tol))) atomicExch(&bad, 1);
     }
     __syncthreads();
     if (threadIdx.x == 0) *ok_all = bad ? 0 : 1;

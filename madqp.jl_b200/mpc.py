@@ -97,6 +97,10 @@ class IPMOptions:
     # as well): the retry multiplies (del_w, del_c) by 100, which leaves del_c = 0 (the reference's default delta_d) at 0 for
     # ever; with the kick the first retry starts del_c at -del_w, so dependent constraint rows get a usable pivot.
     dual_regularization_kick: bool = True
+    # The predictor solve's residual ratio (linear_solver.jl:28-36, computed anyway) above this value counts as a breakdown of
+    # the factorisation as well: exactly dependent rows leave pivots AND their columns at roundoff size, which neither pivot
+    # test can see, but the direction is garbage and the residual says so (healthy solves: 1e-10 ... 1e-6).  0 = off.
+    residual_breakdown_tol: float = 1e-3
     growth_limit: float = 1e13      # element-growth breakdown test of the unpivoted LDL' (madipm_set_pivot_checks); 0 = off
     tiny_pivot: float = 1e-13       # |pivot| at or below it is a breakdown as well; 0 = only exact zeros (the reference)
     fused_iteration: bool = True    # ... and a whole iteration behind ONE synchronisation (madipm_phase_iteration) when max_ncorr = 0
@@ -409,6 +413,14 @@ class MPCSolver:
         self.del_w *= 100.0
         self.del_c *= 100.0
 
+    def _garbage_direction(self, norms):
+        tol = self.opt.residual_breakdown_tol
+        if tol <= 0.0:
+            return False
+        act = self.active.astype(bool)
+        ratio = norms[:, 0] / np.maximum(1.0, norms[:, 1])
+        return bool(np.any(ratio[act] > tol))
+
     def factorize_regularized_system(self, tries=3):
         """/root/reference/src/linear_solver.jl:6-17."""
         for _ in range(tries):
@@ -538,14 +550,14 @@ class MPCSolver:
             self._update_regularization()                               # l.288
             fused = opt.fused_phases
             rule = opt.step_rule
-            if (fused and opt.fused_iteration and opt.max_ncorr == 0 and isinstance(rule, (ConservativeStep, AdaptiveStep))
-                    and not opt.check_residual):
+            if (fused and opt.fused_iteration and opt.fused_factor_forward and opt.max_ncorr == 0
+                    and isinstance(rule, (ConservativeStep, AdaptiveStep)) and not opt.check_residual):
                 # the whole iteration (l.288-342) behind one synchronisation; the device leaves the iterate alone and says so
                 # when a factorisation broke down or a residual is not a number: then the phases below redo the iteration
                 adaptive = isinstance(rule, AdaptiveStep)
                 ok, it = h.phase_iteration(self.del_w, self.del_c, opt.mu_min, rule.tau_min if adaptive else rule.tau, adaptive,
                                            (self.nlb + self.nub) > 0, float(self._c0[0]) if self.B == 1 else 0.0,
-                                           None if self.B == 1 else self.active)
+                                           None if self.B == 1 else self.active, res_tol=opt.residual_breakdown_tol)
                 if ok:
                     self.last_residual_ratio = it[:, 9] / np.maximum(1.0, it[:, 10])
                     self.mu = it[:, 7].copy()
@@ -564,15 +576,23 @@ class MPCSolver:
                     self.kkt.build_kkt()
                     h.factorize_async()
                     rc, norms, aff = h.phase_predictor()                # l.294-297 affine_direction!
-                if not np.all(self.kkt.is_factorized()[self.active.astype(bool)]):
+                for _ in range(2):                                      # the retries of linear_solver.jl:8-16
+                    if np.all(self.kkt.is_factorized()[self.active.astype(bool)]) and not self._garbage_direction(norms):
+                        break
                     self._bump_regularization()
-                    self.factorize_regularized_system(tries=2)
+                    self.factorize_regularized_system(tries=1)
                     rc, norms, aff = h.phase_predictor()
                 self._check_solve_norms(norms)
             else:
                 self.factorize_regularized_system()                     # l.289
                 h.set_predictive_rhs()                                  # l.294 affine_direction!
-                self.solve_system()
+                for _ in range(2):
+                    rc, norms = self.h.solve_system("D", "P")
+                    if not self._garbage_direction(norms):
+                        break
+                    self._bump_regularization()
+                    self.factorize_regularized_system(tries=1)
+                self._check_solve_norms(norms)
                 aff = h.phase_affine()                                  # l.295-297
             mu_affine, mu_curr = aff[:, 2], aff[:, 3]
             self.update_barrier(mu_affine, mu_curr)                     # l.302

@@ -269,7 +269,7 @@ def test_forward_sweep_inside_the_factor_launch_changes_nothing():
                      (P.maros_meszaros_like(), dict(kkt_system="K2.5"))):
         out = []
         for ff in (True, False):
-            s = MPCSolver(qp, regularization=FixedRegularization(1e-8, -1e-8), fused_factor_forward=ff, **opts)
+            s = MPCSolver(qp, regularization=FixedRegularization(1e-8, -1e-8), fused_factor_forward=ff, fused_iteration=False, **opts)
             st = s.solve()
             out.append((st, s.trace, s.h.launch_count(), bool((s.h.symbolic("SUPER_KIND") == 0).all())))
             s.close()
