@@ -95,7 +95,7 @@ class IPMOptions:
     fused_phases: bool = True       # 3 host synchronisations per iteration (madipm_phase_*) instead of 7; same arithmetic
     # Deviation from linear_solver.jl:14-15, acts only after a breakdown (where the reference's unpivoted LDLSolver path fails
     # as well): the retry multiplies (del_w, del_c) by 100, which leaves del_c = 0 (the reference's default delta_d) at 0 for
-    # ever; with the kick the first retry starts del_c at -del_w, so dependent constraint rows get a usable pivot.
+    # ever; with the kick the first retry only sets del_c = -del_w, so dependent constraint rows get a usable pivot.
     dual_regularization_kick: bool = True
     # The predictor solve's residual ratio (linear_solver.jl:28-36, computed anyway) above this value counts as a breakdown of
     # the factorisation as well: exactly dependent rows leave pivots AND their columns at roundoff size, which neither pivot
@@ -409,7 +409,8 @@ class MPCSolver:
     def _bump_regularization(self):
         """linear_solver.jl:14-15 (+ the dual kick described at IPMOptions.dual_regularization_kick)."""
         if self.opt.dual_regularization_kick and self.del_c == 0.0 and self.del_w > 0.0 and self.opt.kkt_system != "NORMAL":
-            self.del_c = -self.del_w / 100.0
+            self.del_c = -self.del_w          # first retry: only the missing dual regularisation (a larger del_w slows the
+            return                            # convergence of the dual residual: r_d after a full step is -del_w * dx)
         self.del_w *= 100.0
         self.del_c *= 100.0
 
