@@ -449,7 +449,18 @@ class MPCSolver:
         h.set_initial_regularization(self.del_w, self.del_c)        # l.16-18
         self.factorize_wrapper()                                    # l.21
         h.set_initial_primal_rhs()                                  # l.25
-        self.solve_system()                                         # l.26
+        rc, norms = h.solve_system("D", "P")                        # l.26
+        if self.opt.dual_regularization_kick or self.opt.residual_breakdown_tol > 0.0:
+            # (deviation, see IPMOptions: the reference factorises once here; a breakdown or a garbage solve gets one retry
+            #  with the dual kick, otherwise the start is garbage along the dependent rows and the solve never recovers)
+            act = self.active.astype(bool)
+            if not np.all(self.kkt.is_factorized()[act]) or self._garbage_direction(norms):
+                self._bump_regularization()
+                h.set_initial_regularization(self.del_w, self.del_c)
+                self.factorize_wrapper()
+                h.set_initial_primal_rhs()
+                rc, norms = h.solve_system("D", "P")
+        self._check_solve_norms(norms)
         h.vec_axpy("X", 0, "D", 0, self.n, 1.0)                     # l.28
         h.set_initial_dual_rhs()                                    # l.31
         self.solve_system()                                         # l.32
