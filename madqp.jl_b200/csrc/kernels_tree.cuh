@@ -30,6 +30,7 @@
 #include <cuda_runtime.h>
 
 #include "kernels_factor.cuh"
+#include "dense_ldl_blk.cuh"
 
 namespace madipm {
 
@@ -377,7 +378,10 @@ __device__ __forceinline__ void tree_factor_task(const TreeView& T, const SnMeta
     }
     TT(1);
     // 2. dense LDL' of the panel: D on the diagonal of the top w x w block, unit-lower L elsewhere
-    dense_ldl<G>(Ps, h, w, F.fail + inst, t, F.growth, F.tiny);  // ends with a barrier of the whole group
+    // (both end with a barrier of the whole group; the blocked right-looking routine needs h <= 2 G, which the task classes
+    //  guarantee except for fronts taller than 512 rows in the 256-thread class)
+    if (h <= 2 * G) dense_ldl_blk<G>(Ps, h, w, ucol, F.fail + inst, t, F.growth, F.tiny);
+    else dense_ldl<G>(Ps, h, w, F.fail + inst, t, F.growth, F.tiny);
     TT(2);
     for (int c = t; c < nchunk; c += G) reinterpret_cast<double2*>(P)[c] = reinterpret_cast<const double2*>(Ps)[c];
     if (nb == 0) {

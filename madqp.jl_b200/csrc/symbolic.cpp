@@ -832,11 +832,13 @@ void analyze(int32_t n, const int64_t* colptr, const int32_t* rowval, const Symb
     auto panel_need = [&](int64_t np) { return even(np) + 2; };            // odd tail chunk + 4-column tile overrun
     S.tree_fixed = even(std::max(S.max_w, 1)) + 16 * 4 + 2;
     // a multiple of 16 doubles, so that the slices of the smaller classes nest exactly inside the larger ones
-    const int32_t slice256 = (panel_need(std::max(S.small_max_panel, 2)) + even(std::max(S.small_max_h, 2)) + S.tree_fixed + 15) & ~15;
+    // (the h-doubles region doubles as the column buffer of dense_ldl_blk: at least 24 doubles)
+    const int32_t slice256 = (panel_need(std::max(S.small_max_panel, 2)) + even(std::max(S.small_max_h, 24)) + S.tree_fixed + 15) & ~15;
     for (int32_t c = 0; c < 4; ++c) {
         const int32_t G = 256 >> c;
         S.tree_slice[c] = slice256 >> c;
-        S.tree_maxh[c] = c == 0 ? even(std::max(S.small_max_h, 2)) : std::min(even(std::max(S.small_max_h, 2)), 4 * G);
+        // a group of G threads owns at most two rows per thread in the panel step of dense_ldl_blk
+        S.tree_maxh[c] = c == 0 ? even(std::max(S.small_max_h, 24)) : std::min(even(std::max(S.small_max_h, 24)), 2 * G);
         S.tree_cap[c] = S.tree_slice[c] - S.tree_maxh[c] - S.tree_fixed;
     }
     std::vector<int8_t> cls(ns, 0);

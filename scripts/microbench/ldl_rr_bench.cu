@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include "../../madqp.jl_b200/csrc/kernels_tree.cuh"
 #include "../../madqp.jl_b200/csrc/dense_ldl_rr.cuh"
+#include "../../madqp.jl_b200/csrc/dense_ldl_blk.cuh"
 using namespace madipm;
 
 template <int WMAX>
@@ -47,6 +48,26 @@ __global__ void kb_old(double* P, int h, int w, int* fail, long long* cyc, int r
     for (int i = t; i < h * w; i += G) P[i] = Ps[i];
 }
 
+template <int G>
+__global__ void kb_blk(double* P, int h, int w, int* fail, long long* cyc, int reps) {
+    extern __shared__ double2 sm2[];
+    double* Ps = reinterpret_cast<double*>(sm2);
+    double* cb = Ps + ((h * w + 1) & ~1);
+    const int t = threadIdx.x % G;
+    long long best = 1LL << 60;
+    for (int r = 0; r < reps; ++r) {
+        for (int i = t; i < h * w; i += G) Ps[i] = P[i];
+        blk_sync<G>();
+        long long t0 = clock64();
+        dense_ldl_blk<G>(Ps, h, w, cb, fail, t, 1e13, 1e-13);
+        blk_sync<G>();
+        long long t1 = clock64();
+        if (t1 - t0 < best) best = t1 - t0;
+    }
+    if (threadIdx.x == 0) cyc[0] = best;
+    for (int i = t; i < h * w; i += G) P[i] = Ps[i];
+}
+
 static double check(const std::vector<double>& A0, const std::vector<double>& L, int h, int w) {
     double err = 0;
     for (int j = 0; j < w; ++j) for (int i = j; i < h; ++i) {
@@ -76,6 +97,19 @@ int main() {
         cudaError_t e = cudaDeviceSynchronize();
         cudaMemcpy(c, cyc, 8, cudaMemcpyDeviceToHost); cudaMemcpy(L.data(), dP, A.size() * 8, cudaMemcpyDeviceToHost);
         printf("h %3d w %2d old<256>   : %7lld cycles (%5.0f per column) err %.2e %s\n", h, w, c[0], c[0] / (double)w, check(A0, L, h, w), cudaGetErrorString(e));
+        // blocked right-looking with DMMA trailing update, 256 and (h <= 64) 32 threads
+        for (int G : {256, 128, 32}) {
+            if (h > 2 * G) continue;
+            cudaMemcpy(dP, A0.data(), A.size() * 8, cudaMemcpyHostToDevice);
+            cudaMemset(fail, 0, 4);
+            if (G == 256) { cudaFuncSetAttribute(kb_blk<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); kb_blk<256><<<1, 256, smem>>>(dP, h, w, fail, cyc, 5); }
+            else if (G == 128) { cudaFuncSetAttribute(kb_blk<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); kb_blk<128><<<1, 128, smem>>>(dP, h, w, fail, cyc, 5); }
+            else { cudaFuncSetAttribute(kb_blk<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); kb_blk<32><<<1, 32, smem>>>(dP, h, w, fail, cyc, 5); }
+            e = cudaDeviceSynchronize();
+            int hf = 0; cudaMemcpy(&hf, fail, 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(c, cyc, 8, cudaMemcpyDeviceToHost); cudaMemcpy(L.data(), dP, A.size() * 8, cudaMemcpyDeviceToHost);
+            printf("h %3d w %2d blk<%3d>    : %7lld cycles (%5.0f per column) err %.2e fail %d %s\n", h, w, G, c[0], c[0] / (double)w, check(A0, L, h, w), hf, cudaGetErrorString(e));
+        }
         // new
         cudaMemcpy(dP, A0.data(), A.size() * 8, cudaMemcpyHostToDevice);
 #define RUN(WM) do { cudaFuncSetAttribute(kb_rr<WM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); kb_rr<WM><<<1, 256, smem>>>(dP, h, w, cyc, 5); } while (0)
