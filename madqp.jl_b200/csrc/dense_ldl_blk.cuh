@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include "dense_ldl_rr.cuh"
+#include "kernels_factor.cuh"
 
 namespace madipm {
 
@@ -21,7 +22,7 @@ template <int G>
 __device__ __forceinline__ void blk_sync() {
     if (G == 32) __syncwarp();
     else if (G >= 256) __syncthreads();
-    else asm volatile("bar.sync %0, %1;" ::"r"((G == 128 ? 1 : 3) + static_cast<int>(threadIdx.x) / G), "n"(G) : "memory");
+    else named_barrier((G == 128 ? 1 : 3) + static_cast<int>(threadIdx.x) / G, G);
 }
 // barrier among the first nact threads (a multiple of 32) of the group: the warps that own rows in the panel step.  Same
 // auxiliary barrier ids as gsync_active in kernels_tree.cuh (7-8: the two 128-thread groups of a block, 9: a 256- or
@@ -30,7 +31,7 @@ template <int G>
 __device__ __forceinline__ void blk_sync_active(int nact) {
     if (G == 32 || nact <= 32) __syncwarp();
     else if (nact >= G) blk_sync<G>();
-    else asm volatile("bar.sync %0, %1;" ::"r"(G == 128 ? 7 + static_cast<int>(threadIdx.x) / G : 9), "r"(nact) : "memory");
+    else named_barrier(G == 128 ? 7 + static_cast<int>(threadIdx.x) / G : 9, nact);
 }
 
 // Ps: panel (ld = h).  cb: 2 * 8 + 8 doubles of shared memory private to the group (16-byte aligned).  Requires h <= 2 * G.

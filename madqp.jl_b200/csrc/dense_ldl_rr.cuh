@@ -33,7 +33,13 @@ __device__ __forceinline__ double rr_rcp(double d) {
 // barrier among the first `n` threads (multiple of 32) of the group that uses named barrier `id`
 __device__ __forceinline__ void rr_bar(int id, int n) {
     if (n <= 32) __syncwarp();
-    else asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+    else {
+#ifdef MADIPM_ALIGNED_BARRIERS
+        asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+#else
+        asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(n) : "memory");     // non-aligned on purpose: see named_barrier in kernels_factor.cuh
+#endif
+    }
 }
 
 constexpr int kRrLd = 64 + 2;           // leading dimension of the two column buffers (doubles)

@@ -31,6 +31,24 @@ struct FactorView {
     double tiny;               // |pivot| at or below it is a breakdown (0 = only exact zeros, the reference's semantics)
 };
 
+// Named barrier among `count` threads (a multiple of 32) of a thread block.
+//
+// This MUST be the non-aligned form.  PTX `bar.sync` is `barrier.sync.aligned`: every thread of a warp has to execute it
+// together, and the result is undefined when the warp's lanes have not reconverged after divergent code (a data-dependent
+// loop, an `if (t < n)` store) -- the compiler usually reconverges them in time, which is what made this a rare,
+// timing- and register-allocation-dependent hang instead of a plain bug: a warp whose halves arrive separately is counted
+// twice, the barrier opens early once and is then one arrival short for ever; the group never finishes its task, its block
+// never reaches the grid barrier, the persistent kernel never returns.  That was the 30-minute hang of round 1's driver
+// benchmark; it became deterministic with -DMADIPM_TREE_BLOCKS=3 (80 registers, different instruction schedule) and went away
+// with `barrier.sync`, which counts threads individually.  -DMADIPM_ALIGNED_BARRIERS restores the old form (to reproduce).
+__device__ __forceinline__ void named_barrier(int id, int count) {
+#ifdef MADIPM_ALIGNED_BARRIERS
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+#else
+    asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+#endif
+}
+
 constexpr int64_t kRelShift = int64_t(1) << 40;
 constexpr int64_t kRelSearch = INT64_MIN;
 

@@ -124,7 +124,7 @@ template <int G>
 __device__ __forceinline__ void gsync() {
     if (G == 32) __syncwarp();
     else if (G >= kTreeThreads) __syncthreads();
-    else asm volatile("bar.sync %0, %1;" ::"r"((G == 128 ? 1 : 3) + static_cast<int>(threadIdx.x) / G), "n"(G) : "memory");
+    else named_barrier((G == 128 ? 1 : 3) + static_cast<int>(threadIdx.x) / G, G);
 }
 
 // barrier among the first `nact` threads (a multiple of 32) of a task group: the warps of a group that still own rows of
@@ -134,7 +134,7 @@ template <int G>
 __device__ __forceinline__ void gsync_active(int nact) {
     if (G == 32 || nact <= 32) __syncwarp();
     else if (nact >= G) gsync<G>();
-    else asm volatile("bar.sync %0, %1;" ::"r"(G == 128 ? 7 + static_cast<int>(threadIdx.x) / G : 9), "r"(nact) : "memory");
+    else named_barrier(G == 128 ? 7 + static_cast<int>(threadIdx.x) / G : 9, nact);
 }
 
 // offset of column b inside a packed lower triangle of order nb, shifted so that [a] addresses row a >= b
@@ -755,8 +755,11 @@ __device__ __forceinline__ void run_class(const TreeView& T, double* smem, int p
 }
 
 // OP: 0 factor, 1 forward, 2 backward, 3 factor + forward step of the right-hand side in xw.  Heights ph_begin, ph_begin + step, ... (ph_end excluded).
+#ifndef MADIPM_TREE_BLOCKS
+#define MADIPM_TREE_BLOCKS 4
+#endif
 template <int OP>
-__global__ void __launch_bounds__(kTreeThreads, 4)
+__global__ void __launch_bounds__(kTreeThreads, MADIPM_TREE_BLOCKS)
 k_tree(TreeView T, int ph_begin, int ph_end, int step) {
     extern __shared__ double2 tree_smem2[];
     double* smem = reinterpret_cast<double*>(tree_smem2);

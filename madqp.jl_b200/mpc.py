@@ -653,8 +653,15 @@ class MPCSolver:
         except AssertionError:
             self._fail(INTERNAL_ERROR)
         except MadIPMError as e:
+            self.last_error_message = str(e)
             if e.code == _lib.CUDA_ERROR:
                 raise
+            if e.code == _lib.INTERNAL:
+                import sys
+                sys.stderr.write(f"[madipm] {e}\n")
+                sys.stderr.flush()
+                if "still busy" in str(e) or "wedged" in str(e):
+                    raise                  # the stream holds a kernel that never returns: nothing more can be read from this handle
             self._fail(ERROR_IN_STEP_COMPUTATION if e.code in (_lib.NONFINITE, _lib.FACTOR_BREAKDOWN) else INTERNAL_ERROR)
         if getattr(self, "_res", None) is None:              # page-locked landing buffers for the results
             self._res = {v: _lib.PinnedArray((self.B, self.h.vec_len(v))) for v in ("X", "Y", "CON_SCALE")}
