@@ -103,6 +103,7 @@ __device__ __forceinline__ void dense_ldl_blk(double* __restrict__ Ps, int h, in
             int q = gw, cj = 0, base = 0;
             const int ntile = nct * nrt - nct * (nct - 1) / 2;
             const double dk0 = fk < bw ? -dblk[fk] : 0.0, dk1 = fk + 4 < bw ? -dblk[fk + 4] : 0.0;
+            __syncwarp();                                     // mma.sync.aligned below: the warp must be converged
             for (; q < ntile; q += NW) {
                 while (q - base >= nrt - cj) { base += nrt - cj; ++cj; }
                 const int ri = cj + (q - base);

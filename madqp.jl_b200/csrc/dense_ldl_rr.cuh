@@ -37,7 +37,9 @@ __device__ __forceinline__ void rr_bar(int id, int n) {
 #ifdef MADIPM_ALIGNED_BARRIERS
         asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
 #else
+        __syncwarp();
         asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(n) : "memory");     // non-aligned on purpose: see named_barrier in kernels_factor.cuh
+        __syncwarp();
 #endif
     }
 }

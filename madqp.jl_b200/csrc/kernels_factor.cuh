@@ -41,11 +41,15 @@ struct FactorView {
 // never reaches the grid barrier, the persistent kernel never returns.  That was the 30-minute hang of round 1's driver
 // benchmark; it became deterministic with -DMADIPM_TREE_BLOCKS=3 (80 registers, different instruction schedule) and went away
 // with `barrier.sync`, which counts threads individually.  -DMADIPM_ALIGNED_BARRIERS restores the old form (to reproduce).
+// The __syncwarp() on both sides makes the warp arrive and leave CONVERGED: code after a barrier uses warp collectives
+// (mma.sync.aligned, __shfl_sync with the full mask) whose convergence requirement is the same as bar.sync's.
 __device__ __forceinline__ void named_barrier(int id, int count) {
 #ifdef MADIPM_ALIGNED_BARRIERS
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 #else
+    __syncwarp();
     asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+    __syncwarp();
 #endif
 }
 

@@ -158,6 +158,7 @@ __device__ __forceinline__ void front_factor_task(const TreeView& T, const Front
         const int fr = lane >> 2, fk = lane & 3;
         const int nb8 = (nb + 7) >> 3;
         const int nblk = nb8 * (nb8 + 1) / 2;
+        __syncwarp();                                          // mma.sync.aligned below: the warp must be converged
         for (int q0 = 2 * gw; q0 < nblk; q0 += 2 * NW) {
             int bi[2], bj[2];
 #pragma unroll

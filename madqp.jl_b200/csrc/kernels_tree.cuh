@@ -399,6 +399,7 @@ __device__ __forceinline__ void tree_factor_task(const TreeView& T, const SnMeta
         const int fr = lane >> 2, fk = lane & 3;
         const int nb8 = (nb + 7) >> 3;
         int bi = 0, bj = 0;                               // block q of the row-major enumeration of the lower triangle
+        __syncwarp();                                     // mma.sync.aligned below: the warp must be converged
         for (int q = 0, mine = gw; mine < nb8 * (nb8 + 1) / 2; mine += NW) {
             while (q < mine) { if (++bj > bi) { ++bi; bj = 0; } ++q; }
             const int ra = w + bi * 8 + fr, rb = w + bj * 8 + fr;
@@ -547,6 +548,7 @@ __device__ __forceinline__ void tree_forward_core(const TreeView& T, const SnMet
     gsync<G>();
     TT(2);
     if (gw == 0) {                                        // unit-lower triangular solve, one warp
+        __syncwarp();                                     // (full-mask shuffles below)
         if (w <= 64) {
             // y in registers (lane l holds y[l] and y[l + 32]); per column one shuffle and one FMA on the dependent
             // chain, the entries of L come from shared memory ahead of it
@@ -637,6 +639,7 @@ __device__ __forceinline__ void tree_backward_task(const TreeView& T, const SnMe
     gsync<G>();
     TT(2);
     if (gw == 0) {                                        // unit-upper triangular solve with L11', one warp
+        __syncwarp();                                     // (full-mask shuffles below)
         if (w <= 64) {
             // x in registers (lane l holds x[l] and x[l + 32]); L11'[k][j] = L[j][k] = Ps[j + k * h]
             double x0 = lane < w ? st[lane] : 0.0, x1 = lane + 32 < w ? st[lane + 32] : 0.0;
