@@ -127,6 +127,7 @@ k_big_trsm(FactorView F, const int* __restrict__ big_sn, const double* __restric
 #pragma unroll
             for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
         const int kmax = min(w, n0 + nn);                 // Z is upper triangular: k <= n
+        __syncwarp();                                     // mma.sync.aligned below: the warp must be converged
         for (int k0 = 0; k0 < kmax; k0 += 4) {
             double af[4], bf[4];
             const int kk = k0 + fk;
@@ -331,6 +332,7 @@ k_big_update(FactorView F, const int* __restrict__ big_sn, const int* __restrict
         while (c >= src_chunk0[sq + 1]) ++sq;
         const double* Dq = Ds + sq * kBigTile + (c - src_chunk0[sq]) * kBigKc;
         const int kleft = src_w[sq] - (c - src_chunk0[sq]) * kBigKc;      // valid k of this chunk (the rest is zero-filled)
+        __syncwarp();                                          // mma.sync.aligned below: the warp must be converged
 #pragma unroll
         for (int k0 = 0; k0 < kBigKc; k0 += 4) {
             double af[4], bf[4];
