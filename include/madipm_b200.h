@@ -410,7 +410,26 @@ int32_t madipm_scale_qp(madipm_scale_options* opt, int32_t nvar, int32_t ncon,
                         int64_t nnzh, const int32_t* hess_I, const int32_t* hess_J, double* hess_V,
                         double* c, double* lvar, double* uvar, double* lcon, double* ucon, double* x0, double* y0,
                         double* Dr, double* Dc, int32_t* sweeps_done, double* final_err);
-const char* madipm_scale_last_error(void);   /* of the calling thread's last madipm_scale_qp */
+const char* madipm_scale_last_error(void);   /* of the calling thread's last madipm_scale_qp / madipm_standard_form_qp */
+
+/* standard_form_qp, /root/reference/scripts/common.jl:156-288: slack variables s = A x for the inequality rows
+ * (lcon < ucon, common.jl:164-168; appended columns nvar+1 .. nvar+ns, entries -1, common.jl:214-219) and every RANGE
+ * bound of x or s (-Inf < l < u < Inf, common.jl:180-183, 192-195) moved into an equality row  x_i + w_k = u_i  with a
+ * new nonnegative variable w_k (rows ncon+1 .. ncon+nw, columns nvar+ns+1 .., common.jl:221-230, 249-259).  Variables
+ * with only an upper bound keep it, fixed variables stay fixed (common.jl:257-259), the Hessian is unchanged (only its
+ * dimension grows, common.jl:209).  Needs no handle; the work is done on the device (classification of the n + m
+ * bounds, one prefix sum for the ranks k, ranked writes), host buffers in and out.  1-based COO triplets.
+ * Outputs, caller-allocated for the worst case, of which the first ... entries are written:
+ *   jac_*_out  [nnzj + ncon + 2 (nvar + ncon)]   nnzj + ns + 2 nw   ([A | slack | range pairs], the reference's order)
+ *   c_out, lvar_out, uvar_out, x0_out [2 (nvar + ncon)]   nvar + ns + nw
+ *   lcon_out, ucon_out, y0_out [nvar + 2 ncon]            ncon + nw
+ * c, x0, y0 may be NULL (zeros); any output pointer may be NULL (not downloaded).  nvar + ncon < 2^30. */
+int32_t madipm_standard_form_qp(int32_t device, int32_t nvar, int32_t ncon, int64_t nnzj, const int32_t* jac_I, const int32_t* jac_J,
+                                const double* jac_V, const double* c, const double* lvar, const double* uvar, const double* lcon,
+                                const double* ucon, const double* x0, const double* y0, int32_t* ns, int32_t* nw,
+                                int32_t* jac_I_out, int32_t* jac_J_out, double* jac_V_out, double* c_out, double* lvar_out,
+                                double* uvar_out, double* x0_out, double* lcon_out, double* ucon_out, double* y0_out,
+                                int64_t* launches);
 
 #ifdef __cplusplus
 }

@@ -694,6 +694,35 @@ function scale_qp!(nvar, ncon, jac_I::Vector{Int32}, jac_J::Vector{Int32}, jac_V
     return Dr, Dc
 end
 
+# ---- preprocessing: standard_form_qp of scripts/common.jl:156-288 ---------------------------------------------------------
+"""
+    standard_form_arrays(nvar, ncon, jac_I, jac_J, jac_V, c, lvar, uvar, lcon, ucon, x0, y0) -> NamedTuple
+
+The arrays of `standard_form_qp(qp)` (slacks for the inequality rows, range bounds moved into equality rows), computed on
+the device; the caller wraps them in a `QuadraticModel` as common.jl:262-287 does (the Hessian triplets are unchanged).
+"""
+function standard_form_arrays(nvar, ncon, jac_I::Vector{Int32}, jac_J::Vector{Int32}, jac_V::Vector{Float64},
+                              c::Vector{Float64}, lvar::Vector{Float64}, uvar::Vector{Float64}, lcon::Vector{Float64},
+                              ucon::Vector{Float64}, x0::Vector{Float64}, y0::Vector{Float64}; device = 0)
+    nnzj = length(jac_V)
+    cap_var = 2 * (nvar + ncon); cap_con = nvar + 2 * ncon; cap_nz = nnzj + ncon + 2 * (nvar + ncon)
+    oI = Vector{Int32}(undef, cap_nz); oJ = Vector{Int32}(undef, cap_nz); oV = Vector{Float64}(undef, cap_nz)
+    oc = Vector{Float64}(undef, cap_var); olv = Vector{Float64}(undef, cap_var); ouv = Vector{Float64}(undef, cap_var)
+    ox0 = Vector{Float64}(undef, cap_var)
+    olc = Vector{Float64}(undef, cap_con); ouc = Vector{Float64}(undef, cap_con); oy0 = Vector{Float64}(undef, cap_con)
+    ns = Ref{Int32}(0); nw = Ref{Int32}(0); launches = Ref{Int64}(0)
+    rc = ccall((:madipm_standard_form_qp, LIB), Int32,
+               (Int32, Int32, Int32, Int64, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64},
+                Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
+               Int32(device), Int32(nvar), Int32(ncon), Int64(nnzj), jac_I, jac_J, jac_V, c, lvar, uvar, lcon, ucon, x0, y0, ns, nw,
+               oI, oJ, oV, oc, olv, ouv, ox0, olc, ouc, oy0, launches)
+    rc == MADIPM_OK || error("madipm_standard_form_qp: " * unsafe_string(ccall((:madipm_scale_last_error, LIB), Cstring, ())))
+    nv = nvar + ns[] + nw[]; nc = ncon + nw[]; nz = nnzj + ns[] + 2 * nw[]
+    return (nvar = nv, ncon = nc, ns = Int(ns[]), nw = Int(nw[]), jac_I = oI[1:nz], jac_J = oJ[1:nz], jac_V = oV[1:nz],
+            c = oc[1:nv], lvar = olv[1:nv], uvar = ouv[1:nv], x0 = ox0[1:nv], lcon = olc[1:nc], ucon = ouc[1:nc], y0 = oy0[1:nc])
+end
+
 # ---- hang guards (see the header) -----------------------------------------------------------------------------------------
 function barrier_state(h::Handle)
     out = Vector{Int64}(undef, 8)

@@ -155,6 +155,8 @@ _SIGNATURES = {
     "madipm_scale_qp": (None, [C.POINTER(ScaleOptions), C.c_int32, C.c_int32, C.c_int64, _P32, _P32, _PD, C.c_int64, _P32, _P32, _PD,
                                _PD, _PD, _PD, _PD, _PD, _PD, _PD, _PD, _PD, _P32, _PD], C.c_int32),
     "madipm_scale_last_error": (None, [], C.c_char_p),
+    "madipm_standard_form_qp": (None, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, _P32, _P32, _PD, _PD, _PD, _PD, _PD, _PD, _PD, _PD,
+                                       _P32, _P32, _P32, _P32, _PD, _PD, _PD, _PD, _PD, _PD, _PD, _PD, _P64], C.c_int32),
 }
 
 EXPORTED_SYMBOLS = sorted(_SIGNATURES)

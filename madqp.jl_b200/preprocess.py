@@ -1,6 +1,11 @@
-"""scale_qp (/root/reference/scripts/common.jl:46-100) through the C ABI: Ruiz equilibration of the constraint matrix
-on the device (`madipm_scale_qp`, csrc/preprocess.cu) and the rescaled model.  There is no CPU fallback: without a
-GPU the call raises.  The numpy restatement used by the tests is `oracle.oracle.scale_qp`."""
+"""Preprocessing of scripts/common.jl through the C ABI, on the device:
+  * scale_qp (/root/reference/scripts/common.jl:46-100): Ruiz equilibration of the constraint matrix and the rescaled
+    model (`madipm_scale_qp`, csrc/preprocess.cu);
+  * standard_form_qp (/root/reference/scripts/common.jl:156-288): slack variables for the inequality rows, range bounds
+    moved into equality rows (`madipm_standard_form_qp`, same file).
+There is no CPU fallback: without a GPU both calls raise.  `standard_form_qp_host` is the same reformulation in numpy for
+callers that hold the model on the host anyway (the reference's own is host code); it is never chosen automatically.
+The loop-for-loop restatements the tests compare against are `oracle.oracle.scale_qp` / `oracle.oracle.standard_form_qp`."""
 from __future__ import annotations
 
 import ctypes as C
@@ -41,8 +46,44 @@ def scale_qp(qp, max_iter=None, tol=None, device=0):
     return out, Dr, Dc, dict(sweeps=sweeps.value, err=err.value, launches=int(opt.launches))
 
 
-def standard_form_qp(qp):
-    """standard_form_qp (/root/reference/scripts/common.jl:129-288), host side like the reference's: slack variables
+def standard_form_qp(qp, device=0, info=None):
+    """standard_form_qp (/root/reference/scripts/common.jl:156-288) on the device (`madipm_standard_form_qp`): the model's
+    bounds and COO triplets go up, the bounds are classified, one prefix sum ranks the inequality rows and the range
+    bounds, the appended entries / new bounds are written at the ranked positions, and the reformulated model comes
+    back -- entry for entry the reference's ([A | slack | range pairs], common.jl:212-233).  Raises without a GPU.
+    `info` (a dict) receives ns, nw and the number of kernels launched."""
+    lib = _lib.load()
+    n, m = int(qp.nvar), int(qp.ncon)
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    i32 = lambda a: np.ascontiguousarray(np.asarray(a) + 1, dtype=np.int32)
+    jI, jJ, jV = i32(qp.A_rows), i32(qp.A_cols), f(qp.A_vals)
+    c, lvar, uvar, x0 = f(qp.c), f(qp.lvar), f(qp.uvar), f(qp.x0)
+    lcon, ucon, y0 = f(qp.lcon), f(qp.ucon), f(qp.y0)
+    nnzj = int(jV.size)
+    cap_var, cap_con, cap_nz = 2 * (n + m), n + 2 * m, nnzj + m + 2 * (n + m)
+    oI, oJ, oV = np.empty(cap_nz, dtype=np.int32), np.empty(cap_nz, dtype=np.int32), np.empty(cap_nz)
+    oc, olv, ouv, ox0 = (np.empty(cap_var) for _ in range(4))
+    olc, ouc, oy0 = (np.empty(cap_con) for _ in range(3))
+    ns, nw, launches = C.c_int32(0), C.c_int32(0), C.c_int64(0)
+    rc = lib.madipm_standard_form_qp(device, n, m, nnzj, _lib._p32(jI), _lib._p32(jJ), _lib._pd(jV), _lib._pd(c), _lib._pd(lvar),
+                                     _lib._pd(uvar), _lib._pd(lcon), _lib._pd(ucon), _lib._pd(x0), _lib._pd(y0), C.byref(ns),
+                                     C.byref(nw), _lib._p32(oI), _lib._p32(oJ), _lib._pd(oV), _lib._pd(oc), _lib._pd(olv),
+                                     _lib._pd(ouv), _lib._pd(ox0), _lib._pd(olc), _lib._pd(ouc), _lib._pd(oy0), C.byref(launches))
+    if rc != _lib.OK:
+        raise _lib.MadIPMError(rc, lib.madipm_scale_last_error().decode())
+    ns, nw = ns.value, nw.value
+    nvar, ncon, nz = n + ns + nw, m + nw, nnzj + ns + 2 * nw
+    if info is not None:
+        info.update(ns=ns, nw=nw, launches=int(launches.value))
+    return dataclasses.replace(
+        qp, name=qp.name + "-std", nvar=nvar, ncon=ncon, c=oc[:nvar].copy(),
+        A_rows=(oI[:nz] - 1).astype(np.asarray(qp.A_rows).dtype), A_cols=(oJ[:nz] - 1).astype(np.asarray(qp.A_cols).dtype),
+        A_vals=oV[:nz].copy(), lcon=olc[:ncon].copy(), ucon=ouc[:ncon].copy(), lvar=olv[:nvar].copy(), uvar=ouv[:nvar].copy(),
+        x0=ox0[:nvar].copy(), y0=oy0[:ncon].copy(), meta=dict(qp.meta, standard_form=True))
+
+
+def standard_form_qp_host(qp):
+    """standard_form_qp (/root/reference/scripts/common.jl:129-288) in numpy, host side like the reference's: slack variables
     s = A x for the inequality rows (columns n+1..n+ns, entries -1), and every RANGE bound of x or s moved into an
     equality row  x_i + w_k = xu_i  with a new nonnegative variable w_k (columns n+ns+1..).  Index and copy work only,
     no arithmetic: the result is the reference's model entry for entry (COO order [A | slack | range pairs]).
