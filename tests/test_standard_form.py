@@ -164,5 +164,5 @@ def test_device_standard_form_then_solve():
     std = preprocess.standard_form_qp(scaled)
     assert (std.lcon == std.ucon).all()
     got = MPCSolver(std, regularization=FixedRegularization(1e-8, -1e-8)).solve()
-    assert got.status == "SOLVE_SUCCEEDED"
-    assert abs(ref.objective - got.objective) <= 1e-6 * max(1.0, abs(ref.objective))
+    assert got.status[0] == "SOLVE_SUCCEEDED"
+    assert abs(ref.objective - got.objective[0]) <= 1e-6 * max(1.0, abs(ref.objective))
