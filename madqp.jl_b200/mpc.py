@@ -20,6 +20,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import Handle, MadIPMError
+from .preprocess import make_parameter
 
 # MadNLP.Status names used by the reference (solver.jl:279-283, 359-390)
 SOLVE_SUCCEEDED = "SOLVE_SUCCEEDED"
@@ -123,7 +124,8 @@ class IndexConstraints:
 def get_index_constraints(lvar, uvar, lcon, ucon):
     """MadNLP.get_index_constraints (call site /root/reference/src/structure.jl:95-102); 0-based."""
     if np.any(lvar == uvar):
-        raise NotImplementedError("fixed variables are removed by MadNLP's MakeParameter before the hot path")
+        raise NotImplementedError("fixed variables reach get_index_constraints: apply preprocess.make_parameter first "
+                                  "(MPCSolver does, fixed_variable_treatment = MakeParameter)")
     ind_eq = np.nonzero(lcon == ucon)[0]
     ind_ineq = np.nonzero(lcon != ucon)[0]
     xl = np.concatenate([lvar, lcon[ind_ineq]])
@@ -196,6 +198,14 @@ class MPCSolver:
 
     def __init__(self, qp, **kwargs):
         self.qps = list(qp) if isinstance(qp, (list, tuple)) else [qp]
+        # fixed_variable_treatment = MakeParameter (utils.jl:81): variables with lvar == uvar leave the model before the hot path
+        self.nx_full = self.qps[0].nvar
+        reduced = [make_parameter(q) for q in self.qps]
+        self._fixed, self._free = reduced[0][1], reduced[0][2]
+        if any(not np.array_equal(r[1], self._fixed) for r in reduced[1:]):
+            raise ValueError("batched instances must fix the same variables")
+        self._x_fixed = np.stack([r[3] for r in reduced])
+        self.qps = [r[0] for r in reduced]
         q0 = self.qps[0]
         self.B = len(self.qps)
         self.opt = IPMOptions(**kwargs)
@@ -672,9 +682,15 @@ class MPCSolver:
             self.con_scale = self.h.vec_get("CON_SCALE", out=self._res["CON_SCALE"].a).reshape(self.B, -1).copy()
             self.d2h_bytes += self.con_scale.nbytes
         self.total_time = time.perf_counter() - t0
+        sol = x[:, :self.nx].copy()
+        if self._fixed.size:                                   # the parameters back in their places
+            full = np.empty((self.B, self.nx_full))
+            full[:, self._free] = sol
+            full[:, self._fixed] = self._x_fixed
+            sol = full
         return ExecutionStats(
             status=list(self.status), iter=self.iters.copy(), objective=self.obj_val / self.obj_scale,
-            solution=x[:, :self.nx].copy(), multipliers=y * self.con_scale / self.obj_scale[:, None],
+            solution=sol, multipliers=y * self.con_scale / self.obj_scale[:, None],
             inf_pr=self.inf_pr.copy(), inf_du=self.inf_du.copy(), inf_compl=self.inf_compl.copy(),
             total_time=self.total_time, init_time=self.init_time)
 

@@ -118,3 +118,40 @@ def standard_form_qp_host(qp):
         qp, name=qp.name + "-std", nvar=nvar, ncon=ncon, c=np.concatenate([qp.c, z]), A_rows=A_rows.astype(qp.A_rows.dtype),
         A_cols=A_cols.astype(qp.A_cols.dtype), A_vals=A_vals, lcon=lcon_, ucon=ucon_, lvar=lvar_, uvar=uvar_,
         x0=np.concatenate([qp.x0, z]), y0=np.concatenate([qp.y0, np.zeros(nw)]), meta=dict(qp.meta, standard_form=True))
+
+
+def make_parameter(qp):
+    """fixed_variable_treatment = MakeParameter (/root/reference/src/utils.jl:81; MadNLP's SparseCallback, un-vendored):
+    variables with lvar == uvar are parameters, not unknowns.  Host-side index work before the hot path, like the
+    reference's: the equivalent model in the free variables (c_free += H[free, fixed] x_f, c0 += c_f' x_f + x_f' H_ff x_f / 2,
+    lcon / ucon -= A[:, fixed] x_f, the fixed rows / columns dropped from the COO triplets in their order).
+    Returns (reduced model, fixed, free, x_fixed) with 0-based index arrays; the model itself when nothing is fixed."""
+    n = qp.nvar
+    lvar, uvar = np.asarray(qp.lvar, dtype=np.float64), np.asarray(qp.uvar, dtype=np.float64)
+    is_fixed = lvar == uvar
+    fixed, free = np.flatnonzero(is_fixed), np.flatnonzero(~is_fixed)
+    if fixed.size == 0:
+        return qp, fixed, free, np.zeros(0)
+    xfull = np.where(is_fixed, lvar, 0.0)                         # x_fixed scattered, zero elsewhere
+    new_index = np.cumsum(~is_fixed) - 1
+    Hr, Hc, Hv = np.asarray(qp.H_rows), np.asarray(qp.H_cols), np.asarray(qp.H_vals, dtype=np.float64)
+    Ar, Ac, Av = np.asarray(qp.A_rows), np.asarray(qp.A_cols), np.asarray(qp.A_vals, dtype=np.float64)
+    c = np.asarray(qp.c, dtype=np.float64).copy()
+    c0 = float(qp.c0) + float(np.dot(c[fixed], lvar[fixed]))
+    rf, cf = is_fixed[Hr], is_fixed[Hc]
+    both = rf & cf
+    c0 += float(np.sum(np.where(Hr[both] == Hc[both], 0.5, 1.0) * Hv[both] * xfull[Hr[both]] * xfull[Hc[both]]))
+    only_r, only_c = rf & ~cf, cf & ~rf                           # lower triangle of a symmetric matrix: both orientations
+    np.add.at(c, Hc[only_r], Hv[only_r] * xfull[Hr[only_r]])
+    np.add.at(c, Hr[only_c], Hv[only_c] * xfull[Hc[only_c]])
+    keep_h = ~rf & ~cf
+    af = is_fixed[Ac]
+    shift = np.bincount(Ar[af], weights=Av[af] * xfull[Ac[af]], minlength=qp.ncon)[:qp.ncon] if qp.ncon else np.zeros(0)
+    red = dataclasses.replace(
+        qp, name=qp.name + "-free", nvar=int(free.size), c=c[free], c0=c0,
+        H_rows=new_index[Hr[keep_h]].astype(Hr.dtype), H_cols=new_index[Hc[keep_h]].astype(Hc.dtype), H_vals=Hv[keep_h],
+        A_rows=Ar[~af], A_cols=new_index[Ac[~af]].astype(Ac.dtype), A_vals=Av[~af],
+        lcon=np.asarray(qp.lcon, dtype=np.float64) - shift, ucon=np.asarray(qp.ucon, dtype=np.float64) - shift,
+        lvar=lvar[free], uvar=uvar[free], x0=np.asarray(qp.x0, dtype=np.float64)[free],
+        meta=dict(qp.meta, make_parameter=int(fixed.size)))
+    return red, fixed, free, lvar[fixed]

@@ -315,11 +315,64 @@ class IndexConstraints:
     ind_uub: np.ndarray
 
 
+def make_parameter(qp):
+    """fixed_variable_treatment = MakeParameter (/root/reference/src/utils.jl:81, the default for the K2 systems;
+    implemented in MadNLP's SparseCallback, un-vendored, [RECALLED]): a variable with lvar == uvar is a parameter of the
+    model, not an unknown -- its direction is identically zero, the entries of its Jacobian column and Hessian row / column
+    leave the KKT system, and its value enters the constraints and the gradient as a constant.  Restated as the equivalent
+    model in the free variables only, loop for loop over the COO entries:
+        c_free += H[free, fixed] x_fixed,  c0 += c_fixed' x_fixed + 1/2 x_fixed' H[fixed, fixed] x_fixed,
+        (lcon, ucon) -= A[:, fixed] x_fixed.
+    Returns (reduced model, fixed indices, free indices, x_fixed), 0-based; (qp, empty, all, empty) without fixed variables."""
+    import dataclasses
+    n = qp.nvar
+    lvar, uvar = np.asarray(qp.lvar, dtype=np.float64), np.asarray(qp.uvar, dtype=np.float64)
+    fixed = [i for i in range(n) if lvar[i] == uvar[i]]
+    free = [i for i in range(n) if not lvar[i] == uvar[i]]
+    if not fixed:
+        return qp, np.zeros(0, dtype=np.int64), np.arange(n), np.zeros(0)
+    new_index = {i: k for k, i in enumerate(free)}
+    is_fixed = set(fixed)
+    xf = {i: lvar[i] for i in fixed}
+    c = np.asarray(qp.c, dtype=np.float64).copy()
+    c0 = float(qp.c0)
+    for i in fixed:
+        c0 += c[i] * xf[i]
+    Hr, Hc, Hv = [], [], []
+    for r, cc, v in zip(qp.H_rows, qp.H_cols, qp.H_vals):              # lower triangle of a symmetric matrix
+        r, cc, v = int(r), int(cc), float(v)
+        if r in is_fixed and cc in is_fixed:
+            c0 += (0.5 if r == cc else 1.0) * v * xf[r] * xf[cc]
+        elif r in is_fixed:
+            c[cc] += v * xf[r]
+        elif cc in is_fixed:
+            c[r] += v * xf[cc]
+        else:
+            Hr.append(new_index[r]); Hc.append(new_index[cc]); Hv.append(v)
+    shift = np.zeros(qp.ncon)
+    Ar, Ac, Av = [], [], []
+    for r, cc, v in zip(qp.A_rows, qp.A_cols, qp.A_vals):
+        r, cc, v = int(r), int(cc), float(v)
+        if cc in is_fixed:
+            shift[r] += v * xf[cc]
+        else:
+            Ar.append(r); Ac.append(new_index[cc]); Av.append(v)
+    idx = lambda a, like: np.array(a, dtype=np.asarray(like).dtype)
+    free_a = np.array(free, dtype=np.int64)
+    red = dataclasses.replace(
+        qp, name=qp.name + "-free", nvar=len(free), c=c[free_a], c0=c0, H_rows=idx(Hr, qp.H_rows), H_cols=idx(Hc, qp.H_cols),
+        H_vals=np.array(Hv, dtype=np.float64), A_rows=idx(Ar, qp.A_rows), A_cols=idx(Ac, qp.A_cols),
+        A_vals=np.array(Av, dtype=np.float64), lcon=np.asarray(qp.lcon, dtype=np.float64) - shift,
+        ucon=np.asarray(qp.ucon, dtype=np.float64) - shift, lvar=lvar[free_a], uvar=uvar[free_a],
+        x0=np.asarray(qp.x0, dtype=np.float64)[free_a], meta=dict(qp.meta, make_parameter=len(fixed)))
+    return red, np.array(fixed, dtype=np.int64), free_a, np.array([xf[i] for i in fixed])
+
+
 def get_index_constraints(lvar, uvar, lcon, ucon):
     """MadNLP.get_index_constraints [RECALLED]; 0-based results.  Call site
-    /root/reference/src/structure.jl:95-102."""
+    /root/reference/src/structure.jl:95-102.  (Fixed variables never get here: make_parameter removed them.)"""
     if np.any(lvar == uvar):
-        raise NotImplementedError("fixed variables (MakeParameter) are outside the hot-path scope")
+        raise NotImplementedError("fixed variables reach get_index_constraints: apply make_parameter first")
     ind_eq = np.nonzero(lcon == ucon)[0]
     ind_ineq = np.nonzero(lcon != ucon)[0]
     xl = np.concatenate([lvar, lcon[ind_ineq]])
@@ -368,6 +421,8 @@ class MPCOracle:
 
     def __init__(self, qp, perm=None, **kw):
         self.opt = Options(**kw)
+        self.qp_full = qp
+        qp, self._fixed, self._free, self._x_fixed = make_parameter(qp)        # utils.jl:81 (MakeParameter)
         self.qp = qp
         opt = self.opt
         ic = get_index_constraints(qp.lvar, qp.uvar, qp.lcon, qp.ucon)
@@ -1024,7 +1079,12 @@ class MPCOracle:
 
     @property
     def solution(self):
-        return self.x[:self.nx].copy()
+        if self._fixed.size == 0:
+            return self.x[:self.nx].copy()
+        full = np.empty(self.qp_full.nvar)
+        full[self._free] = self.x[:self.nx]
+        full[self._fixed] = self._x_fixed
+        return full
 
     @property
     def multipliers(self):
