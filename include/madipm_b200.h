@@ -217,6 +217,13 @@ int32_t madipm_is_factorized(madipm_handle* h, int32_t* flags);
  * explains 1e8).  0 switches a test off; (0, 0) is the reference's exact semantics and the default for the normal
  * equations, whose pivots and factor entries legitimately span many orders of magnitude (Sigma does). */
 int32_t madipm_set_pivot_checks(madipm_handle* h, double tiny, double growth);
+/* Scheduling of the small-front tree kernels (the numeric factorisation K3 and the triangular sweeps K4, no reference
+ * counterpart: LDLFactorizations is sequential).  0: a grid-wide barrier between two heights of the supernodal elimination
+ * tree; 1: dataflow -- every task waits for its own children (parent in the backward sweep) through per-task counters in
+ * global memory, no barrier between heights.  Same tasks, same arithmetic, bit-identical results.  Only for workloads whose
+ * fronts all fit one block (no multi-block fronts); *in_effect (may be NULL) says whether the launches will use it.
+ * Default: environment variable MADIPM_TREE_DATAFLOW. */
+int32_t madipm_set_tree_dataflow(madipm_handle* h, int32_t on, int32_t* in_effect);
 /* inertia of the last factorisation of instance `inst`: signs of D */
 int32_t madipm_inertia(madipm_handle* h, int32_t inst, int64_t* n_pos, int64_t* n_zero, int64_t* n_neg);
 /* solve!(linear_solver, rhs): in-place solve with the current factors on a device vector of

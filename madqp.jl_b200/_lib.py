@@ -151,6 +151,7 @@ _SIGNATURES = {
     "madipm_phase_factor_predictor": ([C.c_double, C.c_double, _PD, _PD], C.c_int32),
     "madipm_phase_corrector": ([_PD, _PD, _PD, _PD], C.c_int32),
     "madipm_phase_iteration": ([C.POINTER(IterOptions), _P32, _PD, _P32], C.c_int32),
+    "madipm_set_tree_dataflow": ([C.c_int32, _P32], C.c_int32),
     "madipm_default_scale_options": (None, [C.POINTER(ScaleOptions)], None),
     "madipm_scale_qp": (None, [C.POINTER(ScaleOptions), C.c_int32, C.c_int32, C.c_int64, _P32, _P32, _PD, C.c_int64, _P32, _P32, _PD,
                                _PD, _PD, _PD, _PD, _PD, _PD, _PD, _PD, _PD, _P32, _PD], C.c_int32),
@@ -412,6 +413,12 @@ class Handle:
 
     def set_pivot_checks(self, tiny, growth):
         self._check(self.lib.madipm_set_pivot_checks(self._h, float(tiny), float(growth)))
+
+    def set_tree_dataflow(self, on=True):
+        """Dependency counters instead of height barriers in the small-front tree kernels; returns whether it is in effect."""
+        eff = C.c_int32(0)
+        self._check(self.lib.madipm_set_tree_dataflow(self._h, int(bool(on)), C.byref(eff)))
+        return bool(eff.value)
 
     def is_factorized(self):
         f = np.zeros(self.batch, dtype=np.int32)

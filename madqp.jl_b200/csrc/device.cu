@@ -43,6 +43,14 @@ struct DeviceState {
     size_t smem_tree = 0;
     int tree_occ[4] = {0, 0, 0, 0};
     int* tickets[3] = {nullptr, nullptr, nullptr};
+    // dataflow scheduling of the k_tree launches (kernels_tree.cuh, DfView): dependency counters instead of height barriers
+    bool dataflow = false;             // MADIPM_TREE_DATAFLOW / madipm_set_tree_dataflow; only without multi-block fronts and per-height launches
+    bool dataflow_ok = false;          // the schedule allows it
+    int* task_parent = nullptr;        // [ntasks]
+    int* dep = nullptr;                // [batch][ntasks]
+    int ntasks = 0;
+    std::vector<int> phase_ptr;        // first task of every height (+ end)
+    int tree_occ_df[4] = {0, 0, 0, 0};
     bool use_front = false;            // the heights near the root are factorised by k_front (kernels_front.cuh) instead of k_tree_top
     FrontLayout front_lo = {};
     size_t smem_front = 0;
@@ -252,9 +260,13 @@ struct Timer {
 std::string describe_tree_debug(const DeviceState* d) {
     const TreeDebug g = d->tree_dbg ? *d->tree_dbg : TreeDebug{};
     if (!g.aborted) return "no grid barrier reported a timeout";
-    static const char* kn[] = {"k_tree", "k_tree_top", "k_front", "?"};
+    static const char* kn[] = {"k_tree", "k_tree_top", "k_front", "k_tree_df"};
     static const char* on[] = {"factor", "forward", "backward"};
     char buf[320];
+    if ((g.kernel & 3) == 3)
+        std::snprintf(buf, sizeof(buf), "dependency wait timed out: k_tree_df<%s> in height %d, block %u of %u saw %u of %u signals, for %.0f ms",
+                      on[g.op == 3 ? 0 : g.op % 3], g.phase, g.block, g.grid, g.seen, g.target, g.waited_ns / 1e6);
+    else
     std::snprintf(buf, sizeof(buf), "grid barrier timed out: %s<%s> after height %d, block %u of %u saw %u arrivals, waited for %u, for %.0f ms",
                   kn[g.kernel & 3], on[g.op == 3 ? 0 : g.op % 3], g.phase, g.block, g.grid, g.seen, g.target, g.waited_ns / 1e6);
     return buf;
@@ -455,6 +467,7 @@ int32_t launch_tree(madipm_handle* h, const DeviceState::TreeSeg& sg) {
     // barrier counters (slot kSyncBar of the first height each launch walks)
     if (sg.ph1 > sg.ph0)
         CUDA_OK(h, cudaMemsetAsync(tickets + kSyncStride * sg.ph0, 0, sizeof(int) * kSyncStride * (sg.ph1 - sg.ph0), d->stream));
+    const bool df_fault = d->inject_barrier_fault && d->dataflow && d->dataflow_ok;   // ... or no dependency counter can
     if (d->inject_barrier_fault) {     // counters start at 0x80000000: no barrier of this segment can complete
         d->inject_barrier_fault = false;
         for (int ph : {sg.ph0, sg.split})
@@ -465,6 +478,17 @@ int32_t launch_tree(madipm_handle* h, const DeviceState::TreeSeg& sg) {
         if (sg.split <= sg.ph0 || sg.grid[OP] <= 0) return MADIPM_OK;
         int b = reverse ? sg.split - 1 : sg.ph0, e = reverse ? sg.ph0 - 1 : sg.split, step = reverse ? -1 : 1;
         T.bar = reinterpret_cast<unsigned*>(tickets + kSyncStride * sg.ph0 + kSyncBar);
+        if (d->dataflow && d->dataflow_ok) {             // dependency counters instead of height barriers (kernels_tree.cuh, DfView)
+            DfView D{d->dep, d->task_parent, d->ntasks, d->phase_ptr[sg.split]};
+            CUDA_OK(h, cudaMemsetAsync(d->dep, df_fault ? 0x80 : 0, sizeof(int) * static_cast<size_t>(d->B) * d->ntasks, d->stream));
+            const int grid = std::min(sg.grid[OP], d->tree_occ_df[OP] * d->num_sms);
+            void* dargs[] = {&T, &D, &b, &e, &step};
+            CUDA_OK(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_tree_df<OP>), dim3(grid), dim3(kTreeThreads), dargs,
+                                                   d->smem_tree, d->stream));
+            ++h->launches;
+            h->last_launch = "k_tree_df (cooperative)";
+            return MADIPM_OK;
+        }
         void* args[] = {&T, &b, &e, &step};
         CUDA_OK(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_tree<OP>), dim3(sg.grid[OP]), dim3(kTreeThreads), args,
                                                d->smem_tree, d->stream));
@@ -705,6 +729,20 @@ int32_t device_create(madipm_handle* h) {
         CUDA_OK(h, cudaMemcpy(d->sn_meta, meta.data(), meta.size() * sizeof(SnMeta), cudaMemcpyHostToDevice));
         if ((rc = dev_alloc(h, &d->child_rec, crec.size()))) return rc;
         CUDA_OK(h, cudaMemcpy(d->child_rec, crec.data(), crec.size() * sizeof(ChildRec), cudaMemcpyHostToDevice));
+        // dataflow scheduling: the task of every supernode's parent, one dependency counter per (instance, task)
+        d->ntasks = static_cast<int>(s.task_sn.size());
+        std::vector<int> sn_parent(std::max(1, s.nsuper), -1), task_of(std::max(1, s.nsuper), -1), tpar(std::max<size_t>(1, s.task_sn.size()), -1);
+        for (int sn = 0; sn < s.nsuper; ++sn)
+            for (int q = s.child_ptr[sn]; q < s.child_ptr[sn + 1]; ++q) sn_parent[s.child_idx[q]] = sn;
+        for (size_t q = 0; q < s.task_sn.size(); ++q) task_of[s.task_sn[q]] = static_cast<int>(q);
+        for (size_t q = 0; q < s.task_sn.size(); ++q) {
+            const int ps = sn_parent[s.task_sn[q]];
+            tpar[q] = ps >= 0 ? task_of[ps] : -1;
+        }
+        if ((rc = dev_alloc(h, &d->task_parent, tpar.size()))) return rc;
+        CUDA_OK(h, cudaMemcpy(d->task_parent, tpar.data(), tpar.size() * sizeof(int), cudaMemcpyHostToDevice));
+        if ((rc = dev_alloc(h, &d->dep, static_cast<size_t>(B) * std::max(1, d->ntasks)))) return rc;
+        d->phase_ptr.assign(s.phase_ptr.begin(), s.phase_ptr.end());
     }
     {
         std::vector<int32_t> pc = s.phase_cls;
@@ -772,6 +810,14 @@ int32_t device_create(madipm_handle* h) {
         CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->tree_occ[1], k_tree<1>, kTreeThreads, d->smem_tree));
         CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->tree_occ[2], k_tree<2>, kTreeThreads, d->smem_tree));
         CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->tree_occ[3], k_tree<3>, kTreeThreads, d->smem_tree));
+        CUDA_OK(h, cudaFuncSetAttribute(k_tree_df<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_tree));
+        CUDA_OK(h, cudaFuncSetAttribute(k_tree_df<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_tree));
+        CUDA_OK(h, cudaFuncSetAttribute(k_tree_df<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_tree));
+        CUDA_OK(h, cudaFuncSetAttribute(k_tree_df<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_tree));
+        CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->tree_occ_df[0], k_tree_df<0>, kTreeThreads, d->smem_tree));
+        CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->tree_occ_df[1], k_tree_df<1>, kTreeThreads, d->smem_tree));
+        CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->tree_occ_df[2], k_tree_df<2>, kTreeThreads, d->smem_tree));
+        CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->tree_occ_df[3], k_tree_df<3>, kTreeThreads, d->smem_tree));
         int top_occ = 1;
         {
             int o = 0;
@@ -839,6 +885,10 @@ int32_t device_create(madipm_handle* h) {
                 l0 = l + 1;
             }
         }
+        // dataflow scheduling needs the whole small tree below the split in ONE launch that starts at the leaves
+        d->dataflow_ok = s.n_big == 0 && !split && d->segs.size() == 1 && d->segs[0].ph0 == 0 && d->ntasks > 0;
+        for (int op = 0; op < 4; ++op) d->dataflow_ok = d->dataflow_ok && d->tree_occ_df[op] >= 1;
+        if (const char* e = std::getenv("MADIPM_TREE_DATAFLOW")) d->dataflow = e[0] == '1';
         d->tri_cap = std::min(s.max_w * s.max_w, 4096);
         d->smem_tri = (static_cast<size_t>(d->tri_cap) + 256) * sizeof(double);
     }
@@ -1451,6 +1501,14 @@ int32_t madipm_set_pivot_checks(madipm_handle* h, double tiny, double growth) {
     if (!(tiny >= 0.0) || !(growth >= 0.0)) return MADIPM_BAD_ARGUMENT;
     h->dev->tiny_pivot = tiny;
     h->dev->growth_limit = growth;
+    return MADIPM_OK;
+}
+
+int32_t madipm_set_tree_dataflow(madipm_handle* h, int32_t on, int32_t* in_effect) {
+    int32_t rc = check(h);
+    if (rc) return rc;
+    h->dev->dataflow = on != 0;
+    if (in_effect) *in_effect = (h->dev->dataflow && h->dev->dataflow_ok) ? 1 : 0;
     return MADIPM_OK;
 }
 

@@ -71,7 +71,7 @@ constexpr int kSyncBar = 4;
 // host can read it even while a kernel is still stuck.
 struct TreeDebug {
     unsigned aborted;            // 0 = never; else 1 + number of aborts seen
-    unsigned kernel;             // 0 k_tree, 1 k_tree_top
+    unsigned kernel;             // 0 k_tree, 1 k_tree_top, 2 k_front, 3 k_tree_df (a dependency wait, not a grid barrier)
     unsigned op;                 // 0 factor, 1 forward, 2 backward
     int phase;                   // height whose end-of-phase barrier gave up
     unsigned block, grid;
@@ -736,9 +736,60 @@ __device__ __forceinline__ void tree_task(const TreeView& T, const SnMeta& m, in
     else tree_backward_task<G>(T, m, inst, sm, cap, maxh);
 }
 
+// ---- dataflow scheduling (k_tree_df): no barrier between two heights --------------------------------------------------
+// The ncu stall samples of k_tree say where its time goes: blocks that ran out of tasks of a height wait at the grid barrier
+// for the slowest front of that height.  In the dataflow variant a task waits for ITS OWN
+// dependencies instead: one counter per (instance, task) in global memory, zeroed by the host before the launch.
+//   * factor / forward (children -> parent): a finished task adds 1 to its parent's counter (all stores of the group, group
+//     barrier, __threadfence, atomicAdd by one thread -- the pattern of the grid barrier); a task starts when its counter has
+//     reached its number of children (ld.acquire.gpu by one thread, group barrier, then the usual L2 reads).
+//   * backward (parent -> children): a finished task sets its own counter; a task starts when its parent's is set.  Every
+//     ancestor's part of x is visible then, because the parent waited for ITS parent before it ran (causality is transitive).
+// Tickets are still handed out height by height, class by class, and a block moves to the next height only after it has seen
+// the ticket counters of all classes of this height exhausted: every task a ticket holder waits for is held by a resident
+// group (cooperative launch) that waits only for tasks of lower heights -- no cycle, no deadlock.  Nothing about the
+// arithmetic changes (same tasks, same summation order): the results are bit-identical to the barrier schedule (tested).
+// The spin is bounded like the grid barrier's: on a timeout or a raised abort flag the group skips the task WITHOUT
+// signalling, everybody downstream gives up at once (they poll the flag), the tickets drain, the kernel ends, and the host
+// reports MADIPM_INTERNAL at its next synchronisation.
+struct DfView {
+    int* dep;                    // [batch][ntasks] dependency counters of this launch (zeroed by the host)
+    const int* task_parent;      // [ntasks] task index of the parent supernode, -1 for a root
+    int ntasks;
+    int df_end;                  // tasks [0, df_end) belong to this launch; parents beyond it are left to the next launch
+};
+
+__device__ __forceinline__ bool df_spin(const TreeView& T, const int* addr, int need, int op, int ph) {
+    unsigned polls = 0;
+    unsigned long long t0 = 0;
+    for (;;) {
+        int v;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+        if (v >= need) return true;
+        if ((polls++ & 1023u) == 0) {
+            unsigned ab;
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(ab) : "l"(T.abort_flag) : "memory");
+            if (ab) return false;
+            const unsigned long long now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > static_cast<unsigned long long>(T.spin_budget_ns)) {
+                if (atomicExch(T.abort_flag, 1u) == 0u) {
+                    TreeDebug* g = T.dbg;
+                    g->kernel = 3; g->op = op; g->phase = ph; g->block = blockIdx.x; g->grid = gridDim.x;
+                    g->seen = static_cast<unsigned>(v); g->target = static_cast<unsigned>(need); g->waited_ns = now - t0;
+                    __threadfence_system();
+                    g->aborted = g->aborted + 1u;
+                    __threadfence_system();
+                }
+                return false;
+            }
+        }
+    }
+}
+
 // one group of G threads drains the tasks of its class in phase ph (ticket counter), then returns
-template <int OP, int G, int CLS>
-__device__ __forceinline__ void run_class(const TreeView& T, double* smem, int ph) {
+template <int OP, int G, int CLS, bool DF>
+__device__ __forceinline__ void run_class(const TreeView& T, const DfView& D, double* smem, int ph) {
     const int first = __ldg(T.phase_cls + ph * 5 + CLS);
     const int n = __ldg(T.phase_cls + ph * 5 + CLS + 1) - first;
     if (n == 0) return;
@@ -753,7 +804,28 @@ __device__ __forceinline__ void run_class(const TreeView& T, double* smem, int p
         const int64_t q = *slot;
         if (q >= total) break;
         const int inst = static_cast<int>(q / n);
-        tree_task<OP, G>(T, ldg_rec(T.meta + first + static_cast<int>(q - static_cast<int64_t>(inst) * n)), inst, sm, T.cap[CLS], T.maxh[CLS]);
+        if (DF) {
+            const int tq = first + static_cast<int>(q - static_cast<int64_t>(inst) * n);
+            const SnMeta m = ldg_rec(T.meta + tq);
+            int* dep = D.dep + static_cast<int64_t>(inst) * D.ntasks;
+            const int par = __ldg(D.task_parent + tq);
+            const bool par_here = par >= 0 && par < D.df_end;
+            const int need = OP == 2 ? (par_here ? 1 : 0) : m.c1 - m.c0;
+            if (need > 0) {                               // (uniform over the group: m and par are)
+                if (t == 0) slot[1] = df_spin(T, dep + (OP == 2 ? par : tq), need, OP, ph) ? 1 : 0;
+                gsync<G>();
+                if (slot[1] == 0) continue;               // aborted: skip the task, do not signal; the loop's first barrier
+            }                                             // keeps slot[1] from being rewritten before everyone has read it
+            tree_task<OP, G>(T, m, inst, sm, T.cap[CLS], T.maxh[CLS]);
+            gsync<G>();                                   // every store of the task has been issued
+            if (t == 0) {
+                __threadfence();
+                if (OP == 2) { if (m.c1 > m.c0) atomicExch(dep + tq, 1); }      // (nobody waits for a leaf)
+                else if (par_here) atomicAdd(dep + par, 1);
+            }
+        } else {
+            tree_task<OP, G>(T, ldg_rec(T.meta + first + static_cast<int>(q - static_cast<int64_t>(inst) * n)), inst, sm, T.cap[CLS], T.maxh[CLS]);
+        }
     }
 }
 
@@ -767,13 +839,29 @@ k_tree(TreeView T, int ph_begin, int ph_end, int step) {
     extern __shared__ double2 tree_smem2[];
     double* smem = reinterpret_cast<double*>(tree_smem2);
     unsigned target = 0;
+    const DfView D{};
     for (int ph = ph_begin; ph != ph_end; ph += step) {
         if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<volatile unsigned*>(&T.dbg->progress) = (0u << 24) | (OP << 16) | ph;
-        run_class<OP, 256, 0>(T, smem, ph);
-        run_class<OP, 128, 1>(T, smem, ph);
-        run_class<OP, 64, 2>(T, smem, ph);
-        run_class<OP, 32, 3>(T, smem, ph);
+        run_class<OP, 256, 0, false>(T, D, smem, ph);
+        run_class<OP, 128, 1, false>(T, D, smem, ph);
+        run_class<OP, 64, 2, false>(T, D, smem, ph);
+        run_class<OP, 32, 3, false>(T, D, smem, ph);
         if (ph + step != ph_end && !grid_barrier(T, target, 0, OP, ph)) return;
+    }
+}
+
+// the same walk without the barrier between two heights: every task waits for its own dependencies (see DfView)
+template <int OP>
+__global__ void __launch_bounds__(kTreeThreads, MADIPM_TREE_BLOCKS)
+k_tree_df(TreeView T, DfView D, int ph_begin, int ph_end, int step) {
+    extern __shared__ double2 tree_smem2[];
+    double* smem = reinterpret_cast<double*>(tree_smem2);
+    for (int ph = ph_begin; ph != ph_end; ph += step) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<volatile unsigned*>(&T.dbg->progress) = (3u << 24) | (OP << 16) | ph;
+        run_class<OP, 256, 0, true>(T, D, smem, ph);
+        run_class<OP, 128, 1, true>(T, D, smem, ph);
+        run_class<OP, 64, 2, true>(T, D, smem, ph);
+        run_class<OP, 32, 3, true>(T, D, smem, ph);
     }
 }
 

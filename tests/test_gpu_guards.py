@@ -90,3 +90,69 @@ def test_bench_supervisor_retries_a_hung_attempt(tmp_path):
     line = json.loads(lines[0])
     assert "error" not in line and line["attempts"] == 2 and len(line["failed_attempts"]) == 1, line
     assert line["value"] > 0 and line["converged"]
+
+
+# ---- dataflow scheduling (k_tree_df): dependency counters instead of height barriers ---------------------------------
+
+@pytest.mark.parametrize("where", ["factor", "solve"])
+def test_broken_dependency_counter_is_an_error_not_a_hang(where, monkeypatch):
+    monkeypatch.setenv("MADIPM_BARRIER_TIMEOUT_MS", "300")
+    s = _factor_ready(P.banded_qp(seed=1, n=40000, m=20000))
+    h = s.h
+    assert h.set_tree_dataflow(True)
+    assert h.factorize() == 0
+    good = h.inertia()
+    t0 = time.perf_counter()
+    h.debug_inject_barrier_fault()                                # every counter starts negative: no task with children can start
+    if where == "factor":
+        with pytest.raises(_lib.MadIPMError) as ei:
+            h.factorize()
+    else:
+        h.set_predictive_rhs()
+        with pytest.raises(_lib.MadIPMError) as ei:
+            h.kkt_solve("P")
+            h.synchronize()
+    dt = time.perf_counter() - t0
+    assert ei.value.code == _lib.INTERNAL
+    assert "dependency wait timed out" in str(ei.value)
+    assert dt < 30.0, dt
+    h.build_kkt()                                                 # the handle is usable again
+    assert h.factorize() == 0
+    assert h.inertia() == good
+    s.close()
+
+
+@pytest.mark.parametrize("maker,kw,opts", [
+    (P.banded_qp, dict(seed=1, n=40000, m=20000), dict()),
+    (P.banded_qp, dict(seed=2, n=20000, m=10000), dict(max_ncorr=3)),
+    (P.maros_meszaros_like, dict(seed=0, n=2000, m=1000, nnz=10000), dict(kkt_system="K2.5")),
+    (P.sparse_lp, dict(seed=4, n=6000, m=3000), dict()),
+])
+def test_dataflow_schedule_is_bit_identical_to_the_barrier_schedule(maker, kw, opts):
+    """Same tasks, same summation order: whole solves agree bit for bit wherever the dataflow launches are in effect."""
+    qp = maker(**kw)
+    ref = MPCSolver(qp, regularization=FixedRegularization(1e-8, -1e-8), **opts)
+    a = ref.solve()
+    ref.close()
+    s = MPCSolver(qp, regularization=FixedRegularization(1e-8, -1e-8), **opts)
+    if not s.h.set_tree_dataflow(True):
+        s.close()
+        pytest.skip("multi-block fronts: the dataflow launches are not in effect")
+    b = s.solve()
+    s.close()
+    assert a.status == b.status and np.array_equal(a.iter, b.iter)
+    assert np.array_equal(a.objective, b.objective) and np.array_equal(a.solution, b.solution)
+    assert np.array_equal(a.multipliers, b.multipliers)
+
+
+def test_dataflow_schedule_batch_is_bit_identical():
+    qps = [P.small_qp(instance=i) for i in range(64)]
+    outs = []
+    for on in (False, True):
+        s = MPCSolver(qps, regularization=FixedRegularization(1e-8, -1e-8))
+        assert s.h.set_tree_dataflow(on) == on
+        outs.append(s.solve())
+        s.close()
+    a, b = outs
+    assert a.status == b.status and np.array_equal(a.iter, b.iter)
+    assert np.array_equal(a.objective, b.objective) and np.array_equal(a.solution, b.solution)
