@@ -37,14 +37,14 @@ struct DeviceState {
     // small supernodes: persistent height-scheduled kernels (kernels_tree.cuh)
     // heights [ph0, split) in one cooperative launch of k_tree, heights [split, ph1) (at most one task per SM) in one
     // launch of k_tree_top; a height with big supernodes ends a segment
-    struct TreeSeg { int ph0, split, ph1, grid[4], grid_top; };   // grid[OP], OP 3 = factor + forward (kernels_tree.cuh)
+    struct TreeSeg { int ph0, split, ph1, grid[4], grid_top; bool df_sweeps; };   // grid[OP], OP 3 = factor + forward (kernels_tree.cuh)
     std::vector<TreeSeg> segs;
     int tree_maxw = 0;
     size_t smem_tree = 0;
     int tree_occ[4] = {0, 0, 0, 0};
     int* tickets[3] = {nullptr, nullptr, nullptr};
     // dataflow scheduling of the k_tree launches (kernels_tree.cuh, DfView): dependency counters instead of height barriers
-    bool dataflow = false;             // MADIPM_TREE_DATAFLOW / madipm_set_tree_dataflow; only without multi-block fronts and per-height launches
+    bool dataflow = false;             // on by default (device_create), MADIPM_TREE_DATAFLOW=0 / madipm_set_tree_dataflow switch it off; only without multi-block fronts and per-height launches
     bool dataflow_ok = false;          // the schedule allows it
     int* task_parent = nullptr;        // [ntasks]
     int* dep = nullptr;                // [batch][ntasks]
@@ -467,7 +467,7 @@ int32_t launch_tree(madipm_handle* h, const DeviceState::TreeSeg& sg) {
     // barrier counters (slot kSyncBar of the first height each launch walks)
     if (sg.ph1 > sg.ph0)
         CUDA_OK(h, cudaMemsetAsync(tickets + kSyncStride * sg.ph0, 0, sizeof(int) * kSyncStride * (sg.ph1 - sg.ph0), d->stream));
-    const bool df_fault = d->inject_barrier_fault && d->dataflow && d->dataflow_ok;   // ... or no dependency counter can
+    const bool df_fault = d->inject_barrier_fault && d->dataflow && d->dataflow_ok && (OP == 0 || OP == 3 || sg.df_sweeps);   // ... or no dependency counter can
     if (d->inject_barrier_fault) {     // counters start at 0x80000000: no barrier of this segment can complete
         d->inject_barrier_fault = false;
         for (int ph : {sg.ph0, sg.split})
@@ -478,7 +478,7 @@ int32_t launch_tree(madipm_handle* h, const DeviceState::TreeSeg& sg) {
         if (sg.split <= sg.ph0 || sg.grid[OP] <= 0) return MADIPM_OK;
         int b = reverse ? sg.split - 1 : sg.ph0, e = reverse ? sg.ph0 - 1 : sg.split, step = reverse ? -1 : 1;
         T.bar = reinterpret_cast<unsigned*>(tickets + kSyncStride * sg.ph0 + kSyncBar);
-        if (d->dataflow && d->dataflow_ok) {             // dependency counters instead of height barriers (kernels_tree.cuh, DfView)
+        if (d->dataflow && d->dataflow_ok && (OP == 0 || OP == 3 || sg.df_sweeps)) {   // dependency counters instead of height barriers (kernels_tree.cuh, DfView)
             DfView D{d->dep, d->task_parent, d->ntasks, d->phase_ptr[sg.split]};
             CUDA_OK(h, cudaMemsetAsync(d->dep, df_fault ? 0x80 : 0, sizeof(int) * static_cast<size_t>(d->B) * d->ntasks, d->stream));
             const int grid = std::min(sg.grid[OP], d->tree_occ_df[OP] * d->num_sms);
@@ -881,6 +881,13 @@ int32_t device_create(madipm_handle* h) {
                 for (int op = 0; op < 4; ++op)
                     sg.grid[op] = static_cast<int>(std::min<int64_t>(need, static_cast<int64_t>(d->tree_occ[op]) * d->num_sms));
                 sg.grid_top = static_cast<int>(std::min<int64_t>(need_top, d->num_sms));
+                // Dataflow for the triangular sweeps only where some height of the launch is short of tasks (its barrier then
+                // costs the latency of a front): with >= 4 tasks per block at EVERY height the sweeps are throughput-bound and
+                // the per-task signalling costs more than the barriers (measured: C5 with 4096 instances 0.86 -> 0.97 ms per
+                // solve, with 1024 instances 0.31 -> 0.29 ms, C3 0.70 -> 0.65 ms).  The factorisation gains in every case.
+                int64_t min_tasks = INT64_MAX;
+                for (int q = sg.ph0; q < sg.split; ++q) min_tasks = std::min(min_tasks, ntasks(q));
+                sg.df_sweeps = min_tasks < 4 * static_cast<int64_t>(std::max(1, sg.grid[1]));
                 d->segs.push_back(sg);
                 l0 = l + 1;
             }
@@ -888,7 +895,8 @@ int32_t device_create(madipm_handle* h) {
         // dataflow scheduling needs the whole small tree below the split in ONE launch that starts at the leaves
         d->dataflow_ok = s.n_big == 0 && !split && d->segs.size() == 1 && d->segs[0].ph0 == 0 && d->ntasks > 0;
         for (int op = 0; op < 4; ++op) d->dataflow_ok = d->dataflow_ok && d->tree_occ_df[op] >= 1;
-        if (const char* e = std::getenv("MADIPM_TREE_DATAFLOW")) d->dataflow = e[0] == '1';
+        d->dataflow = true;                               // (measured faster on C3 and on C5 shards; bit-identical results)
+        if (const char* e = std::getenv("MADIPM_TREE_DATAFLOW")) d->dataflow = e[0] != '0';
         d->tri_cap = std::min(s.max_w * s.max_w, 4096);
         d->smem_tri = (static_cast<size_t>(d->tri_cap) + 256) * sizeof(double);
     }

@@ -33,6 +33,7 @@ def test_broken_grid_barrier_is_an_error_not_a_hang(where, monkeypatch):
     s = _factor_ready(P.banded_qp(seed=1, n=40000, m=20000))     # several heights -> the launches have barriers
     h = s.h
     assert h.info()["n_levels"] > 3
+    h.set_tree_dataflow(False)                                    # the barrier schedule (the dataflow one has its own test below)
     assert h.factorize() == 0
     good = h.inertia()
     assert h.debug_barrier_state()["aborted"] == 0
@@ -132,6 +133,7 @@ def test_dataflow_schedule_is_bit_identical_to_the_barrier_schedule(maker, kw, o
     """Same tasks, same summation order: whole solves agree bit for bit wherever the dataflow launches are in effect."""
     qp = maker(**kw)
     ref = MPCSolver(qp, regularization=FixedRegularization(1e-8, -1e-8), **opts)
+    ref.h.set_tree_dataflow(False)
     a = ref.solve()
     ref.close()
     s = MPCSolver(qp, regularization=FixedRegularization(1e-8, -1e-8), **opts)
