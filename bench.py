@@ -445,7 +445,7 @@ def run_ours(args):
         alg_bytes = (16.0 * (info["nnz_stored"] + c_doubles) + 16.0 * (info["kkt_order"] + cv_doubles)) * B
         sub_avg_s = (sub_ms / max(sub_calls, 1)) / 1e3
         achieved = alg_bytes / sub_avg_s / 1e9 if sub_avg_s > 0 else 0.0
-        roofline = dict(bound="hbm", kernel="k_tree<3> + k_tree_top<3> (numeric factorisation of the small supernodes with the predictor's forward sweep fused in)", achieved=achieved, peak=hbm_peak, unit="GB/s",
+        roofline = dict(bound="hbm", kernel="k_tree_df<3> + k_front<3> (numeric factorisation of the small supernodes with the predictor's forward sweep fused in; dataflow-scheduled heights 0-9 + one front per SM above)", achieved=achieved, peak=hbm_peak, unit="GB/s",
                         frac=achieved / hbm_peak, traffic=None, peak_source=peak_src,
                         algorithmic_bytes_per_launch=alg_bytes, avg_launch_ms=sub_avg_s * 1e3, launches=sub_calls,
                         share_of_step=sub_ms / 1e3 / res["sec"] if res["sec"] > 0 else None,
