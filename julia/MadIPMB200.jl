@@ -723,6 +723,14 @@ function standard_form_arrays(nvar, ncon, jac_I::Vector{Int32}, jac_J::Vector{In
             c = oc[1:nv], lvar = olv[1:nv], uvar = ouv[1:nv], x0 = ox0[1:nv], lcon = olc[1:nc], ucon = ouc[1:nc], y0 = oy0[1:nc])
 end
 
+# ---- scheduling of the small-front tree kernels (no reference counterpart) --------------------------------------------------
+"Dataflow schedule (per-task dependency counters, default) or height barriers; returns whether dataflow is in effect."
+function set_tree_dataflow!(h::Handle, on::Bool)
+    eff = Ref{Int32}(0)
+    check(h, ccall((:madipm_set_tree_dataflow, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}), h.ptr, Int32(on), eff))
+    return eff[] != 0
+end
+
 # ---- hang guards (see the header) -----------------------------------------------------------------------------------------
 function barrier_state(h::Handle)
     out = Vector{Int64}(undef, 8)
