@@ -193,6 +193,62 @@ def test_schedule_covers_every_supernode_once():
     assert sum(used) == len(task) and used[3] > 0 and sum(used[:3]) > 0      # warp tasks and multi-warp tasks both occur
 
 
+@pytest.mark.parametrize("maker,kw,cfg", [
+    (P.banded_qp, dict(n=6000, m=3000), dict(nd_leaf=100)),
+    (P.banded_qp, dict(seed=3, n=20000, m=10000), dict()),
+    (P.small_qp, dict(instance=0), dict()),
+    (P.maros_meszaros_like, dict(seed=0, n=200, m=100, nnz=800), dict(ordering=_lib.ORDER_AMD)),
+])
+def test_ticket_order_is_a_dependency_order_for_the_dataflow_kernels(maker, kw, cfg):
+    """k_tree_df (kernels_tree.cuh) hands out tickets in TASK_SN order (reversed by height for the backward sweep) and lets a
+    ticket holder spin until its children (its parent) have signalled.  That cannot deadlock iff everything a task waits for
+    has a smaller ticket: checked here on the host, together with the counts the kernel compares the counters against, by
+    playing the schedule with a bounded number of groups and random task durations."""
+    h, _ = analyze_handle(maker(**kw), "K2", **cfg)
+    level, parent = h.symbolic("SUPER_LEVEL"), h.symbolic("SUPER_PARENT")
+    cptr, cidx = h.symbolic("CHILD_PTR"), h.symbolic("CHILD_IDX")
+    task, pptr = h.symbolic("TASK_SN"), h.symbolic("PHASE_PTR")
+    nsuper = len(parent)
+    task_of = np.full(nsuper, -1)
+    task_of[task] = np.arange(len(task))
+    small = task_of >= 0
+    for s_ in range(nsuper):                                   # the child lists and the parent array say the same thing
+        assert (parent[cidx[cptr[s_]:cptr[s_ + 1]]] == s_).all()
+    assert np.array_equal(np.bincount(parent[parent >= 0], minlength=nsuper), np.diff(cptr))
+    # forward (factor, forward sweep): children before parents
+    kids_small = np.array([small[cidx[cptr[s_]:cptr[s_ + 1]]].all() for s_ in task])
+    for q, s_ in enumerate(task):
+        kids = cidx[cptr[s_]:cptr[s_ + 1]]
+        if kids_small[q]:
+            assert (task_of[kids] < q).all() and (level[kids] < level[s_]).all()
+    # backward sweep: heights descending, so a parent's phase comes first
+    order_bwd = np.concatenate([np.arange(pptr[k], pptr[k + 1]) for k in range(len(pptr) - 2, -1, -1)]) if len(task) else task
+    pos_bwd = np.empty(len(task), dtype=np.int64)
+    pos_bwd[order_bwd] = np.arange(len(task))
+    for q, s_ in enumerate(task):
+        if parent[s_] >= 0 and small[parent[s_]]:
+            assert pos_bwd[task_of[parent[s_]]] < pos_bwd[q]
+    if not kids_small.all():
+        return                                                 # multi-block fronts: the dataflow launches are not used
+    # play the forward schedule: G groups, tickets in order, a holder waits for its counter; must finish for any durations
+    rng = np.random.default_rng(0)
+    for G in (1, 3, 64):
+        dur = rng.integers(1, 20, len(task))
+        counter = np.zeros(len(task), dtype=np.int64)
+        need = np.diff(cptr)[task]
+        free_at = np.zeros(G, dtype=np.int64)                  # when each group takes its next ticket
+        done_at = np.zeros(len(task), dtype=np.int64)
+        for q, s_ in enumerate(task):                          # ticket q goes to the group that asks first
+            g = int(np.argmin(free_at))
+            kids = task_of[cidx[cptr[s_]:cptr[s_ + 1]]]
+            ready = max([free_at[g]] + [done_at[k] for k in kids])         # every child already HAS a finishing time: no cycle
+            done_at[q] = ready + dur[q]
+            free_at[g] = done_at[q]
+            if parent[s_] >= 0:
+                counter[task_of[parent[s_]]] += 1
+        assert np.array_equal(counter, need)                   # the value k_tree_df waits for (m.c1 - m.c0)
+
+
 def _multifrontal_emulation(h, K):
     """numpy restatement of the data flow of kernels_tree.cuh (pull of packed contribution blocks through
     PAR_POS / SUPER_COFF) on the dense permuted matrix K; returns (L, d) with K = L diag(d) L'."""
