@@ -222,7 +222,7 @@ int32_t madipm_set_pivot_checks(madipm_handle* h, double tiny, double growth);
  * tree; 1: dataflow -- every task waits for its own children (parent in the backward sweep) through per-task counters in
  * global memory, no barrier between heights.  Same tasks, same arithmetic, bit-identical results.  Only for workloads whose
  * fronts all fit one block (no multi-block fronts); *in_effect (may be NULL) says whether the launches will use it.
- * The triangular sweeps keep the barriers where every height of the launch has at least four tasks per block (large
+ * The triangular sweeps keep the barriers where every height of the launch has at least two tasks per block (large
  * batches: throughput-bound, the per-task signalling would cost more than the barriers).
  * Default: on; environment variable MADIPM_TREE_DATAFLOW=0 switches it off. */
 int32_t madipm_set_tree_dataflow(madipm_handle* h, int32_t on, int32_t* in_effect);

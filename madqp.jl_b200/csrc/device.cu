@@ -882,12 +882,13 @@ int32_t device_create(madipm_handle* h) {
                     sg.grid[op] = static_cast<int>(std::min<int64_t>(need, static_cast<int64_t>(d->tree_occ[op]) * d->num_sms));
                 sg.grid_top = static_cast<int>(std::min<int64_t>(need_top, d->num_sms));
                 // Dataflow for the triangular sweeps only where some height of the launch is short of tasks (its barrier then
-                // costs the latency of a front): with >= 4 tasks per block at EVERY height the sweeps are throughput-bound and
+                // costs the latency of a front): with >= 2 tasks per block at EVERY height the sweeps are throughput-bound and
                 // the per-task signalling costs more than the barriers (measured: C5 with 4096 instances 0.86 -> 0.97 ms per
-                // solve, with 1024 instances 0.31 -> 0.29 ms, C3 0.70 -> 0.65 ms).  The factorisation gains in every case.
+                // solve, with 1024 instances 0.31 -> 0.29 ms, C3 0.70 -> 0.65 ms; 2048 instances were not measured and stay with the
+                // barriers: the threshold sits just above the 1024-instance case on 592 blocks).  The factorisation gains in every case.
                 int64_t min_tasks = INT64_MAX;
                 for (int q = sg.ph0; q < sg.split; ++q) min_tasks = std::min(min_tasks, ntasks(q));
-                sg.df_sweeps = min_tasks < 4 * static_cast<int64_t>(std::max(1, sg.grid[1]));
+                sg.df_sweeps = min_tasks < 2 * static_cast<int64_t>(std::max(1, sg.grid[1]));
                 d->segs.push_back(sg);
                 l0 = l + 1;
             }
