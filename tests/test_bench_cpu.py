@@ -39,3 +39,14 @@ def test_gpu_arm_without_a_gpu_fails_loudly():
     d = json.loads(lines[0])
     assert d["value"] is None and "error" in d and len(d["failed_attempts"]) == 2
     assert "no CUDA device" in out.stderr or "no CPU fallback" in out.stderr
+
+
+def test_kernels_named_in_the_roofline_are_in_the_shipped_library():
+    """bench.py names the dominant kernel pair in `roofline.kernel`; those entry points must exist in the .so that travels."""
+    import re
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    names = set(re.findall(r"\b(k_[a-z_]+)(?:<\d>)?", " ".join(re.findall(r'kernel="([^"]+)"', src))))
+    assert {"k_tree_df", "k_front", "k_big_update"} <= names, names
+    blob = open(os.path.join(ROOT, "madqp.jl_b200", "libmadipm_b200.so"), "rb").read()
+    for n in names:
+        assert re.search(rb"_ZN6madipm\d+" + n.encode() + rb"(I|E)", blob), n      # mangled madipm::<kernel>
